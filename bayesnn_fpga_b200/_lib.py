@@ -1,0 +1,123 @@
+"""ctypes binding of the C-ABI library (include/bnn_b200.h) and its in-tree build.
+
+There is no CPU fallback anywhere in this package: if ``libbnn_b200.so`` is missing or the
+device is not sm_100 every compute call raises.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libbnn_b200.so")
+SOURCES = ["kernels_simt.cu", "kernels_head.cu", "conv_tc.cu"]
+HEADERS = ["common.cuh", "philox.cuh", "../../include/bnn_b200.h"]
+
+F32, F16, BF16 = 0, 1, 2
+DROP_NONE, DROP_ELEMENT, DROP_CHANNEL, DROP_MASKSEMBLES = 0, 1, 2, 3
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+
+class DropDesc(ctypes.Structure):
+    """struct bnn_drop_desc"""
+    _fields_ = [("kind", ctypes.c_int), ("p", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("stream_id", ctypes.c_uint32), ("sample0", ctypes.c_uint32), ("batch", ctypes.c_int),
+                ("masks", ctypes.c_void_p), ("n_masks", ctypes.c_int), ("cnt0", ctypes.c_int)]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into csrc/libbnn_b200.so (nvcc cross-compiles
+    without a GPU).  Returns the library path."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [nvcc] + NVCC_FLAGS + srcs + ["-o", LIB_PATH]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB_PATH
+
+
+_SIGS = {
+    "bnn_version": (ctypes.c_int, []),
+    "bnn_last_error": (ctypes.c_char_p, []),
+    "bnn_device_check": (ctypes.c_int, []),
+    "bnn_sm_count": (ctypes.c_int, []),
+    "bnn_philox_words": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.c_void_p]),
+    "bnn_philox_keep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64,
+                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
+    "bnn_nchw_to_nhwc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "bnn_conv2d_simt": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 11 +
+                        [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_conv2d_tc": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
+                      [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_maxpool2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "bnn_exit_head": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p,
+                                                                              ctypes.POINTER(DropDesc)] +
+                      [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]),
+    "bnn_finalize": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 8),
+    "bnn_calibration_bins": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """dlopen the library and declare every signature of include/bnn_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "bayesnn_fpga_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)       # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class BnnError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().bnn_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise BnnError("bnn_b200 error %d: %s" % (rc, msg))
+
+
+def require_device():
+    """Raise unless the current CUDA device is a B200-class (sm_100) part."""
+    check(load().bnn_device_check())

@@ -1,0 +1,256 @@
+// Exit-head and statistics kernels (sm_100a, CUDA cores; HBM/L2-bound, no tensor-core shape here:
+// the FC is F x C with C = 10..100 per image).
+//
+//   exit_head_kernel : global average pool -> stochastic site -> Linear(F, C) -> softmax ->
+//                      warp-shuffle accumulation over the local MC samples.  One CTA per image;
+//                      all samples of that image are processed by the same CTA so the classifier
+//                      weights are read once per image and the running sums never leave the SM.
+//   finalize_kernel  : means, cumulative exit ensembles, entropies.
+//   calibration_kernel: top-label confidence / correctness + equal-width bins.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace bnn {
+
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_WARPS = HEAD_THREADS / 32;
+constexpr int HEAD_SCHUNK = 16;  // samples staged in shared memory at a time
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// dynamic shared memory layout: pooled[HEAD_SCHUNK][F] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] | red[HEAD_WARPS]
+template <typename T>
+__global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
+    const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+    const float* __restrict__ w, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
+    float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate) {
+  extern __shared__ float sm[];
+  float* pooled = sm;
+  float* logits = pooled + (size_t)HEAD_SCHUNK * F;
+  float* acc_p = logits + (size_t)HEAD_SCHUNK * C;
+  float* acc_l = acc_p + C;
+  float* red = acc_l + C;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv_hw = 1.f / (float)HW;
+
+  for (int c = tid; c < C; c += HEAD_THREADS) {
+    acc_p[c] = 0.f;
+    acc_l[c] = 0.f;
+  }
+  float plogp_acc = 0.f;  // meaningful on lane 0 of each warp
+
+  for (int s0 = 0; s0 < S_local; s0 += HEAD_SCHUNK) {
+    const int ns = min(HEAD_SCHUNK, S_local - s0);
+    __syncthreads();
+    // ---- phase 1: pooled + masked feature vectors for ns samples -----------------------------
+    for (int idx = tid; idx < ns * F; idx += HEAD_THREADS) {
+      const int sl = idx / F, f = idx - sl * F;
+      const int s = s0 + sl;
+      const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f;
+      float a = 0.f;
+      for (int p = 0; p < HW; ++p) a += to_f32<T>(src[(size_t)p * F]);
+      a *= inv_hw;
+      if (dp.kind != BNN_DROP_NONE)
+        a *= drop_factor(dp, (uint32_t)s, (uint64_t)b * F + f, (uint64_t)b * F + f, f);
+      pooled[sl * F + f] = a;
+    }
+    __syncthreads();
+    // ---- phase 2: logits[s][c] = bias[c] + <w[c,:], pooled[s,:]>; one warp per class ---------
+    for (int c = warp; c < C; c += HEAD_WARPS) {
+      const float* wr = w + (size_t)c * F;
+      for (int sl = 0; sl < ns; ++sl) {
+        float a = 0.f;
+        for (int f = lane; f < F; f += 32) a = fmaf(__ldg(wr + f), pooled[sl * F + f], a);
+        a = warp_sum(a);
+        if (lane == 0) logits[sl * C + c] = a + __ldg(bias + c);
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: softmax per sample (one warp per sample), accumulate ---------------------
+    for (int sl = warp; sl < ns; sl += HEAD_WARPS) {
+      const float* lg = logits + sl * C;
+      float mx = -INFINITY;
+      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
+      mx = warp_max(mx);
+      float den = 0.f;
+      for (int c = lane; c < C; c += 32) den += expf(lg[c] - mx);
+      den = warp_sum(den);
+      const float inv = 1.f / den, logden = logf(den);
+      float pl = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float z = lg[c] - mx;
+        const float p = expf(z) * inv;
+        pl += p * (z - logden);
+        atomicAdd(&acc_p[c], p);        // shared-memory atomics, <= 8 warps contending
+        atomicAdd(&acc_l[c], lg[c]);
+        if (logits_out) logits_out[((size_t)(s0 + sl) * B + b) * C + c] = lg[c];
+      }
+      pl = warp_sum(pl);
+      plogp_acc += pl;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = plogp_acc;
+  __syncthreads();
+  for (int c = tid; c < C; c += HEAD_THREADS) {
+    const size_t o = (size_t)b * C + c;
+    sum_p[o] = (accumulate ? sum_p[o] : 0.f) + acc_p[c];
+    sum_logit[o] = (accumulate ? sum_logit[o] : 0.f) + acc_l[c];
+  }
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < HEAD_WARPS; ++i) t += red[i];
+    sum_plogp[b] = (accumulate ? sum_plogp[b] : 0.f) + t;
+  }
+}
+
+// one thread per (image, class): means and cumulative exit ensembles
+__global__ void finalize_means_kernel(const float* __restrict__ sum_p, const float* __restrict__ sum_logit, int E,
+                                      int B, int C, float inv_s, float* __restrict__ mean_p,
+                                      float* __restrict__ mean_logit, float* __restrict__ ens_p,
+                                      float* __restrict__ ens_logit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over B*C
+  if (i >= B * C) return;
+  float run_p = 0.f, run_l = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const size_t o = (size_t)e * B * C + i;
+    const float mp = sum_p[o] * inv_s, ml = sum_logit[o] * inv_s;
+    mean_p[o] = mp;
+    mean_logit[o] = ml;
+    run_p += mp;
+    run_l += ml;
+    ens_p[o] = run_p / (float)(e + 1);
+    ens_logit[o] = run_l / (float)(e + 1);
+  }
+}
+
+// one thread per (exit, image): entropy of the mean, -sum_c p log(p + 1e-8) (metric_utils.py:5)
+__global__ void finalize_entropy_kernel(const float* __restrict__ mean_p, const float* __restrict__ ens_p,
+                                        const float* __restrict__ sum_plogp, int EB, int C, float inv_s,
+                                        float* __restrict__ entropy, float* __restrict__ ens_entropy,
+                                        float* __restrict__ exp_entropy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over E*B
+  if (i >= EB) return;
+  const float* p = mean_p + (size_t)i * C;
+  const float* q = ens_p + (size_t)i * C;
+  float h = 0.f, he = 0.f;
+  for (int c = 0; c < C; ++c) {
+    h -= p[c] * logf(p[c] + 1e-8f);
+    he -= q[c] * logf(q[c] + 1e-8f);
+  }
+  entropy[i] = h;
+  ens_entropy[i] = he;
+  exp_entropy[i] = -sum_plogp[i] * inv_s;
+}
+
+__global__ void calibration_kernel(const float* __restrict__ probs, const int32_t* __restrict__ labels, int N, int C,
+                                   int n_bins, float* __restrict__ conf, int32_t* __restrict__ correct,
+                                   float* __restrict__ bin_stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* p = probs + (size_t)i * C;
+  int best = 0;
+  float bp = p[0];
+  for (int c = 1; c < C; ++c)
+    if (p[c] > bp) {   // first maximum wins, like np.argmax
+      bp = p[c];
+      best = c;
+    }
+  const int hit = best == labels[i];
+  conf[i] = bp;
+  correct[i] = hit;
+  int bin = (int)ceilf(bp * (float)n_bins) - 1;
+  bin = max(0, min(n_bins - 1, bin));
+  atomicAdd(&bin_stats[bin * 3 + 0], 1.f);
+  atomicAdd(&bin_stats[bin * 3 + 1], bp);
+  atomicAdd(&bin_stats[bin * 3 + 2], (float)hit);
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" {
+
+int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                  const float* w, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                  float* sum_plogp, float* logits_out, int accumulate, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(feat && w && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
+  BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && C > 0, "bnn_exit_head: bad geometry");
+  if (drop && drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
+                drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_exit_head: Masksembles site without a mask table");
+  }
+  if (B == 0) return BNN_OK;
+  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_SCHUNK * C + 2 * (size_t)C + HEAD_WARPS) * sizeof(float);
+  BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);
+  DropParams dp = make_drop_params(drop, F);
+  dp.batch = B;
+  cudaStream_t st = (cudaStream_t)stream;
+#define BNN_HEAD_LAUNCH(T)                                                                                         \
+  do {                                                                                                             \
+    BNN_CUDA_OK(cudaFuncSetAttribute(exit_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    exit_head_kernel<T><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, C, w,  \
+                                                       bias, dp, sum_p, sum_logit, sum_plogp, logits_out,          \
+                                                       accumulate);                                                \
+  } while (0)
+  switch (dtype) {
+    case BNN_F32: BNN_HEAD_LAUNCH(float); break;
+    case BNN_F16: BNN_HEAD_LAUNCH(__half); break;
+    case BNN_BF16: BNN_HEAD_LAUNCH(__nv_bfloat16); break;
+    default: set_error("unknown dtype code %d", dtype); return BNN_E_ARG;
+  }
+#undef BNN_HEAD_LAUNCH
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+int bnn_finalize(const float* sum_p, const float* sum_logit, const float* sum_plogp, int E, int B, int C,
+                 int S_total, float* mean_p, float* mean_logit, float* ens_p, float* ens_logit, float* entropy,
+                 float* ens_entropy, float* exp_entropy, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(sum_p && sum_logit && sum_plogp && mean_p && mean_logit && ens_p && ens_logit && entropy &&
+                  ens_entropy && exp_entropy,
+              "bnn_finalize: null pointer");
+  BNN_REQUIRE(E > 0 && B >= 0 && C > 0 && S_total > 0, "bnn_finalize: bad geometry");
+  if (B == 0) return BNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int total = B * C;
+  const float inv_s = 1.f / (float)S_total;
+  finalize_means_kernel<<<(total + 127) / 128, 128, 0, st>>>(sum_p, sum_logit, E, B, C, inv_s, mean_p, mean_logit,
+                                                             ens_p, ens_logit);
+  BNN_LAUNCH_OK();
+  finalize_entropy_kernel<<<(E * B + 127) / 128, 128, 0, st>>>(mean_p, ens_p, sum_plogp, E * B, C, inv_s, entropy,
+                                                               ens_entropy, exp_entropy);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C, int n_bins, float* conf,
+                         int32_t* correct, float* bin_stats, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(probs && labels && conf && correct && bin_stats && N >= 0 && C > 0 && n_bins > 0,
+              "bnn_calibration_bins: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  BNN_CUDA_OK(cudaMemsetAsync(bin_stats, 0, sizeof(float) * 3 * n_bins, st));
+  if (N == 0) return BNN_OK;
+  calibration_kernel<<<(N + 127) / 128, 128, 0, st>>>(probs, labels, N, C, n_bins, conf, correct, bin_stats);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+}  // extern "C"

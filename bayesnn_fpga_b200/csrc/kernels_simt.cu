@@ -1,0 +1,422 @@
+// CUDA-core kernels of the MC-dropout / Masksembles inference path (sm_100a):
+//   - error / device plumbing for the C ABI
+//   - Philox test hooks
+//   - NCHW -> NHWC input repack
+//   - exact fp32 implicit-GEMM convolution with fused bias / residual / ReLU / dropout (FP32 parity
+//     path + the layers the tensor-core kernel does not take: Cin % 64 != 0, 5x5, ...)
+//   - stand-alone stochastic layer with prefix -> S-sample broadcast (HBM-bound)
+//   - max-pool
+// The exit-head / statistics kernels live in kernels_head.cu, the tcgen05 convolution in conv_tc.cu.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace bnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_dev_checked = -1000;  // cached result per process (device is fixed per process: one process per GPU)
+static int g_sms = 0;
+
+int check_device() {
+  if (g_dev_checked != -1000) return g_dev_checked;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    cudaGetLastError();
+    return BNN_E_CUDA;  // not cached: a device may appear later
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return BNN_E_CUDA;
+  }
+  g_sms = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    set_error("device '%s' is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.name,
+              prop.major, prop.minor);
+    g_dev_checked = BNN_E_ARCH;
+    return g_dev_checked;
+  }
+  g_dev_checked = BNN_OK;
+  return BNN_OK;
+}
+
+int sm_count() {
+  if (check_device() != BNN_OK) return 0;
+  return g_sms;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox test hooks
+// ------------------------------------------------------------------------------------------
+__global__ void philox_words_kernel(uint32_t* out, int64_t count, uint64_t seed, uint32_t stream_id,
+                                    uint32_t sample) {
+  const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk * 4 >= count) return;
+  const uint4 r = philox_block(seed, stream_id, sample, (uint64_t)blk);
+  const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+  for (int i = 0; i < 4; ++i)
+    if (blk * 4 + i < count) out[blk * 4 + i] = v[i];
+}
+
+__global__ void philox_keep_kernel(uint8_t* out, int64_t count, uint32_t thr, int all_dropped, uint64_t seed,
+                                   uint32_t stream_id, uint32_t sample) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  const uint32_t w = philox_word(seed, stream_id, sample, (uint64_t)e);
+  out[e] = (!all_dropped && w >= thr) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC T
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW, int64_t total) {
+  // one thread per output element; reads are strided by HW but the inputs are small (3 x 32 x 32 images)
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t t = i / C;
+  const int hw = (int)(t % HW);
+  const int64_t n = t / HW;
+  y[i] = from_f32<T>(x[(n * C + c) * HW + hw]);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 implicit-GEMM convolution on CUDA cores
+//   M = N*OH*OW output pixels, Ncols = Cout, K = KH*KW*Cin ((kh, kw, ci) order = NHWC patches)
+//   64 x 64 output tile per CTA, 256 threads, 4 x 4 outputs per thread, K staged 16 at a time.
+// ------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int N, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW, relu;
+};
+
+constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv2d_simt_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias,
+                                                          const T* __restrict__ res, T* __restrict__ y,
+                                                          ConvGeom g, DropParams dp) {
+  __shared__ float As[SIMT_BK][SIMT_BM + 4];
+  __shared__ float Bs[SIMT_BK][SIMT_BN + 4];
+
+  const int K = g.KH * g.KW * g.Cin;
+  const int64_t M = (int64_t)g.N * g.OH * g.OW;
+  const int64_t m0 = (int64_t)blockIdx.x * SIMT_BM;
+  const int n0 = blockIdx.y * SIMT_BN;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // tx -> 4 couts, ty -> 4 pixels
+
+  // loader mapping: each thread fetches 4 consecutive k for one row of A and one row of B
+  const int lrow = tid / 4;          // 0..63
+  const int lk = (tid % 4) * 4;      // 0,4,8,12
+  const int64_t am = m0 + lrow;
+  int a_n = 0, a_oh = 0, a_ow = 0;
+  const bool a_valid = am < M;
+  if (a_valid) {
+    a_ow = (int)(am % g.OW);
+    const int64_t t = am / g.OW;
+    a_oh = (int)(t % g.OH);
+    a_n = (int)(t / g.OH);
+  }
+  const int bn = n0 + lrow;
+  const bool b_valid = bn < g.Cout;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SIMT_BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + lk + j;
+      float av = 0.f, bv = 0.f;
+      if (k < K) {
+        const int tap = k / g.Cin, ci = k - tap * g.Cin;
+        const int kh = tap / g.KW, kw = tap - kh * g.KW;
+        const int ih = a_oh * g.stride - g.pad + kh, iw = a_ow * g.stride - g.pad + kw;
+        if (a_valid && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+          av = to_f32<T>(x[(((int64_t)a_n * g.H + ih) * g.W + iw) * g.Cin + ci]);
+        if (b_valid) bv = __ldg(w + (int64_t)bn * K + k);
+      }
+      As[lk + j][lrow] = av;
+      Bs[lk + j][lrow] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SIMT_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue: + bias (folded BN) [+ residual] [ReLU] [stochastic site] -> store
+  const int64_t ohw = (int64_t)g.OH * g.OW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int64_t img = m / ohw;                      // image index incl. the sample dimension
+    const uint32_t s_local = (uint32_t)(img / dp.batch);
+    const int64_t b = img % dp.batch;
+    const int64_t pix = m - img * ohw;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= g.Cout) continue;
+      float v = acc[i][j] + __ldg(bias + c);
+      if (res != nullptr) v += to_f32<T>(res[m * g.Cout + c]);
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (dp.kind != BNN_DROP_NONE) {
+        const uint64_t e_elem = (uint64_t)((b * ohw + pix) * g.Cout + c);
+        const uint64_t e_chan = (uint64_t)(b * g.Cout + c);
+        v *= drop_factor(dp, s_local, e_elem, e_chan, c);
+      }
+      y[m * g.Cout + c] = from_f32<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone stochastic layer, with prefix -> S-sample broadcast
+//   y[s][i] = x[(x_has_samples ? s : 0)][i] * factor(s, i),  i in [0, n_per) = B*H*W*C (one sample)
+// HBM-bound: algorithmic bytes = (x_has_samples ? S : 1) * n_per * sizeof(T) read + S * n_per * sizeof(T)
+// written.  Each thread owns 8 consecutive elements (two Philox blocks, 16-byte accesses for 16-bit T)
+// and loops over the samples so the broadcast source is read from HBM once.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct __align__(16) Vec8 {
+  T v[8];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n_per,
+                                                      int64_t per_image, int C, int S_local, int x_has_samples,
+                                                      DropParams dp) {
+  const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (v0 >= n_per) return;
+  // vector path: the 8 elements exist, every sample slab stays 16-byte aligned, and (for the per-channel
+  // kinds) the 8 elements sit inside one pixel's channel run
+  const bool vec = (v0 + 8 <= n_per) && (n_per % 8 == 0) && (dp.kind == BNN_DROP_ELEMENT || C % 8 == 0);
+  const int c0 = (int)(v0 % C);
+  const int64_t b0 = v0 / per_image;
+
+  Vec8<T> in;
+  if (vec && !x_has_samples) in = *reinterpret_cast<const Vec8<T>*>(x + v0);   // broadcast source: read once
+
+  for (int s = 0; s < S_local; ++s) {
+    const T* xs = x + (x_has_samples ? (int64_t)s * n_per : 0);
+    T* ys = y + (int64_t)s * n_per;
+    if (vec) {
+      if (x_has_samples) in = *reinterpret_cast<const Vec8<T>*>(xs + v0);
+      float f[8];
+      if (dp.kind == BNN_DROP_ELEMENT) {
+        const uint4 r0 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (uint64_t)(v0 >> 2));
+        const uint4 r1 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (uint64_t)(v0 >> 2) + 1);
+        const uint32_t wd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && wd[j] >= dp.thr) ? dp.scale : 0.f;
+      } else if (dp.kind == BNN_DROP_MASKSEMBLES) {
+        const int row = (int)(((int64_t)dp.cnt0 + dp.sample0 + s) % dp.n_masks);
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(dp.masks + (size_t)row * C + c0));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(dp.masks + (size_t)row * C + c0 + 4));
+        f[0] = m0.x; f[1] = m0.y; f[2] = m0.z; f[3] = m0.w;
+        f[4] = m1.x; f[5] = m1.y; f[6] = m1.z; f[7] = m1.w;
+      } else {  // channel-wise: elements b*C + c0 .. +7 share two Philox blocks (C % 8 == 0)
+        const uint64_t e = (uint64_t)(b0 * C + c0);
+        const uint4 r0 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, e >> 2);
+        const uint4 r1 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (e >> 2) + 1);
+        const uint32_t wd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && wd[j] >= dp.thr) ? dp.scale : 0.f;
+      }
+      Vec8<T> out;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out.v[j] = from_f32<T>(to_f32<T>(in.v[j]) * f[j]);
+      *reinterpret_cast<Vec8<T>*>(ys + v0) = out;
+    } else {
+      for (int j = 0; j < 8 && v0 + j < n_per; ++j) {
+        const int64_t i = v0 + j;
+        const int c = (int)(i % C);
+        const int64_t b = i / per_image;
+        const float f = drop_factor(dp, (uint32_t)s, (uint64_t)i, (uint64_t)(b * C + c), c);
+        ys[i] = from_f32<T>(to_f32<T>(xs[i]) * f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// max-pool k x k stride k, NHWC
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int k, int OH,
+                               int OW, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  int64_t t = i / C;
+  const int ow = (int)(t % OW);
+  t /= OW;
+  const int oh = (int)(t % OH);
+  const int64_t n = t / OH;
+  float m = -INFINITY;
+  for (int a = 0; a < k; ++a)
+    for (int b = 0; b < k; ++b)
+      m = fmaxf(m, to_f32<T>(x[((n * H + oh * k + a) * W + ow * k + b) * C + c]));
+  y[i] = from_f32<T>(m);
+}
+
+template <typename F>
+static int dispatch_dtype(int dtype, F&& f) {
+  switch (dtype) {
+    case BNN_F32: return f((float*)nullptr);
+    case BNN_F16: return f((__half*)nullptr);
+    case BNN_BF16: return f((__nv_bfloat16*)nullptr);
+    default: set_error("unknown dtype code %d", dtype); return BNN_E_ARG;
+  }
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" {
+
+int bnn_version(void) { return 100; }
+const char* bnn_last_error(void) { return g_err; }
+int bnn_device_check(void) { return check_device(); }
+int bnn_sm_count(void) { return sm_count(); }
+
+int bnn_philox_words(uint32_t* out, int64_t count, uint64_t seed, uint32_t stream_id, uint32_t sample,
+                     void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(out != nullptr && count >= 0, "bnn_philox_words: bad arguments");
+  if (count == 0) return BNN_OK;
+  const int64_t blocks = ((count + 3) / 4 + 255) / 256;
+  philox_words_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, count, seed, stream_id, sample);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+int bnn_philox_keep(uint8_t* out, int64_t count, float p, uint64_t seed, uint32_t stream_id, uint32_t sample,
+                    void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(out != nullptr && count >= 0, "bnn_philox_keep: bad arguments");
+  BNN_REQUIRE(p >= 0.f && p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", p);
+  if (count == 0) return BNN_OK;
+  const int64_t blocks = (count + 255) / 256;
+  philox_keep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, count, drop_threshold(p),
+                                                                         p >= 1.f ? 1 : 0, seed, stream_id, sample);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+int bnn_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && y && N >= 0 && C > 0 && H > 0 && W > 0, "bnn_nchw_to_nhwc: bad arguments");
+  const int64_t total = (int64_t)N * C * H * W;
+  if (total == 0) return BNN_OK;
+  return dispatch_dtype(dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    nchw_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, C, H * W,
+                                                                                             total);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  });
+}
+
+int bnn_conv2d_simt(const void* x, const float* w, const float* bias, const void* res, void* y, int dtype, int N,
+                    int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
+                    const bnn_drop_desc* drop, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && w && bias && y, "bnn_conv2d_simt: null pointer");
+  BNN_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0,
+              "bnn_conv2d_simt: bad geometry");
+  ConvGeom g{N, H, W, Cin, Cout, KH, KW, stride, pad, 0, 0, relu};
+  g.OH = (H + 2 * pad - KH) / stride + 1;
+  g.OW = (W + 2 * pad - KW) / stride + 1;
+  BNN_REQUIRE(g.OH > 0 && g.OW > 0, "bnn_conv2d_simt: empty output (%d x %d)", g.OH, g.OW);
+  if (drop && drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->batch > 0 && N % drop->batch == 0, "bnn_conv2d_simt: N=%d not a multiple of batch=%d", N,
+                drop->batch);
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
+                drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_conv2d_simt: Masksembles site without a mask table");
+  }
+  const int64_t M = (int64_t)N * g.OH * g.OW;
+  if (M == 0) return BNN_OK;
+  const DropParams dp = make_drop_params(drop, Cout);
+  dim3 grid((unsigned)((M + SIMT_BM - 1) / SIMT_BM), (unsigned)((Cout + SIMT_BN - 1) / SIMT_BN));
+  return dispatch_dtype(dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    conv2d_simt_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, w, bias, (const T*)res, (T*)y, g, dp);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  });
+}
+
+int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int S_local, int x_has_samples,
+                const bnn_drop_desc* drop, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && y && drop, "bnn_dropout: null pointer");
+  BNN_REQUIRE(per_image > 0 && C > 0 && per_image % C == 0 && S_local >= 0 && drop->batch >= 0,
+              "bnn_dropout: bad geometry");
+  BNN_REQUIRE(drop->kind == BNN_DROP_ELEMENT || drop->kind == BNN_DROP_CHANNEL || drop->kind == BNN_DROP_MASKSEMBLES,
+              "bnn_dropout: unknown kind %d", drop->kind);
+  BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
+              drop->p);
+  BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+              "bnn_dropout: Masksembles site without a mask table");
+  const int64_t n_per = per_image * drop->batch;
+  if (n_per == 0 || S_local == 0) return BNN_OK;
+  const DropParams dp = make_drop_params(drop, C);
+  const int64_t threads = (n_per + 7) / 8;
+  return dispatch_dtype(dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    dropout_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x, (T*)y, n_per, per_image, C, S_local, x_has_samples, dp);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  });
+}
+
+int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C, int k, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && y && N >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H / k > 0 && W / k > 0,
+              "bnn_maxpool2d: bad arguments");
+  const int OH = H / k, OW = W / k;
+  const int64_t total = (int64_t)N * OH * OW * C;
+  if (total == 0) return BNN_OK;
+  return dispatch_dtype(dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    maxpool_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C,
+                                                                                          k, OH, OW, total);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Counter-based mask stream (Philox-4x32-10, Salmon et al. SC'11) and the stochastic-site
+// device functions shared by the stand-alone dropout kernel, the conv epilogues and the exit head.
+//
+// Contract (bit-exact mirror of oracle/philox.py, checked by tests/test_gpu_masks.py):
+//   key = (seed lo, seed hi); counter = (e >> 2 lo, e >> 34, sample, stream); word = out[e & 3]
+//   keep <=> p < 1 && word >= min(rint(p * 2^32), 2^32 - 1)
+// with e the per-sample element index (NHWC order for 4-D activations, b*F + f for 2-D, b*C + c
+// for channel-wise dropout).  Replaces the torch global RNG behind F.dropout (resnet18.py:210).
+#pragma once
+#include "common.cuh"
+
+namespace bnn {
+
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  double t = rint((double)p * 4294967296.0);
+  if (t > 4294967295.0) t = 4294967295.0;
+  if (t < 0.0) t = 0.0;
+  return (uint32_t)t;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// the four words covering elements [4*blk, 4*blk + 3]
+__device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t blk) {
+  return philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), sample, stream),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t e) {
+  const uint4 r = philox_block(seed, stream, sample, e >> 2);
+  const uint32_t l = (uint32_t)e & 3u;
+  return l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w));
+}
+
+// Device-side view of bnn_drop_desc with the derived constants.
+struct DropParams {
+  int kind;
+  uint32_t thr;
+  float scale;      // 1/(1-p), 0 when p >= 1
+  uint64_t seed;
+  uint32_t stream_id, sample0;
+  int batch;
+  const float* masks;
+  int n_masks, cnt0;
+  int channels;     // row length of `masks`
+};
+
+inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
+  DropParams q{};
+  if (d == nullptr || d->kind == BNN_DROP_NONE) {
+    q.kind = BNN_DROP_NONE;
+    q.batch = 1;
+    return q;
+  }
+  q.kind = d->kind;
+  q.thr = drop_threshold(d->p);
+  q.scale = d->p >= 1.0f ? 0.0f : 1.0f / (1.0f - d->p);
+  q.seed = d->seed;
+  q.stream_id = d->stream_id;
+  q.sample0 = d->sample0;
+  q.batch = d->batch > 0 ? d->batch : 1;
+  q.masks = d->masks;
+  q.n_masks = d->n_masks;
+  q.cnt0 = d->cnt0;
+  q.channels = channels;
+  return q;
+}
+
+// multiplier for one element (slow generic path; the vector paths below amortise Philox over 4)
+__device__ __forceinline__ float drop_factor(const DropParams& q, uint32_t sample_local, uint64_t e_elem,
+                                             uint64_t e_chan, int c) {
+  if (q.kind == BNN_DROP_MASKSEMBLES) {
+    const int row = (int)(((int64_t)q.cnt0 + q.sample0 + sample_local) % q.n_masks);
+    return __ldg(q.masks + (size_t)row * q.channels + c);
+  }
+  const uint64_t e = q.kind == BNN_DROP_CHANNEL ? e_chan : e_elem;
+  const uint32_t w = philox_word(q.seed, q.stream_id, q.sample0 + sample_local, e);
+  return (q.scale != 0.f && w >= q.thr) ? q.scale : 0.f;
+}
+
+}  // namespace bnn

@@ -1,0 +1,435 @@
+"""Plan builder and executor of the S-sample multi-exit inference path.
+
+Replaces the reference's sample loop (``FullAnalysis._get_output``,
+Software_Artifact/software/train/results_analyzer.py:236-270: ``for i in range(mc_passes): model(b_x)``
++ per-exit softmax + host-side fp64 means).  What changes:
+
+* the network is described once as a small op graph (:class:`Graph`), built by each model class in
+  the same order its reference ``forward`` executes (so stochastic sites get the same stream ids as
+  the oracle's first-use numbering);
+* ops whose inputs do not depend on a stochastic site form the deterministic PREFIX and run on B
+  images; everything downstream of the first site runs on S_local*B images (sample-major).  This is
+  the reference's own cost model (results_analyzer.py:632-637) turned into the execution plan;
+* eval-mode BatchNorm (and conv bias) is folded into the conv weights at plan time; dropout /
+  Masksembles sites that directly follow a stochastic conv are fused into its epilogue; each exit is
+  one ``bnn_exit_head`` call that pools, masks, applies the classifier, soft-maxes and accumulates
+  the per-exit sums over the samples on the device;
+* samples are addressed by their GLOBAL index in the Philox counters, so a rank that owns samples
+  [s0, s0 + S_local) produces exactly the partial sums of those samples (see distributed.py).
+
+Only the C-ABI library does arithmetic; torch is used for allocation, streams and NCCL.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DTYPES = {"fp32": (_lib.F32, torch.float32), "fp16": (_lib.F16, torch.float16),
+          "bf16": (_lib.BF16, torch.bfloat16)}
+KINDS = {"mc": _lib.DROP_ELEMENT, "mc2d": _lib.DROP_CHANNEL, "mask": _lib.DROP_MASKSEMBLES}
+
+
+# --------------------------------------------------------------------------------------------
+# graph description (host logic, no device needed)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class TensorRef:
+    id: int
+    C: int
+    H: int
+    W: int
+    stoch: bool = False          # carries the sample dimension
+
+
+@dataclass
+class Site:
+    """One stochastic layer. kind: 'mc' (F.dropout), 'mc2d' (F.dropout2d), 'mask' (Masksembles)."""
+    kind: str
+    p: float
+    stream: int
+    name: str
+    module: Optional[object] = None      # Masksembles module (owns `masks` and the rotating `cnt`)
+
+
+@dataclass
+class Op:
+    kind: str                            # conv | site | maxpool | head
+    src: Optional[TensorRef] = None
+    dst: Optional[TensorRef] = None
+    res: Optional[TensorRef] = None
+    weight: Optional[torch.Tensor] = None    # folded, OIHW fp32 (conv) / [C, F] (head)
+    bias: Optional[torch.Tensor] = None
+    ksize: tuple = (1, 1)
+    stride: int = 1
+    pad: int = 0
+    relu: bool = False
+    site: Optional[Site] = None              # conv: fused epilogue site; site/head: the site itself
+    pool_k: int = 1
+    exit_index: int = -1
+    name: str = ""
+
+
+def fold_conv_bn(conv, bn=None):
+    """conv weight/bias with eval-mode BatchNorm folded in:
+    w' = w * g / sqrt(var + eps),  b' = beta + (b - mean) * g / sqrt(var + eps)."""
+    w = conv.weight.detach().double()
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is not None:
+        g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * g.reshape(-1, 1, 1, 1)
+        b = bn.bias.detach().double() + (b - bn.running_mean.detach().double()) * g
+    return w.float().contiguous(), b.float().contiguous()
+
+
+class Graph:
+    """Op graph of one network, in execution order."""
+
+    def __init__(self, in_channels, in_h, in_w):
+        self.tensors: List[TensorRef] = []
+        self.ops: List[Op] = []
+        self.sites: List[Site] = []
+        self.n_exits = 0
+        self.n_classes = None
+        self.input = self._new(in_channels, in_h, in_w, False)
+
+    def _new(self, C, H, W, stoch):
+        t = TensorRef(len(self.tensors), C, H, W, stoch)
+        self.tensors.append(t)
+        return t
+
+    def conv(self, src, conv, bn=None, relu=False, residual=None, name=""):
+        w, b = fold_conv_bn(conv, bn)
+        return self.conv_raw(src, w, b, conv.stride[0], conv.padding[0], relu, residual, name)
+
+    def conv_raw(self, src, w, b, stride, pad, relu=False, residual=None, name=""):
+        cout, cin, kh, kw = w.shape
+        assert cin == src.C, (name, cin, src.C)
+        oh = (src.H + 2 * pad - kh) // stride + 1
+        ow = (src.W + 2 * pad - kw) // stride + 1
+        stoch = src.stoch or (residual is not None and residual.stoch)
+        dst = self._new(cout, oh, ow, stoch)
+        if residual is not None:
+            assert (residual.C, residual.H, residual.W) == (cout, oh, ow)
+        self.ops.append(Op("conv", src, dst, residual, w, b, (kh, kw), stride, pad, relu, name=name))
+        return dst
+
+    def linear(self, src, lin, relu=False, name=""):
+        """nn.Linear over the NCHW-flattened src == a convolution whose kernel covers the whole map."""
+        w = lin.weight.detach().float().reshape(lin.out_features, src.C, src.H, src.W).contiguous()
+        b = lin.bias.detach().float().contiguous() if lin.bias is not None else torch.zeros(lin.out_features)
+        return self.conv_raw(src, w, b, 1, 0, relu, None, name)
+
+    def site(self, src, kind, p=0.5, module=None, name=""):
+        s = Site(kind, float(p), len(self.sites), name, module)
+        self.sites.append(s)
+        dst = self._new(src.C, src.H, src.W, True)
+        self.ops.append(Op("site", src, dst, site=s, name=name))
+        return dst
+
+    def new_site(self, kind, p=0.5, module=None, name=""):
+        """Allocate a stream id for a site that a head will apply itself."""
+        s = Site(kind, float(p), len(self.sites), name, module)
+        self.sites.append(s)
+        return s
+
+    def maxpool(self, src, k, name=""):
+        dst = self._new(src.C, src.H // k, src.W // k, src.stoch)
+        self.ops.append(Op("maxpool", src, dst, pool_k=k, name=name))
+        return dst
+
+    def head(self, src, lin, site=None, name=""):
+        """global average pool -> [site] -> Linear -> softmax -> accumulate (one exit)."""
+        w = lin.weight.detach().float().contiguous()
+        b = lin.bias.detach().float().contiguous()
+        assert w.shape[1] == src.C, (name, w.shape, src.C)
+        if self.n_classes is None:
+            self.n_classes = w.shape[0]
+        assert self.n_classes == w.shape[0]
+        self.ops.append(Op("head", src, None, weight=w, bias=b, site=site, exit_index=self.n_exits, name=name))
+        self.n_exits += 1
+
+    # ---- analysis used by the planner and by the tests -------------------------------------
+    def fuse_sites(self):
+        """Fuse a site into the epilogue of the conv that produces its input when that conv already
+        runs per-sample and nobody else reads the un-masked tensor."""
+        uses = {}
+        for op in self.ops:
+            for t in (op.src, op.res):
+                if t is not None:
+                    uses[t.id] = uses.get(t.id, 0) + 1
+        producer = {op.dst.id: op for op in self.ops if op.dst is not None}
+        out = []
+        for op in self.ops:
+            if op.kind == "site":
+                prod = producer.get(op.src.id)
+                if (prod is not None and prod.kind == "conv" and prod.site is None and op.src.stoch
+                        and uses.get(op.src.id, 0) == 1):
+                    prod.site = op.site
+                    prod.dst = op.dst           # conv now writes the masked tensor
+                    producer[op.dst.id] = prod
+                    continue
+            out.append(op)
+        self.ops = out
+
+    def macs(self):
+        """(prefix MACs, per-sample suffix MACs) per image - the reference's cost model
+        (results_analyzer.py:632-637) evaluated on this graph."""
+        pre = suf = 0
+        for op in self.ops:
+            if op.kind == "conv":
+                m = op.dst.H * op.dst.W * op.dst.C * op.src.C * op.ksize[0] * op.ksize[1]
+            elif op.kind == "head":
+                m = op.weight.shape[0] * op.weight.shape[1]
+                if op.site is not None or op.src.stoch:
+                    suf += m
+                else:
+                    pre += m
+                continue
+            else:
+                continue
+            if op.dst.stoch:
+                suf += m
+            else:
+                pre += m
+        return pre, suf
+
+
+# --------------------------------------------------------------------------------------------
+# executor
+# --------------------------------------------------------------------------------------------
+@dataclass
+class MCResult:
+    mean_probs: torch.Tensor       # [E, B, C]   predictive mean (results_analyzer.py:248)
+    mean_logits: torch.Tensor      # [E, B, C]   (results_analyzer.py:247)
+    ens_probs: torch.Tensor        # [E, B, C]   cumulative exit ensembles (:260-269)
+    ens_logits: torch.Tensor
+    entropy: torch.Tensor          # [E, B]      entropy of the mean (metric_utils.py:3-6, per image)
+    ens_entropy: torch.Tensor
+    expected_entropy: torch.Tensor  # [E, B]     mean over samples of per-sample entropy
+    all_logits: Optional[torch.Tensor] = None   # [S_local, E, B, C] when requested
+    samples: int = 0
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Engine:
+    """Executes a :class:`Graph` on the current CUDA device through the C ABI."""
+
+    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True):
+        if dtype not in DTYPES:
+            raise ValueError("dtype must be one of %s" % sorted(DTYPES))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bayesnn_fpga_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(self.device):
+            _lib.require_device()
+        self.graph = graph
+        if fuse:
+            graph.fuse_sites()
+        self.dtype_name = dtype
+        self.dcode, self.tdtype = DTYPES[dtype]
+        self.use_tc = use_tc and dtype != "fp32"
+        self.launches = 0
+        self._bufs = {}
+        self._prepare_weights()
+
+    # ---- plan-time weight packing -----------------------------------------------------------
+    def _tc_eligible(self, op):
+        kh, kw = op.ksize
+        return (self.use_tc and kh == kw and ((kh == 3 and op.pad == 1) or (kh == 1 and op.pad == 0))
+                and op.stride in (1, 2) and op.src.C % 64 == 0 and op.dst.C % 64 == 0
+                and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0)))
+
+    def _prepare_weights(self):
+        dev = self.device
+        for op in self.graph.ops:
+            if op.kind == "conv":
+                w = op.weight.permute(0, 2, 3, 1).contiguous()       # [Cout][KH][KW][Cin]
+                op.use_tc = self._tc_eligible(op)
+                op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
+                op.d_b = op.bias.to(dev, torch.float32)
+            elif op.kind == "head":
+                op.d_w = op.weight.to(dev, torch.float32)
+                op.d_b = op.bias.to(dev, torch.float32)
+            if op.site is not None and op.site.kind == "mask":
+                op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()
+
+    # ---- buffers ----------------------------------------------------------------------------
+    def _buffers(self, B, S_local, want_logits):
+        key = (B, S_local, want_logits)
+        if key in self._bufs:
+            return self._bufs[key]
+        g, dev = self.graph, self.device
+        acts = {}
+        live = {g.input.id}
+        for op in g.ops:
+            live.update(t.id for t in (op.src, op.dst, op.res) if t is not None)
+        for t in g.tensors:
+            if t.id not in live:
+                continue                      # e.g. the un-masked output of a conv with a fused site
+            n = (S_local if t.stoch else 1) * B
+            acts[t.id] = torch.empty((n, t.H, t.W, t.C), dtype=self.tdtype, device=dev)
+        E, C = g.n_exits, g.n_classes
+        st = {
+            "x": torch.empty((B, g.input.C, g.input.H, g.input.W), dtype=torch.float32, device=dev),
+            "sums": torch.zeros((2 * E * B * C + E * B,), dtype=torch.float32, device=dev),
+            "out": torch.empty((4 * E * B * C + 3 * E * B,), dtype=torch.float32, device=dev),
+            "logits": (torch.empty((E, S_local, B, C), dtype=torch.float32, device=dev) if want_logits else None),
+            "acts": acts,
+        }
+        self._bufs[key] = st
+        return st
+
+    def release_buffers(self):
+        self._bufs.clear()
+
+    # ---- launch helpers ---------------------------------------------------------------------
+    def _drop_desc(self, op_site, d_masks, B, sample0, seed, mask_offset=None):
+        d = _lib.DropDesc()
+        if op_site is None:
+            d.kind = _lib.DROP_NONE
+            d.batch = B
+            return d
+        d.kind = KINDS[op_site.kind]
+        d.p = op_site.p
+        d.seed = seed & 0xFFFFFFFFFFFFFFFF
+        d.stream_id = op_site.stream
+        d.sample0 = sample0
+        d.batch = B
+        if op_site.kind == "mask":
+            d.masks = d_masks.data_ptr()
+            d.n_masks = d_masks.shape[0]
+            # kernel row = (cnt0 + sample0 + s) % n; we want (module.cnt + mask_offset + s) % n
+            off = sample0 if mask_offset is None else mask_offset
+            d.cnt0 = (int(op_site.module.cnt) + off - sample0) % d.n_masks
+        return d
+
+    def sums_views(self, st, B):
+        E, C = self.graph.n_exits, self.graph.n_classes
+        n = E * B * C
+        s = st["sums"]
+        return s[:n].view(E, B, C), s[n:2 * n].view(E, B, C), s[2 * n:].view(E, B)
+
+    def enqueue(self, x, S_local, sample0=0, seed=0x5EED, accumulate=False, want_logits=False, mask_offset=None):
+        """Enqueue the whole pass for local samples [sample0, sample0 + S_local) on the current
+        stream. Returns the buffer set (sums are in st['sums'])."""
+        g, lib = self.graph, self.lib
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (g.input.C, g.input.H, g.input.W):
+            raise ValueError("expected input [B, %d, %d, %d], got %s" % (g.input.C, g.input.H, g.input.W,
+                                                                         tuple(x.shape)))
+        if S_local < 0:
+            raise ValueError("S_local must be >= 0")
+        st = self._buffers(B, S_local, want_logits)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        acts = st["acts"]
+        st["x"].copy_(x, non_blocking=True)
+        if B == 0:
+            return st
+        _lib.check(lib.bnn_nchw_to_nhwc(_ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C,
+                                         g.input.H, g.input.W, stream))
+        self.launches += 1
+        sum_p, sum_l, sum_pl = self.sums_views(st, B)
+        for op in g.ops:
+            if op.kind == "conv":
+                n_img = (S_local if op.dst.stoch else 1) * B
+                if n_img == 0:
+                    continue
+                src = acts[op.src.id]
+                if op.dst.stoch and not op.src.stoch:
+                    raise NotImplementedError("conv %s mixes deterministic input with stochastic residual" % op.name)
+                res = acts[op.res.id] if op.res is not None else None
+                if op.res is not None and op.dst.stoch and not op.res.stoch:
+                    raise NotImplementedError("conv %s: deterministic residual into stochastic output" % op.name)
+                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                if op.use_tc:
+                    rc = lib.bnn_conv2d_tc(_ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]),
+                                           self.dcode, n_img, op.src.H, op.src.W, op.src.C, op.dst.C, op.ksize[0],
+                                           op.stride, int(op.relu), ctypes.byref(dd), stream)
+                else:
+                    rc = lib.bnn_conv2d_simt(_ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]),
+                                             self.dcode, n_img, op.src.H, op.src.W, op.src.C, op.dst.C,
+                                             op.ksize[0], op.ksize[1], op.stride, op.pad, int(op.relu),
+                                             ctypes.byref(dd), stream)
+                _lib.check(rc)
+                self.launches += 1
+            elif op.kind == "site":
+                if S_local == 0:
+                    continue
+                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                per_image = op.src.H * op.src.W * op.src.C
+                _lib.check(lib.bnn_dropout(_ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, per_image,
+                                           op.src.C, S_local, int(op.src.stoch), ctypes.byref(dd), stream))
+                self.launches += 1
+            elif op.kind == "maxpool":
+                n_img = (S_local if op.dst.stoch else 1) * B
+                if n_img == 0:
+                    continue
+                _lib.check(lib.bnn_maxpool2d(_ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                                             op.src.H, op.src.W, op.src.C, op.pool_k, stream))
+                self.launches += 1
+            elif op.kind == "head":
+                e = op.exit_index
+                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                lo = st["logits"]
+                # per-sample logits are written [S_local][B][C] per exit; we keep one [S, B, C] slab per
+                # exit and permute on return
+                lo_e = lo.view(-1)[e * S_local * B * g.n_classes:] if lo is not None else None
+                _lib.check(lib.bnn_exit_head(_ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local,
+                                             op.src.H * op.src.W, op.src.C, g.n_classes, _ptr(op.d_w), _ptr(op.d_b),
+                                             ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
+                                             _ptr(lo_e), int(accumulate), stream))
+                self.launches += 1
+        return st
+
+    def finalize(self, st, B, S_total):
+        g = self.graph
+        E, C = g.n_exits, g.n_classes
+        n = E * B * C
+        o = st["out"]
+        views = [o[i * n:(i + 1) * n].view(E, B, C) for i in range(4)]
+        ent = [o[4 * n + i * E * B: 4 * n + (i + 1) * E * B].view(E, B) for i in range(3)]
+        sum_p, sum_l, sum_pl = self.sums_views(st, B)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if B > 0:
+            _lib.check(self.lib.bnn_finalize(_ptr(sum_p), _ptr(sum_l), _ptr(sum_pl), E, B, C, S_total,
+                                             _ptr(views[0]), _ptr(views[1]), _ptr(views[2]), _ptr(views[3]),
+                                             _ptr(ent[0]), _ptr(ent[1]), _ptr(ent[2]), stream))
+            self.launches += 2
+        return views, ent
+
+    def advance_masksembles(self, S):
+        """Model the reference's stateful rotation (utils.py:168): every Masksembles module advances
+        its `cnt` by one per forward pass."""
+        seen = set()
+        for s in self.graph.sites:
+            if s.kind == "mask" and s.module is not None and id(s.module) not in seen:
+                seen.add(id(s.module))
+                s.module.cnt = (int(s.module.cnt) + S) % int(s.module.n)
+
+    def run(self, x, S, seed=0x5EED, sample0=0, S_total=None, want_logits=False, reduce_fn=None,
+            mask_offset=None):
+        """S local samples starting at global sample index `sample0`; `reduce_fn(sums)` (optional)
+        all-reduces the flat sums tensor across ranks before the finaliser.  Masksembles rows are
+        (module.cnt + mask_offset + s) % n with mask_offset defaulting to sample0."""
+        x = x.to(self.device, torch.float32)
+        B = x.shape[0]
+        with torch.cuda.device(self.device):
+            st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
+            if reduce_fn is not None:
+                reduce_fn(st["sums"])
+            S_total = S if S_total is None else S_total
+            views, ent = self.finalize(st, B, S_total)
+        self.advance_masksembles(S_total)
+        all_logits = None
+        if want_logits:
+            E, C = self.graph.n_exits, self.graph.n_classes
+            all_logits = st["logits"].view(E, S, B, C).permute(1, 0, 2, 3)
+        return MCResult(views[0], views[1], views[2], views[3], ent[0], ent[1], ent[2], all_logits, S_total)

@@ -1,0 +1,56 @@
+"""``mc_predict`` - the fused replacement of the reference's S-pass loop, plus sample sharding.
+
+Reference: ``FullAnalysis._get_output`` (Software_Artifact/software/train/results_analyzer.py:236-270).
+Multi-GPU (new; the reference is single-device): rank r of G owns the contiguous global samples
+``shard_samples(S, G, r)``; the deterministic prefix is replicated; ONE all-reduce(sum) of the flat
+per-exit statistics buffer ([E,B,C] sum of probs, [E,B,C] sum of logits, [E,B] sum of p log p) over
+NCCL precedes the finaliser.  Because Philox counters carry the GLOBAL sample index the reduced sums
+do not depend on G.
+"""
+import torch
+
+from .engine import MCResult  # noqa: F401
+
+
+def shard_samples(S, world_size, rank):
+    """(first global sample, number of local samples) of `rank`: contiguous, sizes differ by <= 1."""
+    if S < 0 or world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad shard request S=%d world=%d rank=%d" % (S, world_size, rank))
+    base, extra = divmod(S, world_size)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def shard_batch(B, world_size, rank):
+    """Alternative partitioning (independent images): contiguous slice of the batch."""
+    return shard_samples(B, world_size, rank)
+
+
+def allreduce_sums(flat, group=None):
+    """The single collective of the path: sum the flat statistics buffer over ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def mc_predict(model, x, S, seed=0x5EED, dtype=None, want_logits=False, distributed=False, group=None,
+               engine_kwargs=None):
+    """S stochastic passes of `model` over the batch `x` ([B, C, H, W] float32, host or device).
+
+    Returns an :class:`MCResult` whose tensors live in the engine's cached device buffers (valid
+    until the next call on the same model/batch shape; ``.clone()`` to keep).  With
+    ``distributed=True`` (inside an initialised ``torch.distributed`` process group) the S samples
+    are sharded over the ranks and every rank gets the full statistics.
+    """
+    if S <= 0:
+        raise ValueError("S must be positive, got %d" % S)
+    eng = model.bnn_engine(dtype, **(engine_kwargs or {}))
+    sample0, s_local, reduce_fn = 0, S, None
+    if distributed:
+        import torch.distributed as dist
+        ws, rk = dist.get_world_size(group), dist.get_rank(group)
+        sample0, s_local = shard_samples(S, ws, rk)
+        reduce_fn = lambda flat: allreduce_sums(flat, group)
+    return eng.run(x, s_local, seed=seed, sample0=sample0, S_total=S, want_logits=want_logits,
+                   reduce_fn=reduce_fn)

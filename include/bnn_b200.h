@@ -1,0 +1,153 @@
+/*
+ * bnn_b200.h - C ABI of the B200-native multi-exit MC-dropout / Masksembles inference path.
+ *
+ * The reference (os-hxfan/BayesNN_FPGA) has no plugin / operator / FFI layer of its own: its hot
+ * path is plain PyTorch (`FullAnalysis._get_output`, Software_Artifact/software/train/
+ * results_analyzer.py:236-270, calling `model(b_x)` S times).  The drop-in boundary is therefore
+ * the Python object model (same class names / kwargs / return structures), and
+ * THIS header is what those Python classes bind underneath with ctypes.  Every entry point names
+ * the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *     buffers are borrowed (the caller, i.e. torch, owns every allocation)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - return value: 0 on success, negative BNN_E_* otherwise; bnn_last_error() gives the message
+ *   - activations are NHWC ("channels last"), one image = H*W*C contiguous elements; a tensor that
+ *     carries Monte-Carlo samples is [S_local][B][H][W][C] (sample-major)
+ *   - dtype codes: 0 = float32, 1 = float16, 2 = bfloat16 (storage of activations; accumulation is
+ *     always float32)
+ *   - there is NO CPU fallback: every compute entry point returns BNN_E_ARCH unless the current
+ *     device is sm_100
+ */
+#ifndef BNN_B200_H
+#define BNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_OK 0
+#define BNN_E_ARG (-1)
+#define BNN_E_ARCH (-2)
+#define BNN_E_CUDA (-3)
+#define BNN_E_UNSUPPORTED (-4)
+
+#define BNN_F32 0
+#define BNN_F16 1
+#define BNN_BF16 2
+
+/* stochastic-layer kinds (which reference module a site replaces) */
+#define BNN_DROP_NONE 0
+#define BNN_DROP_ELEMENT 1 /* MCDropout / F.dropout: resnet18.py:207-210, vgg19.py:384-387, Dropouts.py:32-34 */
+#define BNN_DROP_CHANNEL 2 /* F.dropout2d / dropout3d: converter Dropouts.py:43-45, :54-56 */
+#define BNN_DROP_MASKSEMBLES 3 /* Masksembles1D/2D eval branch: utils.py:165-169, :227-231 */
+
+int bnn_version(void);
+const char* bnn_last_error(void);
+/* 0 if the current CUDA device is an sm_100 part, BNN_E_ARCH / BNN_E_CUDA otherwise. */
+int bnn_device_check(void);
+int bnn_sm_count(void);
+
+/* ---- mask contract (test hooks; the same device functions are inlined in the fused kernels) ----
+ * Philox-4x32-10 words / keep flags for element indices [0, count) of (seed, stream, sample).
+ * Replaces torch's global dropout RNG inside F.dropout (resnet18.py:210) with a counter-based
+ * stream so that masks are reproducible, shard-invariant and injectable into the oracle. */
+int bnn_philox_words(uint32_t* out, int64_t count, uint64_t seed, uint32_t stream_id, uint32_t sample,
+                     void* stream);
+int bnn_philox_keep(uint8_t* out, int64_t count, float p, uint64_t seed, uint32_t stream_id, uint32_t sample,
+                    void* stream);
+
+/* ---- layout ----
+ * x[N][C][H][W] float32 (what `model(b_x)` receives, results_analyzer.py:144-146) -> y[N][H][W][C] in
+ * `dtype`. */
+int bnn_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
+
+/* ---- convolution + folded BatchNorm + residual + ReLU (+ fused dropout) ----
+ * Replaces conv2d -> BatchNorm2d(eval) [-> += residual] [-> ReLU] [-> MCDropout / Masksembles2D] chains:
+ * BasicBlock.forward resnet18.py:32-48, exit branches :306-308, VGG make_layers vgg19.py:121-143, LeNet
+ * t_qmodels_bayes_me.py:49-52.  `w` is [Cout][KH][KW][Cin] with the BN scale folded in, `bias` the
+ * folded shift (float32 [Cout]); `res` (nullable) has the output's shape.  N counts images including the
+ * sample dimension.
+ *
+ * Fused stochastic epilogue (drop_kind != BNN_DROP_NONE), applied after the ReLU exactly like the
+ * reference's Sequential(layerN, MCDropout) (resnet18.py:278): the output is [S_local][B] images,
+ * image n belongs to sample sample0 + n / B and to batch element n % B.
+ *
+ * bnn_conv2d_simt : exact fp32 CUDA-core implicit GEMM, any geometry, w is float32 (FP32 parity path,
+ *                   and the layers whose Cin is not a multiple of 64).
+ * bnn_conv2d_tc   : tcgen05 / TMEM / TMA implicit GEMM; x, w, y, res in float16 or bfloat16; 3x3 pad 1
+ *                   or 1x1 pad 0, stride 1 or 2, Cin % 64 == 0, Cout % 64 == 0.
+ */
+typedef struct bnn_drop_desc {
+  int kind;             /* BNN_DROP_* */
+  float p;              /* drop probability (ELEMENT / CHANNEL) */
+  uint64_t seed;        /* Philox key */
+  uint32_t stream_id;   /* dropout site number */
+  uint32_t sample0;     /* GLOBAL index of the first local sample */
+  int batch;            /* B: images per sample */
+  const float* masks;   /* MASKSEMBLES: float32 [n_masks][C] on the device */
+  int n_masks;
+  int cnt0;             /* MASKSEMBLES: value of the module's rotating `cnt` at sample 0 */
+} bnn_drop_desc;
+
+int bnn_conv2d_simt(const void* x, const float* w, const float* bias, const void* res, void* y, int dtype, int N,
+                    int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
+                    const bnn_drop_desc* drop, void* stream);
+
+int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype, int N,
+                  int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
+                  void* stream);
+/* Bytes of persistent workspace bnn_conv2d_tc wants (tile counters); may be 0. */
+
+/* ---- stand-alone stochastic layer (prefix -> suffix broadcast) ----
+ * y[s][b][...] = drop_s(x[b][...]) for s in [0, S_local) when x_has_samples == 0 (the deterministic
+ * prefix is computed once per image and broadcast across the S samples), or drop_s(x[s][b][...])
+ * otherwise.  `per_image` = H*W*C elements, C = channel count (innermost). Replaces MCDropout.forward
+ * (resnet18.py:207-210), BayesianDropout*.forward's dropout half (Dropouts.py:32-56) and the
+ * Masksembles eval branch (utils.py:165-169, :227-231). */
+int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int S_local, int x_has_samples,
+                const bnn_drop_desc* drop, void* stream);
+
+/* ---- max-pool k x k, stride k (vgg19.py:128, LeNet t_qmodels_bayes_me.py:54,:104) ---- */
+int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C, int k, void* stream);
+
+/* ---- exit head: global average pool -> stochastic layer -> Linear -> softmax -> accumulate over samples ----
+ * Replaces, per exit, `F.avg_pool2d(F.relu(out), k)` -> view -> exitN_dropout -> exNlinear
+ * (resnet18.py:309-314, vgg19.py:297-322) plus `softmax(out, dim=1)` and the per-pass buffers of
+ * _get_output (results_analyzer.py:242-248): instead of S x E device->host copies the kernel keeps
+ * running sums over the local samples.
+ *   feat        [S_local or 1][B][HW][F]   (feat_has_samples says which)
+ *   w, bias     float32 [C][F], [C]
+ *   sum_p, sum_logit   float32 [B][C]   (+= if accumulate != 0, else overwritten)
+ *   sum_plogp          float32 [B]      sum_s sum_c p log p
+ *   logits_out         nullable float32 [S_local][B][C]: per-sample logits (for parity tests)
+ */
+int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                  const float* w, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                  float* sum_plogp, float* logits_out, int accumulate, void* stream);
+
+/* ---- statistics finaliser ----
+ * From the (all-reduced) sums over S_total samples: predictive mean, mean logits, cumulative exit ensembles
+ * (results_analyzer.py:247-248, :260-269), entropy of the mean with the reference's 1e-8 epsilon
+ * (bayes_hw/metric_utils.py:3-6) and the expected per-sample entropy.
+ *   sums layout: sum_p [E][B][C], sum_logit [E][B][C], sum_plogp [E][B]
+ *   outputs: mean_p, mean_logit, ens_p, ens_logit [E][B][C]; entropy, ens_entropy, exp_entropy [E][B]
+ */
+int bnn_finalize(const float* sum_p, const float* sum_logit, const float* sum_plogp, int E, int B, int C,
+                 int S_total, float* mean_p, float* mean_logit, float* ens_p, float* ens_logit, float* entropy,
+                 float* ens_entropy, float* exp_entropy, void* stream);
+
+/* ---- calibration statistics on the device ----
+ * Top-label confidence / correctness per image and the equal-width-bin ECE
+ * (hls4ml_pred.py:90-91 statistic). probs [N][C] float32, labels int32 [N].
+ * bin_stats: float32 [n_bins][3] = (count, sum confidence, sum correct), zeroed by the call. */
+int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C, int n_bins, float* conf,
+                         int32_t* correct, float* bin_stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNN_B200_H */

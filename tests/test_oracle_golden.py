@@ -1,0 +1,96 @@
+"""CPU: the oracle restatement against the fixtures frozen from the LIVE reference
+(tests/golden/make_golden.py).  This is what pins the oracle (the reference ships no
+golden vectors of its own)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import masksembles as o_masks
+from oracle import philox, seeded, stats
+from tests.cases import CASES, GOLDEN, build_seeded, load_golden, oracle_run
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kats = [((0, 0, 0, 0), (0, 0), "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kats:
+        got = " ".join("%08x" % int(v) for v in philox.philox4x32_10(*ctr, *key))
+        assert got == want
+
+
+def test_philox_thresholds_and_edges():
+    assert philox.threshold(0.0) == 0 and philox.threshold(0.5) == 2 ** 31 and philox.threshold(1.0) == 2 ** 32 - 1
+    assert philox.keep_mask_flat(1, 2, 3, 1000, 0.0).all()          # p = 0 keeps everything
+    assert not philox.keep_mask_flat(1, 2, 3, 1000, 1.0).any()      # p = 1 drops everything (F.dropout -> zeros)
+    assert philox.keep_mask_flat(1, 2, 3, 0, 0.5).shape == (0,)     # empty
+    m = philox.keep_mask_flat(1, 2, 3, 200003, 0.25)                # ragged length, statistics
+    assert abs(m.mean() - 0.75) < 5e-3
+    # NHWC contract: element e of the flat stream is (b, h, w, c)
+    k = philox.keep_mask(9, 4, 7, (2, 8, 3, 5), 0.5)
+    flat = philox.keep_mask_flat(9, 4, 7, 2 * 8 * 3 * 5, 0.5).reshape(2, 3, 5, 8)
+    assert (k == flat.transpose(0, 3, 1, 2)).all()
+    # channel-wise masks are constant over space
+    c = philox.keep_mask(9, 4, 7, (2, 8, 3, 5), 0.5, mode="channel")
+    assert (c == c[:, :, :1, :1]).all()
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_oracle_reproduces_live_reference(tag):
+    model_sd_gold = build_seeded(tag)
+    _, sd, gold = model_sd_gold
+    x = torch.from_numpy(gold["x"])
+    assert np.array_equal(x.numpy(), seeded.seeded_input(x.shape, seed=99).numpy())
+    got = oracle_run(tag, sd, x, int(gold["S"]), int(gold["seed"]), float(gold["p"]))
+    for k in ("mean_logits", "mean_probs", "ens_logits", "ens_probs"):
+        assert np.abs(got[k] - gold[k]).max() <= 1e-6, k      # reference outputs, same torch ops
+    assert np.abs(got["all_logits"] - gold["all_logits"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_state_dict_names_match_reference(tag):
+    model, _, gold = build_seeded(tag)
+    assert sorted(model.state_dict().keys()) == list(gold["state_keys"])
+
+
+def test_masksembles_generator_bit_exact():
+    from bayesnn_fpga_b200 import utils as product
+    z = np.load(GOLDEN + "/masksembles_masks.npz")
+    assert len(z.files) == 8
+    for name in z.files:
+        c, n, s, seed = name.split("_")
+        c, n, s, seed = int(c[1:]), int(n[1:]), float(s[1:]), int(seed[4:])
+        for gen in (o_masks.generation_wrapper, product.generation_wrapper):
+            np.random.seed(seed)
+            got = gen(c, n, s)
+            assert got.shape == z[name].shape and (got == z[name]).all(), (name, gen.__module__)
+        assert (z[name].sum(1) == z[name].sum(1)[0]).all()          # every mask keeps the same count
+
+
+def test_masksembles_generator_errors():
+    from bayesnn_fpga_b200 import utils as product
+    for gen in (o_masks.generation_wrapper, product.generation_wrapper):
+        with pytest.raises(ValueError):
+            gen(9, 4, 2.0)          # c < 10 (utils.py:77-81)
+        with pytest.raises(ValueError):
+            gen(64, 4, 6.5)         # scale > 6 (utils.py:83-85)
+
+
+def test_ece_hist_matches_reference_source():
+    z = np.load(GOLDEN + "/ece_hist.npz")
+    for k in range(3):
+        p, lab = z["p%d" % k], z["label%d" % k]
+        onehot = np.eye(p.shape[1])[lab]
+        assert abs(stats.ece_hist(p, onehot) - float(z["ece%d" % k])) < 1e-7
+
+
+def test_entropy_and_ece_width_definitions():
+    p = np.array([[0.5, 0.5], [1.0, 0.0]])
+    want = -(2 * 0.5 * np.log(0.5 + 1e-8) + 1.0 * np.log(1.0 + 1e-8) + 0.0) / 2
+    assert abs(stats.entropy(p) - want) < 1e-12
+    # perfectly calibrated two-bin toy: conf 0.75 with 3/4 correct
+    p = np.array([[0.75, 0.25]] * 4)
+    assert abs(stats.ece_width(p, np.array([0, 0, 0, 1]))) < 1e-12
+    assert abs(stats.ece_width(p, np.array([0, 0, 1, 1])) - 0.25) < 1e-12
