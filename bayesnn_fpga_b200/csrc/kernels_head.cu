@@ -27,7 +27,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// dynamic shared memory layout: pooled[HEAD_SCHUNK][F] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] | red[HEAD_WARPS]
+// dynamic shared memory layout:
+//   pooled[HEAD_SCHUNK][F] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] | red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   float* acc_p = logits + (size_t)HEAD_SCHUNK * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
+  float* smax = red + HEAD_WARPS;
+  float* sinv = smax + HEAD_SCHUNK;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
       }
     }
     __syncthreads();
-    // ---- phase 3: softmax per sample (one warp per sample), accumulate ---------------------
+    // ---- phase 3a: softmax statistics per sample (one warp per sample) -----------------------
     for (int sl = warp; sl < ns; sl += HEAD_WARPS) {
       const float* lg = logits + sl * C;
       float mx = -INFINITY;
@@ -90,14 +93,27 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
       float pl = 0.f;
       for (int c = lane; c < C; c += 32) {
         const float z = lg[c] - mx;
-        const float p = expf(z) * inv;
-        pl += p * (z - logden);
-        atomicAdd(&acc_p[c], p);        // shared-memory atomics, <= 8 warps contending
-        atomicAdd(&acc_l[c], lg[c]);
-        if (logits_out) logits_out[((size_t)(s0 + sl) * B + b) * C + c] = lg[c];
+        pl += expf(z) * inv * (z - logden);
       }
       pl = warp_sum(pl);
       plogp_acc += pl;
+      if (lane == 0) {
+        smax[sl] = mx;
+        sinv[sl] = inv;
+      }
+    }
+    __syncthreads();
+    // ---- phase 3b: one thread per class walks the samples in order (deterministic sums) ---------
+    for (int c = tid; c < C; c += HEAD_THREADS) {
+      float ap = 0.f, al = 0.f;
+      for (int sl = 0; sl < ns; ++sl) {
+        const float lg = logits[sl * C + c];
+        ap += expf(lg - smax[sl]) * sinv[sl];
+        al += lg;
+        if (logits_out) logits_out[((size_t)(s0 + sl) * B + b) * C + c] = lg;
+      }
+      acc_p[c] += ap;
+      acc_l[c] += al;
     }
   }
   __syncthreads();
@@ -196,7 +212,8 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
                 "bnn_exit_head: Masksembles site without a mask table");
   }
   if (B == 0) return BNN_OK;
-  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_SCHUNK * C + 2 * (size_t)C + HEAD_WARPS) * sizeof(float);
+  const size_t smem =
+      ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_SCHUNK * C + 2 * (size_t)C + HEAD_WARPS + 2 * HEAD_SCHUNK) * sizeof(float);
   BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);
   DropParams dp = make_drop_params(drop, F);
   dp.batch = B;

@@ -20,6 +20,7 @@ Software_Artifact/software/train/results_analyzer.py:236-270: ``for i in range(m
 Only the C-ABI library does arithmetic; torch is used for allocation, streams and NCCL.
 """
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -235,7 +236,8 @@ class Engine:
             graph.fuse_sites()
         self.dtype_name = dtype
         self.dcode, self.tdtype = DTYPES[dtype]
-        self.use_tc = use_tc and dtype != "fp32"
+        # BNN_DISABLE_TC=1 routes the 16-bit path through the CUDA-core kernel too (debugging aid)
+        self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
         self.launches = 0
         self._bufs = {}
         self._prepare_weights()

@@ -112,6 +112,8 @@ class FullAnalysis:
         _, _, bins = self._device_bins(p, label_index, n_bins)
         b = bins.double().cpu().numpy()
         n = b[:, 0].sum()
+        if n == 0:
+            return 0.0
         nz = b[:, 0] > 0
         return float(np.sum(np.abs(b[nz, 1] / b[nz, 0] - b[nz, 2] / b[nz, 0]) * b[nz, 0] / n))
 

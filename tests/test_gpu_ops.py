@@ -1,0 +1,188 @@
+"""GPU: each C-ABI kernel against a plain fp32/fp64 restatement of the same op."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import philox, stats
+from tests.gpu_util import TORCH_DT, drop_desc, report, stream
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_case(lib, fn, dt, N, H, W, Cin, Cout, k, stride, pad, relu, with_res, drop=None, seed=0):
+    tdt, code = TORCH_DT[dt]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    xq, wq = x.to(tdt).float(), (w.to(tdt).float() if fn == "tc" else w)
+    want = F.conv2d(xq.double(), wq.double(), b.double(), stride, pad)
+    res = None
+    if with_res:
+        res = torch.randn(want.shape, generator=g).to(tdt)
+        want = want + res.double()
+    if relu:
+        want = want.relu()
+    OH, OW = want.shape[2:]
+    d_x = xq.permute(0, 2, 3, 1).contiguous().to(tdt).cuda()
+    d_w = wq.permute(0, 2, 3, 1).contiguous().cuda()
+    d_w = d_w.to(tdt) if fn == "tc" else d_w
+    d_b = b.cuda()
+    d_res = res.permute(0, 2, 3, 1).contiguous().cuda() if with_res else None
+    d_y = torch.full((N, OH, OW, Cout), float("nan"), dtype=tdt, device="cuda")
+    dd = drop if drop is not None else drop_desc(batch=N)
+    rp = ctypes.c_void_p(d_res.data_ptr() if with_res else 0)
+    if fn == "tc":
+        rc = lib.bnn_conv2d_tc(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), rp, d_y.data_ptr(), code, N, H, W, Cin,
+                               Cout, k, stride, int(relu), ctypes.byref(dd), stream())
+    else:
+        rc = lib.bnn_conv2d_simt(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), rp, d_y.data_ptr(), code, N, H, W,
+                                 Cin, Cout, k, k, stride, pad, int(relu), ctypes.byref(dd), stream())
+    assert rc == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    return d_y.cpu().float().permute(0, 3, 1, 2), want
+
+
+SIMT_SHAPES = [
+    # N, H, W, Cin, Cout, k, stride, pad, relu, res
+    (3, 9, 7, 5, 11, 3, 1, 1, True, True),        # ragged everything
+    (2, 32, 32, 3, 64, 3, 1, 1, False, False),    # conv1 of the ResNet
+    (2, 14, 14, 20, 20, 5, 7, 0, True, False),    # LeNet second-exit conv ("same" at stride 7)
+    (4, 28, 28, 1, 20, 5, 1, 2, True, False),     # LeNet conv2d_1
+    (5, 2, 2, 20, 100, 2, 1, 0, True, False),     # an nn.Linear over a flattened 2x2 map
+    (2, 16, 16, 64, 128, 1, 2, 0, False, False),  # 1x1 stride-2 shortcut
+    (1, 8, 8, 128, 70, 3, 2, 1, True, True),      # stride 2, Cout not a multiple of the tile
+    (130, 1, 1, 100, 10, 1, 1, 0, False, False),  # more than two tiles of 1x1 images
+]
+
+
+@pytest.mark.parametrize("shape", SIMT_SHAPES)
+def test_conv_simt_fp32(lib, shape):
+    got, want = _conv_case(lib, "simt", "fp32", *shape)
+    err = (got.double() - want).abs().max().item()
+    report(test="conv_simt_fp32", shape=list(shape), max_err=err)
+    assert err <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_conv_simt_16bit_storage(lib, dt):
+    got, want = _conv_case(lib, "simt", dt, 2, 10, 10, 24, 40, 3, 1, 1, True, True)
+    tol = 2e-3 if dt == "fp16" else 1.6e-2            # one rounding of the output to 16-bit storage
+    assert (got.double() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+
+def test_conv_simt_fused_dropout(lib):
+    N_img, B, S = 6, 2, 3
+    dd = drop_desc(1, 0.5, 0x77, 4, 5, B)
+    got, want = _conv_case(lib, "simt", "fp32", N_img, 6, 6, 8, 16, 3, 1, 1, True, False, drop=dd)
+    for s in range(S):
+        keep = torch.from_numpy(philox.keep_mask(0x77, 4, 5 + s, (B, 16, 6, 6), 0.5))
+        ref = want[s * B:(s + 1) * B] * keep * 2.0
+        assert (got[s * B:(s + 1) * B].double() - ref).abs().max().item() <= 2e-5
+
+
+def test_conv_empty_and_bad_args(lib):
+    y = torch.zeros(1, device="cuda")
+    dd = drop_desc(batch=1)
+    assert lib.bnn_conv2d_simt(y.data_ptr(), y.data_ptr(), y.data_ptr(), None, y.data_ptr(), 0, 0, 4, 4, 1, 1, 3, 3, 1,
+                               1, 0, ctypes.byref(dd), stream()) == 0                 # empty batch: no-op
+    assert lib.bnn_conv2d_simt(y.data_ptr(), y.data_ptr(), y.data_ptr(), None, y.data_ptr(), 0, 1, 2, 2, 1, 1, 5, 5, 1,
+                               0, 0, ctypes.byref(dd), stream()) == -1                # empty output
+    assert lib.bnn_conv2d_simt(y.data_ptr(), y.data_ptr(), y.data_ptr(), None, y.data_ptr(), 9, 1, 4, 4, 1, 1, 3, 3, 1,
+                               1, 0, ctypes.byref(dd), stream()) == -1                # bad dtype
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16"])
+@pytest.mark.parametrize("k", [2, 7])
+def test_maxpool(lib, dt, k):
+    tdt, code = TORCH_DT[dt]
+    x = torch.randn(3, 5, 14, 14).to(tdt)
+    d_x = x.permute(0, 2, 3, 1).contiguous().cuda()
+    d_y = torch.empty(3, 14 // k, 14 // k, 5, dtype=tdt, device="cuda")
+    assert lib.bnn_maxpool2d(d_x.data_ptr(), d_y.data_ptr(), code, 3, 14, 14, 5, k, stream()) == 0
+    assert torch.equal(d_y.cpu().permute(0, 3, 1, 2), F.max_pool2d(x.float(), k, k).to(tdt))
+
+
+def test_nchw_to_nhwc(lib):
+    x = torch.randn(3, 5, 4, 6, device="cuda")
+    for dt in ("fp32", "fp16", "bf16"):
+        tdt, code = TORCH_DT[dt]
+        y = torch.empty(3, 4, 6, 5, dtype=tdt, device="cuda")
+        assert lib.bnn_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), code, 3, 5, 4, 6, stream()) == 0
+        assert torch.equal(y, x.permute(0, 2, 3, 1).to(tdt))
+
+
+@pytest.mark.parametrize("C,F_,HW,has_samples,kind", [(10, 512, 16, 1, 1), (100, 512, 4, 0, 1), (7, 100, 1, 1, 0),
+                                                      (100, 512, 1, 1, 3), (33, 48, 4, 1, 2)])
+def test_exit_head_and_finalize(lib, C, F_, HW, has_samples, kind):
+    """pool -> site -> linear -> softmax -> sums over samples, then the finaliser, vs float64 numpy."""
+    B, S, s0, p, seed, sid = 5, 19, 3, 0.25, 0x99, 2          # S > HEAD_SCHUNK exercises the chunk loop
+    g = torch.Generator().manual_seed(C)
+    feat = torch.randn((S if has_samples else 1) * B, HW, F_, generator=g).abs()
+    w = torch.randn(C, F_, generator=g) / np.sqrt(F_) * 3
+    bias = torch.randn(C, generator=g)
+    masks = (torch.rand(4, F_, generator=g) > 0.5).float()
+    d_masks = masks.cuda()
+    dd = drop_desc(kind, p, seed, sid, s0, B, d_masks if kind == 3 else None, cnt0=1)
+    d = dict(feat=feat.cuda(), w=w.cuda(), b=bias.cuda(), sp=torch.zeros(B, C).cuda(), sl=torch.zeros(B, C).cuda(),
+             spl=torch.zeros(B).cuda(), lo=torch.zeros(S, B, C).cuda())
+    rc = lib.bnn_exit_head(d["feat"].data_ptr(), 0, has_samples, B, S, HW, F_, C, d["w"].data_ptr(), d["b"].data_ptr(),
+                           ctypes.byref(dd), d["sp"].data_ptr(), d["sl"].data_ptr(), d["spl"].data_ptr(),
+                           d["lo"].data_ptr(), 0, stream())
+    assert rc == 0, lib.bnn_last_error()
+    fv = feat.double().view(-1, B, HW, F_).mean(2)                       # [S or 1, B, F]
+    logits = np.zeros((S, B, C))
+    for s in range(S):
+        v = fv[s if has_samples else 0].numpy()
+        if kind in (1, 2):
+            v = v * philox.keep_mask(seed, sid, s0 + s, (B, F_), p) * (1 / (1 - p))
+        elif kind == 3:
+            v = v * masks[(1 + s0 + s) % 4].double().numpy()
+        logits[s] = v @ w.double().numpy().T + bias.double().numpy()
+    z = logits - logits.max(-1, keepdims=True)
+    probs = np.exp(z) / np.exp(z).sum(-1, keepdims=True)
+    assert np.abs(d["lo"].cpu().numpy() - logits).max() < 2e-5
+    assert np.abs(d["sp"].cpu().numpy() - probs.sum(0)).max() < 2e-5
+    assert np.abs(d["sl"].cpu().numpy() - logits.sum(0)).max() < 2e-4
+    assert np.abs(d["spl"].cpu().numpy() - (probs * np.log(probs)).sum(-1).sum(0)).max() < 2e-4
+
+    # accumulate=1 adds a second shard on top
+    rc = lib.bnn_exit_head(d["feat"].data_ptr(), 0, has_samples, B, S, HW, F_, C, d["w"].data_ptr(), d["b"].data_ptr(),
+                           ctypes.byref(dd), d["sp"].data_ptr(), d["sl"].data_ptr(), d["spl"].data_ptr(), None, 1, stream())
+    assert rc == 0
+    assert np.abs(d["sp"].cpu().numpy() - 2 * probs.sum(0)).max() < 4e-5
+
+    # finaliser over E = 2 "exits" (the same sums twice, second one scaled) and 2*S samples
+    E = 2
+    sums_p = torch.stack([d["sp"], d["sp"]]).contiguous()
+    sums_l = torch.stack([d["sl"], 0.5 * d["sl"]]).contiguous()
+    sums_pl = torch.stack([d["spl"], d["spl"]]).contiguous()
+    outs = [torch.zeros(E, B, C, device="cuda") for _ in range(4)] + [torch.zeros(E, B, device="cuda") for _ in range(3)]
+    assert lib.bnn_finalize(sums_p.data_ptr(), sums_l.data_ptr(), sums_pl.data_ptr(), E, B, C, 2 * S,
+                            *[o.data_ptr() for o in outs], stream()) == 0
+    mp = np.stack([probs.mean(0), probs.mean(0)])
+    ml = np.stack([logits.mean(0), 0.5 * logits.mean(0)])
+    got = [o.cpu().numpy() for o in outs]
+    assert np.abs(got[0] - mp).max() < 1e-5 and np.abs(got[1] - ml).max() < 1e-5
+    assert np.abs(got[2][1] - mp.mean(0)).max() < 1e-5 and np.abs(got[3][1] - ml.mean(0)).max() < 1e-5
+    assert np.abs(got[4][0] - stats.entropy_per_image(mp[0])).max() < 1e-5
+    assert np.abs(got[6][0] - (-(probs * np.log(probs)).sum(-1).mean(0))).max() < 1e-5
+
+
+def test_calibration_bins_and_ece(lib):
+    from bayesnn_fpga_b200.results_analyzer import FullAnalysis
+
+    class Dummy:
+        n_exits, out_dim = 1, 10
+    fa = FullAnalysis(Dummy(), None, run=False)
+    z = np.load(__import__("tests.cases", fromlist=["GOLDEN"]).GOLDEN + "/ece_hist.npz")
+    for k in range(3):
+        p, lab = z["p%d" % k], z["label%d" % k]
+        onehot = np.eye(p.shape[1])[lab]
+        got = fa.ece_hist_binary(p, onehot)
+        assert abs(got - float(z["ece%d" % k])) < 1e-4            # reference's own ece_hist_binary value
+        assert abs(fa.ece_width(p, lab) - stats.ece_width(p.astype(np.float32), lab)) < 1e-5
+    assert fa.ece_width(np.zeros((0, 10)), np.zeros(0, dtype=np.int64)) == 0.0        # empty dataset

@@ -1,0 +1,149 @@
+"""CPU: host-side logic - graph lowering, BN folding, site fusion, sharding, the C-ABI library's
+symbol table, and the no-CPU-fallback contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from bayesnn_fpga_b200 import _lib, engine, lenet, predict, resnet18, vgg19
+from bayesnn_fpga_b200 import Dropouts, nn2bnn, utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "bnn_b200.h")).read()
+    declared = set(re.findall(r"\b(bnn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"bnn_drop_desc"}
+    assert declared == set(_lib.exported_symbols())
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.bnn_version() == 100
+
+
+def test_no_cpu_fallback(lib):
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only contract")
+    # every compute entry point refuses to run without an sm_100 device
+    assert lib.bnn_device_check() != 0
+    buf = (ctypes.c_uint32 * 8)()
+    assert lib.bnn_philox_words(ctypes.addressof(buf), 8, 1, 2, 3, None) != 0
+    assert b"no CPU fallback" in lib.bnn_last_error()
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, out_dim=10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Dropouts.MCDropout(0.5)(torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        np.random.seed(0)
+        utils.Masksembles1D(16, 4, 2.0).eval()(torch.zeros(4, 16))
+
+
+def test_cost_model_matches_survey():
+    # SURVEY.md section 8d, hook-derived MACs of the live reference
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", out_dim=10)
+    assert m._bnn_graph().macs() == (152764416, 515919872)
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout=None, out_dim=10)
+    pre, suf = m._bnn_graph().macs()
+    assert pre + suf == 668684288 and suf == 4 * 5120
+    v = vgg19.VGG19MCEarlyExit(dropout_exit=True, dropout=None, out_dim=100, n_exits=5).append_block_dropout((2, 3, 4))
+    assert v._bnn_graph().macs() == (251854848, 174843904)
+
+
+def test_site_numbering_and_fusion():
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", out_dim=10)
+    g = m._bnn_graph()
+    assert [s.name for s in g.sites] == ["layer1.1", "exit1_dropout", "layer2.1", "exit2_dropout", "layer3.1",
+                                         "exit3_dropout", "exit_dropout"]
+    assert [s.stream for s in g.sites] == list(range(7))
+    n_before = len(g.ops)
+    g.fuse_sites()
+    fused = [op for op in g.ops if op.kind == "conv" and op.site is not None]
+    # layer2 / layer3 sites ride in the epilogue of the block's last conv; the layer1 site is the
+    # prefix -> suffix broadcast and stays a kernel of its own
+    assert [op.site.name for op in fused] == ["layer2.1", "layer3.1"] and len(g.ops) == n_before - 2
+    assert [op.site.name for op in g.ops if op.kind == "site"] == ["layer1.1"]
+    # prefix = everything before the first site
+    first = next(i for i, op in enumerate(g.ops) if op.kind == "site")
+    assert all(not op.dst.stoch for op in g.ops[:first] if op.dst is not None)
+    assert all(op.dst.stoch for op in g.ops[first:] if op.dst is not None)
+
+
+def test_exit_only_dropout_keeps_all_convs_in_prefix():
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout=None, out_dim=10)
+    g = m._bnn_graph()
+    assert all(not op.dst.stoch for op in g.ops if op.kind == "conv")
+    assert all(op.site is not None for op in g.ops if op.kind == "head")
+
+
+def test_bn_fold_is_exact():
+    torch.manual_seed(0)
+    conv, bn = nn.Conv2d(5, 7, 3, padding=1, bias=True), nn.BatchNorm2d(7)
+    bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.2)
+    bn.eval()
+    x = torch.randn(2, 5, 6, 6)
+    w, b = engine.fold_conv_bn(conv, bn)
+    assert torch.allclose(F.conv2d(x, w, b, 1, 1), bn(conv(x)), atol=1e-5)
+
+
+def test_shard_samples_partitions():
+    for S in (0, 1, 7, 32, 128):
+        for G in (1, 2, 3, 4, 8):
+            parts = [predict.shard_samples(S, G, r) for r in range(G)]
+            assert sum(n for _, n in parts) == S
+            assert parts[0][0] == 0 and all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(G - 1))
+            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+    with pytest.raises(ValueError):
+        predict.shard_samples(8, 2, 2)
+
+
+def test_converter_type_map_and_errors():
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(3, 4, 3)
+            self.p = nn.MaxPool2d(2)
+            self.f = nn.Sequential(nn.Flatten(), nn.Linear(4, 2), nn.ReLU())
+            self.c3 = nn.Conv3d(1, 1, 1)
+    bnn = nn2bnn.MCDropout(Net(), nSamples=5, p=0.25)
+    assert type(bnn.model.c) is Dropouts.BayesianDropout2D
+    assert type(bnn.model.p) is Dropouts.BayesianDropout
+    assert type(bnn.model.f[1]) is Dropouts.BayesianDropout
+    assert type(bnn.model.f[0]) is nn.Flatten and type(bnn.model.f[2]) is nn.ReLU
+    assert type(bnn.model.c3) is Dropouts.BayesianDropout3D
+    assert bnn.nSamples == 5 and bnn.p == 0.25 and bnn.model.c.p == 0.25
+    assert "nSamples: 5" in bnn.extra_repr()
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        Dropouts.BayesianDropout(nn.Linear(2, 2), p=1.5)          # Dropouts.py:15-17
+    assert Dropouts.BayesianDropout(nn.Linear(2, 2), p=0.3).extra_repr() == "p=0.3, inplace=False"
+
+
+def test_masksembles_module_contract():
+    np.random.seed(0)
+    m = utils.Masksembles2D(64, 4, 2.0)
+    assert m.masks.shape == (4, 64) and not m.masks.requires_grad and m.cnt == 0
+    assert "masks" in m.state_dict()
+    assert set(np.unique(m.masks.numpy())) == {0.0, 1.0}
+    assert [len(k) for k in utils.kept_channels(m.masks)] == [34] * 4          # 34/64 at scale 2
+    m.train()
+    with pytest.raises(ValueError, match="divisible by n"):
+        m(torch.zeros(6, 64, 2, 2))                                          # utils.py:159-160
+    assert m.extra_repr() == "scale=2.0, n=4"
+
+
+def test_model_attributes_read_by_analyzers():
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", dropout_p=0.3, out_dim=10)
+    assert (m.n_exits, m.out_dim, m.dropout, m.dropout_exit, m.dropout_p) == (4, 10, "block", True, 0.3)
+    assert isinstance(m.layer1[1], Dropouts.MCDropout) and isinstance(m.exit1_dropout, Dropouts.MCDropout)
+    with pytest.raises(NotImplementedError):
+        np.random.seed(0)
+        resnet18.ResNet18MCEarlyExit(dropout="layer", mask_type="mask")
+    l = lenet.LeNetMCEarlyExit()
+    g = l._bnn_graph()
+    assert g.n_exits == 2 and g.n_classes == 10 and [s.name for s in g.sites] == ["bayes_2nd_exit", "bayes_1st_exit"]
