@@ -77,12 +77,13 @@ class Op:
 def fold_conv_bn(conv, bn=None):
     """conv weight/bias with eval-mode BatchNorm folded in:
     w' = w * g / sqrt(var + eps),  b' = beta + (b - mean) * g / sqrt(var + eps)."""
-    w = conv.weight.detach().double()
-    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    f64 = lambda t: t.detach().cpu().double()        # plan-time host arithmetic, done once per model
+    w = f64(conv.weight)
+    b = f64(conv.bias) if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
     if bn is not None:
-        g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        g = f64(bn.weight) / torch.sqrt(f64(bn.running_var) + bn.eps)
         w = w * g.reshape(-1, 1, 1, 1)
-        b = bn.bias.detach().double() + (b - bn.running_mean.detach().double()) * g
+        b = f64(bn.bias) + (b - f64(bn.running_mean)) * g
     return w.float().contiguous(), b.float().contiguous()
 
 
@@ -120,8 +121,8 @@ class Graph:
 
     def linear(self, src, lin, relu=False, name=""):
         """nn.Linear over the NCHW-flattened src == a convolution whose kernel covers the whole map."""
-        w = lin.weight.detach().float().reshape(lin.out_features, src.C, src.H, src.W).contiguous()
-        b = lin.bias.detach().float().contiguous() if lin.bias is not None else torch.zeros(lin.out_features)
+        w = lin.weight.detach().cpu().float().reshape(lin.out_features, src.C, src.H, src.W).contiguous()
+        b = lin.bias.detach().cpu().float().contiguous() if lin.bias is not None else torch.zeros(lin.out_features)
         return self.conv_raw(src, w, b, 1, 0, relu, None, name)
 
     def site(self, src, kind, p=0.5, module=None, name=""):
@@ -144,8 +145,8 @@ class Graph:
 
     def head(self, src, lin, site=None, name=""):
         """global average pool -> [site] -> Linear -> softmax -> accumulate (one exit)."""
-        w = lin.weight.detach().float().contiguous()
-        b = lin.bias.detach().float().contiguous()
+        w = lin.weight.detach().cpu().float().contiguous()
+        b = lin.bias.detach().cpu().float().contiguous()
         assert w.shape[1] == src.C, (name, w.shape, src.C)
         if self.n_classes is None:
             self.n_classes = w.shape[0]

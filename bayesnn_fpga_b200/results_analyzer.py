@@ -101,7 +101,9 @@ class FullAnalysis:
             N, C = dp.shape
             conf = torch.empty(N, dtype=torch.float32, device=self.device)
             hit = torch.empty(N, dtype=torch.int32, device=self.device)
-            bins = torch.empty((n_bins, 3), dtype=torch.float32, device=self.device)
+            bins = torch.zeros((n_bins, 3), dtype=torch.float32, device=self.device)
+            if N == 0:
+                return conf, hit, bins
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(lib.bnn_calibration_bins(dp.data_ptr(), dl.data_ptr(), N, C, n_bins, conf.data_ptr(),
                                                 hit.data_ptr(), bins.data_ptr(), stream))

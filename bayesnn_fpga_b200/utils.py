@@ -102,6 +102,7 @@ def _site_forward(x, kind, p, masks, mask_rows, seed, stream_id, sample0, channe
         d = _lib.DropDesc()
         d.kind, d.p, d.seed, d.stream_id = kind, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id)
         if masks is not None:
+            masks = masks.contiguous()
             d.masks, d.n_masks = masks.data_ptr(), masks.shape[0]
         if B > 0:
             if mask_rows is None:
@@ -130,7 +131,9 @@ class _MasksemblesBase(nn.Module):
         self.n = n
         self.scale = scale
         self.cnt = 0
-        masks = torch.from_numpy(generation_wrapper(channels, n, scale)).float()
+        # numpy's column selection inside the generator may return a non-C-contiguous array; the
+        # kernels index the table as row-major [n][C]
+        masks = torch.from_numpy(np.ascontiguousarray(generation_wrapper(channels, n, scale))).float()
         self.masks = torch.nn.Parameter(masks, requires_grad=False)
 
     def forward(self, inputs):
