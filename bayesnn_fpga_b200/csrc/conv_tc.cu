@@ -1,7 +1,541 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bnn_conv2d_tc in include/bnn_b200.h).
+//
+// Replaces conv2d -> BatchNorm(eval) [-> += residual] [-> ReLU] [-> MCDropout | Masksembles2D] of the
+// reference networks (resnet18.py:32-48,:306-308; vgg19.py:121-143) for the layers behind the first
+// stochastic site, where the work is S x the prefix and really is a dense contraction.
+//
+// GEMM view: D[M, Cout] = A[M, K] * W[Cout, K]^T,  M = N*OH*OW (N counts samples x images),
+//            K = taps * Cin ordered (kh, kw, ci) = NHWC patches.
+//   A is never materialised: for k-block (tap, 64-channel block) the 128 x 64 operand tile is ONE TMA box of
+//   the NHWC activation tensor shifted by the tap offset; out-of-bounds rows/columns are zero-filled by the
+//   TMA unit, which is exactly the convolution's zero padding.
+//     stride 1: 4-D map (C, W, H, N), box (64, tw, th, tn), coords (c0, kw-pad, oh0+kh-pad, n0)
+//     stride 2: the same memory viewed as 5-D (2C, W/2, 2, H/2, N) (parity planes); a stride-2 tap is a
+//               dense box of one (row parity, column parity) plane: box (64, tw, 1, th, tn)
+//   Tiles are 128 consecutive output pixels (tw = OW, th rows, tn images) x BN output channels.
+//
+// CTA = 6 warps, persistent over tiles:
+//   warp 0  : TMA producer (one elected lane) - A box + W box per k-block into a STAGES-deep smem ring
+//   warp 1  : TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators
+//             in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5: epilogue - tcgen05.ld 32 lanes x 32 columns -> + folded-BN bias -> + residual -> ReLU ->
+//             Philox dropout / Masksembles mask -> 16-bit pack -> 64-byte row stores
+#include <cuda.h>
+
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+
 #include "common.cuh"
-extern "C" int bnn_conv2d_tc(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int,
-                             int, int, int, const bnn_drop_desc*, void*) {
-  bnn::set_error("bnn_conv2d_tc: not built");
+#include "philox.cuh"
+
+namespace bnn {
+namespace tc {
+
+constexpr int BM = 128;          // rows (output pixels) per tile
+constexpr int BK = 64;           // K elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+__host__ __device__ constexpr int stages_for(int bn) { return bn == 256 ? 4 : (bn == 128 ? 6 : 8); }
+__host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * BK * 2; }
+__host__ __device__ constexpr int smem_bytes(int bn) {
+  return stages_for(bn) * (A_TILE_BYTES + b_tile_bytes(bn)) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+struct Params {
+  int M, Cout, n_tiles_n, num_tiles;
+  int taps, cblocks, Cin, stride, pad;
+  int OH, OW, OHW;
+  int relu;
+  const float* bias;
+  const void* res;
+  void* y;
+  DropParams dp;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 / bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // bits  0-13 start address >> 4
+  d |= (uint64_t)0 << 16;                           // bits 16-29 leading byte offset (unused: swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // bits 32-45 stride byte offset = 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                           // bits 46-47 descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // bits 61-63 layout: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor for kind::f16: fp32 accumulator, A/B type, both K-major, M = 128, N = BN
+template <typename T>
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  const uint32_t ab = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = f16, 1 = bf16
+  return (1u << 4)                 // D format f32
+         | (ab << 7) | (ab << 10)  // A, B format
+         | (0u << 15) | (0u << 16) // A, B K-major
+         | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, typename T>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  constexpr int STAGES = stages_for(BN);
+  constexpr int B_TILE = b_tile_bytes(BN);
+  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;
+  constexpr int TMEM_COLS = 2 * BN;                 // double-buffered accumulator (power of two >= 32)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = p.taps * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);                 // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+        const int m0 = m_tile * BM;
+        const int img0 = m0 / p.OHW;
+        const int oh0 = (m0 - img0 * p.OHW) / p.OW;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            uint8_t* a_dst = smem_a + stage * A_TILE_BYTES;
+            if (p.stride == 1) {
+              tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, kw - p.pad, oh0 + kh - p.pad, img0);
+            } else {
+              // input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
+              const int rh = kh - p.pad, rw = kw - p.pad;                 // -1, 0, +1  (0 only for 1x1)
+              const int hp = rh & 1, dh = (rh - hp) >> 1;                 // -1 -> (1, -1); 0 -> (0, 0); 1 -> (1, 0)
+              const int wp = rw & 1, dw = (rw - wp) >> 1;
+              tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0 + dh, img0);
+            }
+            tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK, n_tile * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<T>(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_TILE_BYTES));
+          const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);                     // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                               // TMEM lane group this warp may access
+    const int row = q * 32 + lane;
+    T* __restrict__ y = reinterpret_cast<T*>(p.y);
+    const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+      const int m = m_tile * BM + row;
+      const int n0 = n_tile * BN;
+      const bool valid = m < p.M;
+      // stochastic-site coordinates of this output pixel
+      int s_local = 0;
+      uint64_t e_base = 0;
+      if (p.dp.kind != BNN_DROP_NONE && valid) {
+        const int img = m / p.OHW;
+        s_local = img / p.dp.batch;
+        const int b = img - s_local * p.dp.batch;
+        const int pix = m - img * p.OHW;
+        e_base = p.dp.kind == BNN_DROP_CHANNEL ? (uint64_t)b * p.Cout : ((uint64_t)b * p.OHW + pix) * (uint64_t)p.Cout;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(ch * 32), v);
+        tmem_ld_wait();
+        if (valid) {
+          const int c0 = n0 + ch * 32;
+          const size_t off = (size_t)m * p.Cout + c0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (res != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + off + j));
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 a = unpack2<T>(rw[t]);
+                f[j + 2 * t] += a.x;
+                f[j + 2 * t + 1] += a.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.dp.kind == BNN_DROP_ELEMENT || p.dp.kind == BNN_DROP_CHANNEL) {
+            const uint64_t blk0 = (e_base + (uint64_t)c0) >> 2;      // c0 % 32 == 0 and Cout % 64 == 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 r = philox_block(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, blk0 + j);
+              f[4 * j] *= (p.dp.scale != 0.f && r.x >= p.dp.thr) ? p.dp.scale : 0.f;
+              f[4 * j + 1] *= (p.dp.scale != 0.f && r.y >= p.dp.thr) ? p.dp.scale : 0.f;
+              f[4 * j + 2] *= (p.dp.scale != 0.f && r.z >= p.dp.thr) ? p.dp.scale : 0.f;
+              f[4 * j + 3] *= (p.dp.scale != 0.f && r.w >= p.dp.thr) ? p.dp.scale : 0.f;
+            }
+          } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
+            const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
+            const float* mk = p.dp.masks + (size_t)mrow * p.Cout + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + j));
+              f[j] *= m4.x;
+              f[j + 1] *= m4.y;
+              f[j + 2] *= m4.z;
+              f[j + 3] *= m4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            o.x = pack2<T>(f[j], f[j + 1]);
+            o.y = pack2<T>(f[j + 2], f[j + 3]);
+            o.z = pack2<T>(f[j + 4], f[j + 5]);
+            o.w = pack2<T>(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(y + off + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return BNN_E_CUDA;
+  }
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == BNN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return BNN_E_CUDA;
+  }
+  return BNN_OK;
+}
+
+template <int BN, typename T>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
+  static bool configured = false;
+  constexpr int smem = smem_bytes(BN);
+  if (!configured) {
+    BNN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_tc_kernel<BN, T><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace tc
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype,
+                             int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
+                             const bnn_drop_desc* drop, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && w && bias && y, "bnn_conv2d_tc: null pointer");
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_conv2d_tc: dtype must be float16 or bfloat16");
+  BNN_REQUIRE(N >= 0 && H > 0 && W > 0, "bnn_conv2d_tc: bad geometry");
+  const int pad = ksize == 3 ? 1 : 0;
+  const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
+  const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && Cout % 64 == 0 &&
+                  (stride == 1 || (H % 2 == 0 && W % 2 == 0)) && tc::pow2(OW) && tc::pow2(OH) && OW <= 128;
+  if (!ok) {
+    set_error("bnn_conv2d_tc: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", ksize, stride,
+              Cin, Cout, H, W);
+    return BNN_E_UNSUPPORTED;
+  }
+  if (drop && drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->batch > 0 && N % drop->batch == 0, "bnn_conv2d_tc: N=%d not a multiple of batch=%d", N,
+                drop->batch);
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_conv2d_tc: Masksembles site without a mask table");
+  }
+  if (N == 0) return BNN_OK;
+  BNN_REQUIRE((int64_t)N * OH * OW < (int64_t)1 << 31, "bnn_conv2d_tc: M overflows int32");
+
+  // tile geometry: 128 consecutive output pixels = tn images x th rows x OW columns
+  const int tw = OW;
+  const int th = OH < tc::BM / tw ? OH : tc::BM / tw;
+  const int tn = tc::BM / (tw * th);
+
+  CUtensorMap ta, tb;
+  const cuuint64_t eb = 2;
+  if (stride == 1) {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)H * W * Cin * eb};
+    const cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    if (int rc = tc::encode_map(&ta, dtype, 4, x, dims, strides, box)) return rc;
+  } else {
+    const cuuint64_t dims[5] = {(cuuint64_t)2 * Cin, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+    const cuuint64_t strides[4] = {(cuuint64_t)2 * Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)2 * W * Cin * eb,
+                                   (cuuint64_t)H * W * Cin * eb};
+    const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
+    if (int rc = tc::encode_map(&ta, dtype, 5, x, dims, strides, box)) return rc;
+  }
+  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  {
+    const int K = ksize * ksize * Cin;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)BN};
+    if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
+  }
+
+  tc::Params p{};
+  p.M = N * OH * OW;
+  p.Cout = Cout;
+  p.n_tiles_n = Cout / BN;
+  p.num_tiles = ((p.M + tc::BM - 1) / tc::BM) * p.n_tiles_n;
+  p.taps = ksize * ksize;
+  p.cblocks = Cin / tc::BK;
+  p.Cin = Cin;
+  p.stride = stride;
+  p.pad = pad;
+  p.OH = OH;
+  p.OW = OW;
+  p.OHW = OH * OW;
+  p.relu = relu;
+  p.bias = bias;
+  p.res = res;
+  p.y = y;
+  p.dp = make_drop_params(drop, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+
+#define BNN_TC_DISPATCH(BN_)                                                      \
+  case BN_:                                                                       \
+    return dtype == BNN_F16 ? tc::launch<BN_, __half>(ta, tb, p, st)              \
+                            : tc::launch<BN_, __nv_bfloat16>(ta, tb, p, st);
+  switch (BN) {
+    BNN_TC_DISPATCH(256)
+    BNN_TC_DISPATCH(128)
+    BNN_TC_DISPATCH(64)
+  }
+#undef BNN_TC_DISPATCH
   return BNN_E_UNSUPPORTED;
 }

@@ -240,15 +240,19 @@ class Engine:
         # BNN_DISABLE_TC=1 routes the 16-bit path through the CUDA-core kernel too (debugging aid)
         self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
         self.launches = 0
+        self._prof = None
         self._bufs = {}
         self._prepare_weights()
 
     # ---- plan-time weight packing -----------------------------------------------------------
     def _tc_eligible(self, op):
+        """Same rule as bnn_conv2d_tc (conv_tc.cu): decided at plan time, never a silent run-time fallback."""
         kh, kw = op.ksize
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
         return (self.use_tc and kh == kw and ((kh == 3 and op.pad == 1) or (kh == 1 and op.pad == 0))
                 and op.stride in (1, 2) and op.src.C % 64 == 0 and op.dst.C % 64 == 0
-                and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0)))
+                and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0))
+                and pow2(op.dst.H) and pow2(op.dst.W) and op.dst.W <= 128)
 
     def _prepare_weights(self):
         dev = self.device
@@ -320,6 +324,18 @@ class Engine:
         s = st["sums"]
         return s[:n].view(E, B, C), s[n:2 * n].view(E, B, C), s[2 * n:].view(E, B)
 
+    def _launch(self, kernel, name, flops, nbytes, call):
+        """One C-ABI launch; with profiling on, bracket it with CUDA events on the launching stream."""
+        if self._prof is None:
+            _lib.check(call())
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(call())
+            e1.record()
+            self._prof.append((kernel, name, flops, nbytes, e0, e1))
+        self.launches += 1
+
     def enqueue(self, x, S_local, sample0=0, seed=0x5EED, accumulate=False, want_logits=False, mask_offset=None):
         """Enqueue the whole pass for local samples [sample0, sample0 + S_local) on the current
         stream. Returns the buffer set (sums are in st['sums'])."""
@@ -336,9 +352,10 @@ class Engine:
         st["x"].copy_(x, non_blocking=True)
         if B == 0:
             return st
-        _lib.check(lib.bnn_nchw_to_nhwc(_ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C,
-                                         g.input.H, g.input.W, stream))
-        self.launches += 1
+        es = 4 if self.dtype_name == "fp32" else 2
+        n_in = B * g.input.C * g.input.H * g.input.W
+        self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc(
+            _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W, stream))
         sum_p, sum_l, sum_pl = self.sums_views(st, B)
         for op in g.ops:
             if op.kind == "conv":
@@ -352,45 +369,67 @@ class Engine:
                 if op.res is not None and op.dst.stoch and not op.res.stoch:
                     raise NotImplementedError("conv %s: deterministic residual into stochastic output" % op.name)
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                kh, kw = op.ksize
+                out_px = n_img * op.dst.H * op.dst.W
+                flops = 2 * out_px * op.dst.C * op.src.C * kh * kw
+                nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * op.dst.C * (2 if res is not None else 1)) * es \
+                    + op.d_w.numel() * op.d_w.element_size()
                 if op.use_tc:
-                    rc = lib.bnn_conv2d_tc(_ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]),
-                                           self.dcode, n_img, op.src.H, op.src.W, op.src.C, op.dst.C, op.ksize[0],
-                                           op.stride, int(op.relu), ctypes.byref(dd), stream)
+                    call = lambda: lib.bnn_conv2d_tc(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd), stream)
                 else:
-                    rc = lib.bnn_conv2d_simt(_ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]),
-                                             self.dcode, n_img, op.src.H, op.src.W, op.src.C, op.dst.C,
-                                             op.ksize[0], op.ksize[1], op.stride, op.pad, int(op.relu),
-                                             ctypes.byref(dd), stream)
-                _lib.check(rc)
-                self.launches += 1
+                    call = lambda: lib.bnn_conv2d_simt(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, kw, op.stride, op.pad, int(op.relu),
+                        ctypes.byref(dd), stream)
+                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name, flops, nbytes, call)
             elif op.kind == "site":
                 if S_local == 0:
                     continue
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
                 per_image = op.src.H * op.src.W * op.src.C
-                _lib.check(lib.bnn_dropout(_ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, per_image,
-                                           op.src.C, S_local, int(op.src.stoch), ctypes.byref(dd), stream))
-                self.launches += 1
+                nbytes = B * per_image * es * ((S_local if op.src.stoch else 1) + S_local)
+                self._launch("dropout", op.name, 0, nbytes, lambda: lib.bnn_dropout(
+                    _ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, per_image, op.src.C, S_local,
+                    int(op.src.stoch), ctypes.byref(dd), stream))
             elif op.kind == "maxpool":
                 n_img = (S_local if op.dst.stoch else 1) * B
                 if n_img == 0:
                     continue
-                _lib.check(lib.bnn_maxpool2d(_ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, n_img,
-                                             op.src.H, op.src.W, op.src.C, op.pool_k, stream))
-                self.launches += 1
+                nbytes = n_img * op.src.C * (op.src.H * op.src.W + op.dst.H * op.dst.W) * es
+                self._launch("maxpool", op.name, 0, nbytes, lambda: lib.bnn_maxpool2d(
+                    _ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, n_img, op.src.H, op.src.W, op.src.C,
+                    op.pool_k, stream))
             elif op.kind == "head":
                 e = op.exit_index
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
                 lo = st["logits"]
-                # per-sample logits are written [S_local][B][C] per exit; we keep one [S, B, C] slab per
-                # exit and permute on return
-                lo_e = lo.view(-1)[e * S_local * B * g.n_classes:] if lo is not None else None
-                _lib.check(lib.bnn_exit_head(_ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local,
-                                             op.src.H * op.src.W, op.src.C, g.n_classes, _ptr(op.d_w), _ptr(op.d_b),
-                                             ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
-                                             _ptr(lo_e), int(accumulate), stream))
-                self.launches += 1
+                # per-sample logits: one [S_local][B][C] slab per exit
+                lo_e = lo[e] if lo is not None else None
+                hw = op.src.H * op.src.W
+                nbytes = (S_local if op.src.stoch else 1) * B * hw * op.src.C * es + op.d_w.numel() * 4
+                flops = 2 * S_local * B * op.src.C * g.n_classes
+                self._launch("exit_head", op.name, flops, nbytes, lambda: lib.bnn_exit_head(
+                    _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
+                    _ptr(op.d_w), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
+                    _ptr(lo_e), int(accumulate), stream))
         return st
+
+    def profile_step(self, x, S_local, seed=0x5EED):
+        """Device time of every launch of one step (CUDA events on the launching stream).
+        -> list of {kernel, name, ms, flops (algorithmic), bytes (algorithmic)} in launch order."""
+        x = x.to(self.device, torch.float32)
+        with torch.cuda.device(self.device):
+            self._prof = []
+            try:
+                st = self.enqueue(x, S_local, 0, seed)
+                self.finalize(st, x.shape[0], max(S_local, 1))
+                torch.cuda.synchronize(self.device)
+                rec = self._prof
+            finally:
+                self._prof = None
+        return [{"kernel": k, "name": n, "flops": f, "bytes": b, "ms": e0.elapsed_time(e1)} for k, n, f, b, e0, e1 in rec]
 
     def finalize(self, st, B, S_total):
         g = self.graph

@@ -186,3 +186,56 @@ def test_calibration_bins_and_ece(lib):
         assert abs(got - float(z["ece%d" % k])) < 1e-4            # reference's own ece_hist_binary value
         assert abs(fa.ece_width(p, lab) - stats.ece_width(p.astype(np.float32), lab)) < 1e-5
     assert fa.ece_width(np.zeros((0, 10)), np.zeros(0, dtype=np.int64)) == 0.0        # empty dataset
+
+
+TC_SHAPES = [
+    # N, H, W, Cin, Cout, k, stride, pad, relu, res
+    (8, 32, 32, 64, 64, 3, 1, 1, True, True),       # layer1 conv (BN = 64)
+    (4, 32, 32, 64, 128, 3, 2, 1, True, False),     # layer2.0.conv1 / ex1conv1: stride 2 through parity planes
+    (4, 32, 32, 64, 128, 1, 2, 0, False, False),    # 1x1 stride-2 shortcut
+    (4, 16, 16, 128, 128, 3, 1, 1, True, True),     # layer2 conv + residual
+    (16, 8, 8, 256, 256, 3, 1, 1, True, True),      # layer3 (BN = 256), two images per tile
+    (40, 4, 4, 512, 512, 3, 1, 1, True, True),      # layer4: 8 images per tile, two N tiles
+    (3, 8, 8, 128, 256, 3, 2, 1, True, False),      # M = 48 < one tile, box larger than the tensor
+    (130, 2, 2, 512, 512, 3, 1, 1, True, False),    # VGG block 3 (2x2 maps)
+    (300, 1, 1, 512, 512, 3, 1, 1, True, False),    # VGG block 4 (1x1 maps: only the centre tap is in bounds)
+    (6, 4, 4, 256, 512, 3, 2, 1, True, False),      # VGG ex3 feature extractor
+    (2, 64, 64, 64, 64, 3, 1, 1, False, False),     # wider image: 2 rows per tile
+]
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_matches_fp64_conv_of_the_rounded_operands(lib, shape, dt):
+    got, want = _conv_case(lib, "tc", dt, *shape)
+    err = (got.double() - want).abs().max().item()
+    scale = max(1.0, want.abs().max().item())
+    report(test="conv_tc", dtype=dt, shape=list(shape), max_err=err, scale=scale)
+    # fp32 accumulation of exact 16-bit products + one rounding of the output to 16-bit storage
+    assert err <= (1e-3 if dt == "fp16" else 8e-3) * scale
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_conv_tc_fused_site(lib, kind):
+    N_img, B, S, C, HW = 12, 4, 3, 128, 8
+    masks = (torch.rand(4, C) > 0.5).float().cuda()
+    dd = drop_desc(kind, 0.5, 0x77, 4, 5, B, masks if kind == 3 else None, cnt0=2)
+    got, want = _conv_case(lib, "tc", "fp16", N_img, HW, HW, 64, C, 3, 1, 1, True, False, drop=dd)
+    for s in range(S):
+        if kind == 3:
+            f = masks[(2 + 5 + s) % 4].cpu().view(1, C, 1, 1).double()
+        else:
+            keep = philox.keep_mask(0x77, 4, 5 + s, (B, C, HW, HW), 0.5, "channel" if kind == 2 else "element")
+            f = torch.from_numpy(keep).double() * 2.0
+        ref = want[s * B:(s + 1) * B] * f
+        assert (got[s * B:(s + 1) * B].double() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_tc_rejects_unsupported_geometry(lib):
+    y = torch.zeros(64, device="cuda", dtype=torch.float16)
+    dd = drop_desc(batch=1)
+    args = lambda cin, cout, k, h: (y.data_ptr(), y.data_ptr(), y.data_ptr(), None, y.data_ptr(), 1, 1, h, h, cin,
+                                    cout, k, 1, 0, ctypes.byref(dd), stream())
+    assert lib.bnn_conv2d_tc(*args(3, 64, 3, 32)) == -4         # Cin % 64 != 0 -> use the CUDA-core kernel
+    assert lib.bnn_conv2d_tc(*args(64, 64, 5, 32)) == -4        # 5x5
+    assert lib.bnn_conv2d_tc(*args(64, 64, 3, 12)) == -4        # 12x12 output rows do not tile 128
