@@ -21,6 +21,7 @@
 //   warps 2-5: epilogue - tcgen05.ld 32 lanes x 32 columns -> + folded-BN bias -> + residual -> ReLU ->
 //             Philox dropout / Masksembles mask -> 16-bit pack -> 64-byte row stores
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <type_traits>
@@ -35,13 +36,18 @@ namespace tc {
 constexpr int BM = 128;          // rows (output pixels) per tile
 constexpr int BK = 64;           // K elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
-__host__ __device__ constexpr int stages_for(int bn) { return bn == 256 ? 4 : (bn == 128 ? 6 : 8); }
 __host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * BK * 2; }
-__host__ __device__ constexpr int smem_bytes(int bn) {
-  return stages_for(bn) * (A_TILE_BYTES + b_tile_bytes(bn)) + 1024 /*align slack*/ + 256 /*barriers*/;
+// as many pipeline stages as fit in ~200 KB of shared memory (at most 8)
+__host__ __device__ constexpr int stages_for(int bn, int mt) {
+  return (200 * 1024) / (mt * A_TILE_BYTES + b_tile_bytes(bn)) > 8 ? 8
+                                                                  : (200 * 1024) / (mt * A_TILE_BYTES + b_tile_bytes(bn));
+}
+__host__ __device__ constexpr int smem_bytes(int bn, int mt) {
+  return stages_for(bn, mt) * (mt * A_TILE_BYTES + b_tile_bytes(bn)) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 struct Params {
@@ -176,18 +182,26 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, typename T>
+// SWAP (BN == 128, MT == 2): the roles of the operands are exchanged - the 128 x 64 weight tile is the MMA's
+// A operand (M = 128 output channels) and the 256 x 64 pixel tile its B operand (N = 256), so that Cout = 128
+// layers also issue 128 x 256 x 16 MMAs (a 128 x 128 MMA re-reads its operands from shared memory twice as often
+// per FLOP and measured ~55% tensor-pipe utilisation).  The accumulator is then D^T: TMEM lanes = channels,
+// columns = pixels, and the epilogue writes 2-byte elements that coalesce across the warp's 32 channels.
+template <int BN, int MT, bool SWAP, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  constexpr int STAGES = stages_for(BN);
+  constexpr int STAGES = stages_for(BN, MT);
+  constexpr int A_STAGE = MT * A_TILE_BYTES;
   constexpr int B_TILE = b_tile_bytes(BN);
-  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;
-  constexpr int TMEM_COLS = 2 * BN;                 // double-buffered accumulator (power of two >= 32)
+  constexpr int STAGE_BYTES = A_STAGE + B_TILE;
+  constexpr int ACC_COLS = MT * BN;                 // one accumulator set: MT row-tiles of BN columns
+  constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered (power of two, <= 512)
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+  uint8_t* smem_b = smem + STAGES * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -207,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);                 // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], EPI_WARPS);         // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -224,23 +238,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
-        const int m0 = m_tile * BM;
-        const int img0 = m0 / p.OHW;
-        const int oh0 = (m0 - img0 * p.OHW) / p.OW;
+        int img0[MT], oh0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          int m0 = (m_tile * MT + mt) * BM;
+          if (m0 >= p.M) m0 = m_tile * MT * BM;       // row-tile past the end: reload the first one, never stored
+          img0[mt] = m0 / p.OHW;
+          oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
+          // stride 2: input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
+          const int rh = kh - p.pad, rw = kw - p.pad;                 // -1, 0, +1  (0 only for 1x1)
+          const int hp = rh & 1, dh = (rh - hp) >> 1;                 // -1 -> (1, -1); 0 -> (0, 0); 1 -> (1, 0)
+          const int wp = rw & 1, dw = (rw - wp) >> 1;
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            uint8_t* a_dst = smem_a + stage * A_TILE_BYTES;
-            if (p.stride == 1) {
-              tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, kw - p.pad, oh0 + kh - p.pad, img0);
-            } else {
-              // input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
-              const int rh = kh - p.pad, rw = kw - p.pad;                 // -1, 0, +1  (0 only for 1x1)
-              const int hp = rh & 1, dh = (rh - hp) >> 1;                 // -1 -> (1, -1); 0 -> (0, 0); 1 -> (1, 0)
-              const int wp = rw & 1, dw = (rw - wp) >> 1;
-              tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0 + dh, img0);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
+              if (p.stride == 1)
+                tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+              else
+                tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
             }
             tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK, n_tile * BN);
             if (++stage == STAGES) {
@@ -254,24 +275,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<T>(BN);
+      constexpr uint32_t idesc = make_idesc<T>(SWAP ? MT * BM : BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_TILE_BYTES));
-          const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
+          const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
+          if (SWAP) {
+            // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
+            const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+              }
+            }
           }
           umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
           if (++stage == STAGES) {
@@ -279,101 +312,214 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);                     // accumulator complete -> epilogue
+        umma_commit(&tmem_full[acc]);                     // accumulators complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                               // TMEM lane group this warp may access
-    const int row = q * 32 + lane;
+    // ===================== epilogue (warps 2..9) =====================
+    // warp w may touch TMEM lanes 32*(w%4)..+31; two warps share a lane group and split the columns.
+    constexpr int NCH = BN / 64;                          // 32-column chunks per warp (non-swapped layout)
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;                       // which half of the columns
     T* __restrict__ y = reinterpret_cast<T*>(p.y);
     const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (SWAP) {
+      // ---- transposed accumulator: this thread owns output channel c, TMEM columns are pixels ----
+      // Host guarantees Cout == BN (one channel tile) so every row stride is the compile-time constant BN,
+      // which keeps this fully unrolled loop small (the first version, with run-time strides and per-pixel
+      // 64-bit address arithmetic, was 100 KB of code and instruction-cache bound).
+      constexpr int PX = MT * BM;                         // pixels per tile (256)
+      constexpr int PCH = PX / 64;                        // 32-pixel chunks per warp
+      const uint16_t* __restrict__ res16 = reinterpret_cast<const uint16_t*>(p.res);
+      uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.y);
+      const int64_t sample_px = (int64_t)p.dp.batch * p.OHW;          // pixels per MC sample
+      const int c = q * 32 + lane;
+      const float bias_c = __ldg(p.bias + c);
+      const bool has_res = res16 != nullptr;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_base = tile * PX + hf * (PX / 2);
+        if (has_res) {
+          // pull this warp's residual rows (32 channels = 64 bytes per pixel) into L2 while the MMAs of this tile
+          // are still running: lane l touches pixels l, l+32, l+64, l+96 of the warp's 128-pixel half
+#pragma unroll
+          for (int i = 0; i < PX / 64; ++i) {
+            const int m = m_base + i * 32 + lane;
+            if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(res16 + (size_t)m * BN + q * 32));
+          }
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + hf * (PX / 2));
+#pragma unroll 1
+        for (int ch = 0; ch < PCH; ++ch) {
+          const int m0 = m_base + ch * 32;
+          const int nvalid = p.M - m0;                    // pixels of this chunk that exist (may be <= 0)
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)(ch * 32), v);
+          const size_t off0 = (size_t)m0 * BN + c;
+          // stochastic site: one Philox block covers 8 consecutive channels of one pixel. Lane (c & 7) draws the
+          // blocks of pixels j = (c & 7) + 8t (t < 4) for its channel octet and packs the 8 keep bits of each into
+          // one word; 8 shuffles hand every lane the bits of its own channel
+          uint32_t kw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+                            0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          float fac = 1.f;
+          if (p.dp.kind == BNN_DROP_ELEMENT) {
+            // a 32-pixel chunk lies inside one MC sample whenever sample_px % 32 == 0 (host-checked)
+            const uint32_t s_local = (uint32_t)((int64_t)m0 / sample_px);
+            const uint64_t px0 = (uint64_t)((int64_t)m0 - (int64_t)s_local * sample_px) + (uint64_t)(lane & 7);
+            uint32_t bits = 0;
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+              const uint64_t e = (px0 + 8 * t) * (uint64_t)BN + (uint64_t)(c & ~7);
+              bits |= philox_keep8(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, e >> 3, p.dp.thr) << (8 * t);
+            }
+            if (p.dp.scale == 0.f) bits = 0;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) kw[sl] = __shfl_sync(0xffffffffu, bits, (lane & ~7) | sl);
+            fac = p.dp.scale;
+          } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
+            // host guarantees sample_px % 32 == 0: a 32-pixel chunk never straddles two samples
+            const int64_t s_local = (int64_t)m0 / sample_px;
+            const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
+            fac = __ldg(p.dp.masks + (size_t)mrow * BN + c);
+          }
+          const uint16_t* rp = res16 + off0;
+          uint16_t* yp = y16 + off0;
+          // all 32 residual loads are issued together (each is a 64-byte coalesced warp access), then consumed
+          uint32_t rr[32];
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = (j < nvalid) ? (uint32_t)__ldg(rp + j * BN) : 0u;
+          }
+          tmem_ld_wait();
+          if (nvalid > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + bias_c;
+              if (has_res) f += unpack2<T>(rr[j]).x;
+              if (p.relu) f = fmaxf(f, 0.f);
+              f *= ((kw[j & 7] >> (8 * (j >> 3) + (lane & 7))) & 1u) ? fac : 0.f;
+              if (j < nvalid) yp[j * BN] = (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
-      const int m = m_tile * BM + row;
-      const int n0 = n_tile * BN;
-      const bool valid = m < p.M;
-      // stochastic-site coordinates of this output pixel
-      int s_local = 0;
-      uint64_t e_base = 0;
-      if (p.dp.kind != BNN_DROP_NONE && valid) {
-        const int img = m / p.OHW;
-        s_local = img / p.dp.batch;
-        const int b = img - s_local * p.dp.batch;
-        const int pix = m - img * p.OHW;
-        e_base = p.dp.kind == BNN_DROP_CHANNEL ? (uint64_t)b * p.Cout : ((uint64_t)b * p.OHW + pix) * (uint64_t)p.Cout;
+      const int cbase = n_tile * BN + hf * (BN / 2);      // first output channel of this warp
+
+      // residual rows are fetched BEFORE waiting for the accumulator: the DRAM latency hides behind the MMAs
+      uint4 rpre[MT][NCH][4];
+      if (res != nullptr) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+          if (m < p.M) {
+            const uint4* src = reinterpret_cast<const uint4*>(res + (size_t)m * p.Cout + cbase);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rpre[mt][ch][j] = __ldg(src + ch * 4 + j);
+          }
+        }
       }
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)(ch * 32), v);
-        tmem_ld_wait();
-        if (valid) {
-          const int c0 = n0 + ch * 32;
-          const size_t off = (size_t)m * p.Cout + c0;
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (res != nullptr) {
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+        const bool valid = m < p.M;
+        // stochastic-site coordinates of this output pixel
+        int s_local = 0;
+        uint64_t e_base = 0;
+        if (p.dp.kind != BNN_DROP_NONE && valid) {
+          const int img = m / p.OHW;
+          s_local = img / p.dp.batch;
+          const int b = img - s_local * p.dp.batch;
+          const int pix = m - img * p.OHW;
+          e_base =
+              p.dp.kind == BNN_DROP_CHANNEL ? (uint64_t)b * p.Cout : ((uint64_t)b * p.OHW + pix) * (uint64_t)p.Cout;
+        }
+        const uint32_t t_row =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * BN + hf * (BN / 2));
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + off + j));
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + (uint32_t)(ch * 32), v);
+          const int c0 = cbase + ch * 32;
+          float4 bia[8];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 a = unpack2<T>(rw[t]);
-                f[j + 2 * t] += a.x;
-                f[j + 2 * t + 1] += a.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.dp.kind == BNN_DROP_ELEMENT || p.dp.kind == BNN_DROP_CHANNEL) {
-            const uint64_t blk0 = (e_base + (uint64_t)c0) >> 2;      // c0 % 32 == 0 and Cout % 64 == 0
+          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+          tmem_ld_wait();
+          if (valid) {
+            const size_t off = (size_t)m * p.Cout + c0;
+            float f[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint4 r = philox_block(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, blk0 + j);
-              f[4 * j] *= (p.dp.scale != 0.f && r.x >= p.dp.thr) ? p.dp.scale : 0.f;
-              f[4 * j + 1] *= (p.dp.scale != 0.f && r.y >= p.dp.thr) ? p.dp.scale : 0.f;
-              f[4 * j + 2] *= (p.dp.scale != 0.f && r.z >= p.dp.thr) ? p.dp.scale : 0.f;
-              f[4 * j + 3] *= (p.dp.scale != 0.f && r.w >= p.dp.thr) ? p.dp.scale : 0.f;
+              f[4 * j] = __uint_as_float(v[4 * j]) + bia[j].x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
             }
-          } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
-            const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
-            const float* mk = p.dp.masks + (size_t)mrow * p.Cout + c0;
+            if (res != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + j));
-              f[j] *= m4.x;
-              f[j + 1] *= m4.y;
-              f[j + 2] *= m4.z;
-              f[j + 3] *= m4.w;
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r = rpre[mt][ch][j];
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 a = unpack2<T>(rw[t]);
+                  f[8 * j + 2 * t] += a.x;
+                  f[8 * j + 2 * t + 1] += a.y;
+                }
+              }
             }
-          }
+            if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack2<T>(f[j], f[j + 1]);
-            o.y = pack2<T>(f[j + 2], f[j + 3]);
-            o.z = pack2<T>(f[j + 4], f[j + 5]);
-            o.w = pack2<T>(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(y + off + j) = o;
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.dp.kind == BNN_DROP_ELEMENT || p.dp.kind == BNN_DROP_CHANNEL) {
+              const uint64_t blk0 = (e_base + (uint64_t)c0) >> 3;      // c0 % 32 == 0 and Cout % 64 == 0
+              // rolled loop (keeps the kernel inside the instruction cache): 4 Philox blocks -> 32 keep bits
+              uint32_t bits = 0;
+#pragma unroll 1
+              for (int j = 0; j < 4; ++j)
+                bits |= philox_keep8(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, blk0 + j, p.dp.thr) << (8 * j);
+              if (p.dp.scale == 0.f) bits = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= ((bits >> j) & 1u) ? p.dp.scale : 0.f;
+            } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
+              const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
+              const float* mk = p.dp.masks + (size_t)mrow * p.Cout + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + j));
+                f[j] *= m4.x;
+                f[j + 1] *= m4.y;
+                f[j + 2] *= m4.z;
+                f[j + 3] *= m4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack2<T>(f[j], f[j + 1]);
+              o.y = pack2<T>(f[j + 2], f[j + 3]);
+              o.z = pack2<T>(f[j + 4], f[j + 5]);
+              o.w = pack2<T>(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(y + off + j) = o;
+            }
           }
         }
       }
@@ -432,16 +578,18 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, typename T>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
+template <int BN, int MT, bool SWAP, typename T>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
   static bool configured = false;
-  constexpr int smem = smem_bytes(BN);
+  constexpr int smem = smem_bytes(BN, MT);
   if (!configured) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BNN_CUDA_OK(
+        cudaFuncSetAttribute(conv_tc_kernel<BN, MT, SWAP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  p.num_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * p.n_tiles_n;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_tc_kernel<BN, T><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  conv_tc_kernel<BN, MT, SWAP, T><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
   BNN_LAUNCH_OK();
   return BNN_OK;
 }
@@ -527,14 +675,22 @@ extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, co
   p.dp = make_drop_params(drop, Cout);
   cudaStream_t st = (cudaStream_t)stream;
 
-#define BNN_TC_DISPATCH(BN_)                                                      \
-  case BN_:                                                                       \
-    return dtype == BNN_F16 ? tc::launch<BN_, __half>(ta, tb, p, st)              \
-                            : tc::launch<BN_, __nv_bfloat16>(ta, tb, p, st);
+  // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
+#define BNN_TC_DISPATCH(BN_, MT_, SWAP_)                                                      \
+  case BN_:                                                                                   \
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, __half>(ta, tb, p, st)              \
+                            : tc::launch<BN_, MT_, SWAP_, __nv_bfloat16>(ta, tb, p, st);
+  // channel-wise dropout is not implemented in the transposed epilogue: those (rare) sites take the 128x128 path
+  const bool swap_ok =
+      Cout == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
+      !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
+  if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
+    switch (BN) { BNN_TC_DISPATCH(128, 2, true) }
+  }
   switch (BN) {
-    BNN_TC_DISPATCH(256)
-    BNN_TC_DISPATCH(128)
-    BNN_TC_DISPATCH(64)
+    BNN_TC_DISPATCH(256, 1, false)
+    BNN_TC_DISPATCH(128, 2, false)
+    BNN_TC_DISPATCH(64, 2, false)
   }
 #undef BNN_TC_DISPATCH
   return BNN_E_UNSUPPORTED;

@@ -16,6 +16,11 @@ constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_WARPS = HEAD_THREADS / 32;
 constexpr int HEAD_SCHUNK = 16;  // samples staged in shared memory at a time
 
+template <typename T>
+struct __align__(16) Vec8h {
+  T v[8];
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -57,16 +62,47 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const int ns = min(HEAD_SCHUNK, S_local - s0);
     __syncthreads();
     // ---- phase 1: pooled + masked feature vectors for ns samples -----------------------------
-    for (int idx = tid; idx < ns * F; idx += HEAD_THREADS) {
-      const int sl = idx / F, f = idx - sl * F;
-      const int s = s0 + sl;
-      const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f;
-      float a = 0.f;
-      for (int p = 0; p < HW; ++p) a += to_f32<T>(src[(size_t)p * F]);
-      a *= inv_hw;
-      if (dp.kind != BNN_DROP_NONE)
-        a *= drop_factor(dp, (uint32_t)s, (uint64_t)b * F + f, (uint64_t)b * F + f, f);
-      pooled[sl * F + f] = a;
+    if (F % 8 == 0) {
+      // vector path: a thread owns 8 consecutive features (16-byte loads for 16-bit storage, all HW loads of
+      // one item in flight together) and one Philox block (= 8 elements) per (sample, feature octet)
+      const int octs = F / 8;
+      for (int idx = tid; idx < ns * octs; idx += HEAD_THREADS) {
+        const int sl = idx / octs, f0 = (idx - sl * octs) * 8;
+        const int s = s0 + sl;
+        const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f0;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int p = 0; p < HW; ++p) {
+          const Vec8h<T> v = *reinterpret_cast<const Vec8h<T>*>(src + (size_t)p * F);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] += to_f32<T>(v.v[j]);
+        }
+        uint32_t k8 = 0xffu;
+        float fac = inv_hw;
+        if (dp.kind == BNN_DROP_ELEMENT || dp.kind == BNN_DROP_CHANNEL) {
+          k8 = dp.scale == 0.f ? 0u
+                               : philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, ((uint64_t)b * F + f0) >> 3, dp.thr);
+          fac *= dp.scale;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = ((k8 >> j) & 1u) ? a[j] * fac : 0.f;
+          if (dp.kind == BNN_DROP_MASKSEMBLES) v *= drop_factor(dp, (uint32_t)s, 0, 0, f0 + j);
+          pooled[sl * F + f0 + j] = v;
+        }
+      }
+    } else {
+      for (int idx = tid; idx < ns * F; idx += HEAD_THREADS) {
+        const int sl = idx / F, f = idx - sl * F;
+        const int s = s0 + sl;
+        const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f;
+        float a = 0.f;
+        for (int p = 0; p < HW; ++p) a += to_f32<T>(src[(size_t)p * F]);
+        a *= inv_hw;
+        if (dp.kind != BNN_DROP_NONE)
+          a *= drop_factor(dp, (uint32_t)s, (uint64_t)b * F + f, (uint64_t)b * F + f, f);
+        pooled[sl * F + f] = a;
+      }
     }
     __syncthreads();
     // ---- phase 2: logits[s][c] = bias[c] + <w[c,:], pooled[s,:]>; one warp per class ---------

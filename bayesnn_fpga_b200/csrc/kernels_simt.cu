@@ -74,8 +74,8 @@ __global__ void philox_keep_kernel(uint8_t* out, int64_t count, uint32_t thr, in
                                    uint32_t stream_id, uint32_t sample) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
-  const uint32_t w = philox_word(seed, stream_id, sample, (uint64_t)e);
-  out[e] = (!all_dropped && w >= thr) ? 1 : 0;
+  const uint32_t h = philox_half(seed, stream_id, sample, (uint64_t)e);
+  out[e] = (!all_dropped && h >= thr) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) conv2d_simt_kernel(const T* __restrict__ 
 // stand-alone stochastic layer, with prefix -> S-sample broadcast
 //   y[s][i] = x[(x_has_samples ? s : 0)][i] * factor(s, i),  i in [0, n_per) = B*H*W*C (one sample)
 // HBM-bound: algorithmic bytes = (x_has_samples ? S : 1) * n_per * sizeof(T) read + S * n_per * sizeof(T)
-// written.  Each thread owns 8 consecutive elements (two Philox blocks, 16-byte accesses for 16-bit T)
+// written.  Each thread owns 8 consecutive elements (one Philox block, 16-byte accesses for 16-bit T)
 // and loops over the samples so the broadcast source is read from HBM once.
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -232,24 +232,20 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
       if (x_has_samples) in = *reinterpret_cast<const Vec8<T>*>(xs + v0);
       float f[8];
       if (dp.kind == BNN_DROP_ELEMENT) {
-        const uint4 r0 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (uint64_t)(v0 >> 2));
-        const uint4 r1 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (uint64_t)(v0 >> 2) + 1);
-        const uint32_t wd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const uint32_t k8 = philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, (uint64_t)(v0 >> 3), dp.thr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && wd[j] >= dp.thr) ? dp.scale : 0.f;
+        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && ((k8 >> j) & 1u)) ? dp.scale : 0.f;
       } else if (dp.kind == BNN_DROP_MASKSEMBLES) {
         const int row = (int)(((int64_t)dp.cnt0 + dp.sample0 + s) % dp.n_masks);
         const float4 m0 = __ldg(reinterpret_cast<const float4*>(dp.masks + (size_t)row * C + c0));
         const float4 m1 = __ldg(reinterpret_cast<const float4*>(dp.masks + (size_t)row * C + c0 + 4));
         f[0] = m0.x; f[1] = m0.y; f[2] = m0.z; f[3] = m0.w;
         f[4] = m1.x; f[5] = m1.y; f[6] = m1.z; f[7] = m1.w;
-      } else {  // channel-wise: elements b*C + c0 .. +7 share two Philox blocks (C % 8 == 0)
+      } else {  // channel-wise: elements b*C + c0 .. +7 are one Philox block (C % 8 == 0)
         const uint64_t e = (uint64_t)(b0 * C + c0);
-        const uint4 r0 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, e >> 2);
-        const uint4 r1 = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, (e >> 2) + 1);
-        const uint32_t wd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const uint32_t k8 = philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, e >> 3, dp.thr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && wd[j] >= dp.thr) ? dp.scale : 0.f;
+        for (int j = 0; j < 8; ++j) f[j] = (dp.scale != 0.f && ((k8 >> j) & 1u)) ? dp.scale : 0.f;
       }
       Vec8<T> out;
 #pragma unroll

@@ -2,8 +2,9 @@
 // device functions shared by the stand-alone dropout kernel, the conv epilogues and the exit head.
 //
 // Contract (bit-exact mirror of oracle/philox.py, checked by tests/test_gpu_masks.py):
-//   key = (seed lo, seed hi); counter = (e >> 2 lo, e >> 34, sample, stream); word = out[e & 3]
-//   keep <=> p < 1 && word >= min(rint(p * 2^32), 2^32 - 1)
+//   key = (seed lo, seed hi); counter = (e >> 3 lo, e >> 35, sample, stream): one block covers 8 elements;
+//   element e uses the 16-bit half (e & 1) of word (e >> 1) & 3 (low half first)
+//   keep <=> p < 1 && half >= min(rint(p * 2^16), 2^16 - 1)
 // with e the per-sample element index (NHWC order for 4-D activations, b*F + f for 2-D, b*C + c
 // for channel-wise dropout).  Replaces the torch global RNG behind F.dropout (resnet18.py:210).
 #pragma once
@@ -12,8 +13,8 @@
 namespace bnn {
 
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = rint((double)p * 4294967296.0);
-  if (t > 4294967295.0) t = 4294967295.0;
+  double t = rint((double)p * 65536.0);
+  if (t > 65535.0) t = 65535.0;
   if (t < 0.0) t = 0.0;
   return (uint32_t)t;
 }
@@ -30,16 +31,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// the four words covering elements [4*blk, 4*blk + 3]
+// the four words of block `blk` (raw generator output)
 __device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t blk) {
   return philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), sample, stream),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-__device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t e) {
-  const uint4 r = philox_block(seed, stream, sample, e >> 2);
-  const uint32_t l = (uint32_t)e & 3u;
-  return l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w));
+// 8 keep bits of the elements [8*blk, 8*blk + 7]: bit i <=> element 8*blk + i is kept
+__device__ __forceinline__ uint32_t keep_bits8(const uint4 r, uint32_t thr) {
+  return ((r.x & 0xffffu) >= thr ? 1u : 0u) | ((r.x >> 16) >= thr ? 2u : 0u) | ((r.y & 0xffffu) >= thr ? 4u : 0u) |
+         ((r.y >> 16) >= thr ? 8u : 0u) | ((r.z & 0xffffu) >= thr ? 16u : 0u) | ((r.z >> 16) >= thr ? 32u : 0u) |
+         ((r.w & 0xffffu) >= thr ? 64u : 0u) | ((r.w >> 16) >= thr ? 128u : 0u);
+}
+__device__ __forceinline__ uint32_t philox_keep8(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t blk,
+                                                 uint32_t thr) {
+  return keep_bits8(philox_block(seed, stream, sample, blk), thr);
+}
+
+// the 16-bit draw of one element (generic / scalar paths)
+__device__ __forceinline__ uint32_t philox_half(uint64_t seed, uint32_t stream, uint32_t sample, uint64_t e) {
+  const uint4 r = philox_block(seed, stream, sample, e >> 3);
+  const uint32_t l = ((uint32_t)e >> 1) & 3u;
+  const uint32_t w = l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w));
+  return (e & 1u) ? (w >> 16) : (w & 0xffffu);
 }
 
 // Device-side view of bnn_drop_desc with the derived constants.
@@ -76,7 +90,7 @@ inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
   return q;
 }
 
-// multiplier for one element (slow generic path; the vector paths below amortise Philox over 4)
+// multiplier for one element (slow generic path; the vector paths amortise one Philox block over 8 elements)
 __device__ __forceinline__ float drop_factor(const DropParams& q, uint32_t sample_local, uint64_t e_elem,
                                              uint64_t e_chan, int c) {
   if (q.kind == BNN_DROP_MASKSEMBLES) {
@@ -84,8 +98,8 @@ __device__ __forceinline__ float drop_factor(const DropParams& q, uint32_t sampl
     return __ldg(q.masks + (size_t)row * q.channels + c);
   }
   const uint64_t e = q.kind == BNN_DROP_CHANNEL ? e_chan : e_elem;
-  const uint32_t w = philox_word(q.seed, q.stream_id, q.sample0 + sample_local, e);
-  return (q.scale != 0.f && w >= q.thr) ? q.scale : 0.f;
+  const uint32_t h = philox_half(q.seed, q.stream_id, q.sample0 + sample_local, e);
+  return (q.scale != 0.f && h >= q.thr) ? q.scale : 0.f;
 }
 
 }  // namespace bnn

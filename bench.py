@@ -115,11 +115,18 @@ class ClockSampler:
 
     def __init__(self, device_index):
         self.idx, self.proc, self.lines = device_index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -128,7 +135,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -140,7 +147,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        window = "timed region"
+        if not inside:                       # region shorter than one sampling period: nearest samples
+            inside, window = [ln for (_, ln) in self.lines[-3:]], "nearest samples (timed region < sampling period)"
+        for ln in inside:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -154,8 +165,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "sm_mhz_min": sm[0], "power_w_max": max(pw),
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def load_peaks():
@@ -212,7 +223,7 @@ def reference_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -294,13 +305,15 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(W):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                      # nvidia-smi needs ~1 s to start: launch it before the warm-up
+    for _ in range(W):
+        step_device()
     launches0 = eng.launches
+    sampler.mark_start()
     ms = timed(step_device, args.steps)
+    sampler.mark_end()
     launches = eng.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):

@@ -8,9 +8,12 @@ Philox-4x32-10 (Salmon et al., SC'11), counter-based.
 Contract (mirrored bit-exactly by ``bayesnn_fpga_b200/csrc/philox.cuh``):
 
   key      = (seed & 0xffffffff, seed >> 32)
-  counter  = (e >> 2  [low 32 bits], e >> 34, sample, stream)
-  word     = philox4x32_10(counter, key)[e & 3]
-  keep     = (p < 1) and (word >= thr(p)),   thr(p) = min(rint(p * 2**32), 2**32 - 1)
+  counter  = (e >> 3  [low 32 bits], e >> 35, sample, stream)      one Philox block covers 8 elements
+  half     = 16-bit half (e & 1) of word (e >> 1) & 3 of philox4x32_10(counter, key)   (low half first)
+  keep     = (p < 1) and (half >= thr(p)),   thr(p) = min(rint(p * 2**16), 2**16 - 1)
+
+(16-bit decisions halve the generator cost inside the GEMM epilogues; the drop probability is realised to
+within 2**-17, finer than any dropout rate is ever specified.)
 
 ``e`` is the linear element index of the masked tensor for ONE sample:
   * element-wise dropout on a 4-D activation: NHWC order, e = ((b*H + h)*W + w)*C + c
@@ -61,15 +64,22 @@ def random_words(seed, stream, sample, count):
     return np.stack(r, axis=1).reshape(-1)[:count]
 
 
+def random_halves(seed, stream, sample, count):
+    """``count`` 16-bit draws for element indices 0..count-1: two per 32-bit word, low half first."""
+    w = random_words(seed, stream, sample, (count + 1) // 2)
+    h = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=1).reshape(-1)
+    return h[:count].astype(np.uint32)
+
+
 def threshold(p):
-    """u32 drop threshold: keep iff word >= threshold(p)."""
-    return int(min(np.rint(float(p) * 4294967296.0), 4294967295.0))
+    """16-bit drop threshold: keep iff half >= threshold(p)."""
+    return int(min(np.rint(float(p) * 65536.0), 65535.0))
 
 
 def keep_mask_flat(seed, stream, sample, count, p):
     if p >= 1.0:
         return np.zeros(count, dtype=bool)
-    return random_words(seed, stream, sample, count) >= np.uint32(threshold(p))
+    return random_halves(seed, stream, sample, count) >= np.uint32(threshold(p))
 
 
 def keep_mask(seed, stream, sample, shape, p, mode="element"):

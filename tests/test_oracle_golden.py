@@ -22,7 +22,7 @@ def test_philox_known_answers():
 
 
 def test_philox_thresholds_and_edges():
-    assert philox.threshold(0.0) == 0 and philox.threshold(0.5) == 2 ** 31 and philox.threshold(1.0) == 2 ** 32 - 1
+    assert philox.threshold(0.0) == 0 and philox.threshold(0.5) == 2 ** 15 and philox.threshold(1.0) == 2 ** 16 - 1
     assert philox.keep_mask_flat(1, 2, 3, 1000, 0.0).all()          # p = 0 keeps everything
     assert not philox.keep_mask_flat(1, 2, 3, 1000, 1.0).any()      # p = 1 drops everything (F.dropout -> zeros)
     assert philox.keep_mask_flat(1, 2, 3, 0, 0.5).shape == (0,)     # empty
