@@ -32,16 +32,18 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// dynamic shared memory layout:
-//   pooled[HEAD_SCHUNK][F] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] | red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
+// dynamic shared memory layout (floats):
+//   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
+//   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
-    const float* __restrict__ w, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
+    const float* __restrict__ wt, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
     float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate) {
   extern __shared__ float sm[];
   float* pooled = sm;
-  float* logits = pooled + (size_t)HEAD_SCHUNK * F;
+  float* part = pooled + (size_t)HEAD_SCHUNK * F;
+  float* logits = part + HEAD_THREADS * HEAD_SCHUNK;
   float* acc_p = logits + (size_t)HEAD_SCHUNK * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
         for (int j = 0; j < 8; ++j) {
           float v = ((k8 >> j) & 1u) ? a[j] * fac : 0.f;
           if (dp.kind == BNN_DROP_MASKSEMBLES) v *= drop_factor(dp, (uint32_t)s, 0, 0, f0 + j);
-          pooled[sl * F + f0 + j] = v;
+          pooled[(f0 + j) * HEAD_SCHUNK + sl] = v;
         }
       }
     } else {
@@ -101,21 +103,71 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
         a *= inv_hw;
         if (dp.kind != BNN_DROP_NONE)
           a *= drop_factor(dp, (uint32_t)s, (uint64_t)b * F + f, (uint64_t)b * F + f, f);
-        pooled[sl * F + f] = a;
+        pooled[f * HEAD_SCHUNK + sl] = a;
       }
     }
     __syncthreads();
-    // ---- phase 2: logits[s][c] = bias[c] + <w[c,:], pooled[s,:]>; one warp per class ---------
-    for (int c = warp; c < C; c += HEAD_WARPS) {
-      const float* wr = w + (size_t)c * F;
-      for (int sl = 0; sl < ns; ++sl) {
-        float a = 0.f;
-        for (int f = lane; f < F; f += 32) a = fmaf(__ldg(wr + f), pooled[sl * F + f], a);
-        a = warp_sum(a);
-        if (lane == 0) logits[sl * C + c] = a + __ldg(bias + c);
+    // ---- phase 2: logits[ns x C] = pooled[ns x F] * W^T[F x C] + bias as a register-tiled small GEMM ----
+    // thread = (class cl of a group of Cpad classes, K-split kq): 16 sample accumulators in registers; per f one
+    // coalesced weight load (W^T is [F][C]) and four broadcast LDS.128 of the 16 pooled samples feed 16 FMAs
+    for (int cg0 = 0; cg0 < C; cg0 += HEAD_THREADS) {
+      int cpad = 1;
+      while (cpad < min(C - cg0, HEAD_THREADS)) cpad <<= 1;
+      const int ks = HEAD_THREADS / cpad;
+      const int cl = tid % cpad, kq = tid / cpad;
+      const int c = cg0 + cl;
+      const int fk = (F + ks - 1) / ks;
+      const int f_lo = kq * fk, f_hi = min(F, f_lo + fk);
+      float accs[HEAD_SCHUNK];
+#pragma unroll
+      for (int i = 0; i < HEAD_SCHUNK; ++i) accs[i] = 0.f;
+      if (c < C) {
+        // the weights come from L2 (the CTAs' shared memory leaves almost no L1): keep 8 loads in flight
+        constexpr int U = 8;
+        int f = f_lo;
+        for (; f + U <= f_hi; f += U) {
+          float wv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) wv[u] = __ldg(wt + (size_t)(f + u) * C + c);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)(f + u) * HEAD_SCHUNK);
+#pragma unroll
+            for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
+              const float4 pv = pp[i];
+              accs[4 * i] = fmaf(wv[u], pv.x, accs[4 * i]);
+              accs[4 * i + 1] = fmaf(wv[u], pv.y, accs[4 * i + 1]);
+              accs[4 * i + 2] = fmaf(wv[u], pv.z, accs[4 * i + 2]);
+              accs[4 * i + 3] = fmaf(wv[u], pv.w, accs[4 * i + 3]);
+            }
+          }
+        }
+        for (; f < f_hi; ++f) {
+          const float wv = __ldg(wt + (size_t)f * C + c);
+          const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)f * HEAD_SCHUNK);
+#pragma unroll
+          for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
+            const float4 pv = pp[i];
+            accs[4 * i] = fmaf(wv, pv.x, accs[4 * i]);
+            accs[4 * i + 1] = fmaf(wv, pv.y, accs[4 * i + 1]);
+            accs[4 * i + 2] = fmaf(wv, pv.z, accs[4 * i + 2]);
+            accs[4 * i + 3] = fmaf(wv, pv.w, accs[4 * i + 3]);
+          }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < HEAD_SCHUNK; ++i) part[(kq * HEAD_SCHUNK + i) * cpad + cl] = accs[i];
+      __syncthreads();
+      for (int idx = tid; idx < ns * cpad; idx += HEAD_THREADS) {
+        const int sl = idx / cpad, cc = idx - sl * cpad;
+        if (cg0 + cc < C) {
+          float a = __ldg(bias + cg0 + cc);
+          for (int k = 0; k < ks; ++k) a += part[(k * HEAD_SCHUNK + sl) * cpad + cc];
+          logits[sl * C + cg0 + cc] = a;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- phase 3a: softmax statistics per sample (one warp per sample) -----------------------
     for (int sl = warp; sl < ns; sl += HEAD_WARPS) {
       const float* lg = logits + sl * C;
@@ -236,10 +288,10 @@ using namespace bnn;
 extern "C" {
 
 int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
-                  const float* w, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                  const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                   float* sum_plogp, float* logits_out, int accumulate, void* stream) {
   if (int rc = check_device()) return rc;
-  BNN_REQUIRE(feat && w && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
+  BNN_REQUIRE(feat && wt && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
   BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && C > 0, "bnn_exit_head: bad geometry");
   if (drop && drop->kind != BNN_DROP_NONE) {
     BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
@@ -248,8 +300,9 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
                 "bnn_exit_head: Masksembles site without a mask table");
   }
   if (B == 0) return BNN_OK;
-  const size_t smem =
-      ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_SCHUNK * C + 2 * (size_t)C + HEAD_WARPS + 2 * HEAD_SCHUNK) * sizeof(float);
+  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_THREADS * HEAD_SCHUNK + (size_t)HEAD_SCHUNK * C +
+                       2 * (size_t)C + HEAD_WARPS + 2 * HEAD_SCHUNK) *
+                      sizeof(float);
   BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);
   DropParams dp = make_drop_params(drop, F);
   dp.batch = B;
@@ -257,7 +310,7 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
 #define BNN_HEAD_LAUNCH(T)                                                                                         \
   do {                                                                                                             \
     BNN_CUDA_OK(cudaFuncSetAttribute(exit_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    exit_head_kernel<T><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, C, w,  \
+    exit_head_kernel<T><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, C, wt, \
                                                        bias, dp, sum_p, sum_logit, sum_plogp, logits_out,          \
                                                        accumulate);                                                \
   } while (0)

@@ -225,6 +225,34 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   Vec8<T> in;
   if (vec && !x_has_samples) in = *reinterpret_cast<const Vec8<T>*>(x + v0);   // broadcast source: read once
 
+  if constexpr (sizeof(T) == 2) {
+    // 16-bit storage, element-wise dropout, prefix broadcast: scale once, then every sample is one Philox block,
+    // four per-halfword compares (the 16-bit draws line up with the 16-bit elements) and four ANDs per 16 bytes
+    if (vec && !x_has_samples && dp.kind == BNN_DROP_ELEMENT) {
+      uint4 xs;
+      {
+        Vec8<T> sc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sc.v[j] = from_f32<T>(to_f32<T>(in.v[j]) * dp.scale);
+        xs = *reinterpret_cast<const uint4*>(&sc);
+      }
+      const uint32_t thr2 = dp.thr | (dp.thr << 16);
+      const uint64_t blk = (uint64_t)(v0 >> 3);
+#pragma unroll 2
+      for (int s = 0; s < S_local; ++s) {
+        const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk);
+        uint4 o;
+        o.x = xs.x & __vcmpgeu2(r.x, thr2);
+        o.y = xs.y & __vcmpgeu2(r.y, thr2);
+        o.z = xs.z & __vcmpgeu2(r.z, thr2);
+        o.w = xs.w & __vcmpgeu2(r.w, thr2);
+        if (dp.scale == 0.f) o = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(y + (int64_t)s * n_per + v0) = o;
+      }
+      return;
+    }
+  }
+
   for (int s = 0; s < S_local; ++s) {
     const T* xs = x + (x_has_samples ? (int64_t)s * n_per : 0);
     T* ys = y + (int64_t)s * n_per;
@@ -282,6 +310,33 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int H
     for (int b = 0; b < k; ++b)
       m = fmaxf(m, to_f32<T>(x[((n * H + oh * k + a) * W + ow * k + b) * C + c]));
   y[i] = from_f32<T>(m);
+}
+
+// 8 channels (one 16-byte access for 16-bit storage) per thread; requires C % 8 == 0
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_vec8_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W,
+                                                           int C8, int k, int OH, int OW, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  int64_t t = i / C8;
+  const int ow = (int)(t % OW);
+  t /= OW;
+  const int oh = (int)(t % OH);
+  const int64_t n = t / OH;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int a = 0; a < k; ++a)
+    for (int b = 0; b < k; ++b) {
+      const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(x + (((n * H + oh * k + a) * W + ow * k + b) * C8 + c8) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], to_f32<T>(v.v[j]));
+    }
+  Vec8<T> o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = from_f32<T>(m[j]);
+  *reinterpret_cast<Vec8<T>*>(y + i * 8) = o;
 }
 
 template <typename F>
@@ -408,8 +463,14 @@ int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C,
   if (total == 0) return BNN_OK;
   return dispatch_dtype(dtype, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
-    maxpool_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C,
-                                                                                          k, OH, OW, total);
+    if (C % 8 == 0) {
+      const int64_t tv = total / 8;
+      maxpool_vec8_kernel<T><<<(unsigned)((tv + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W,
+                                                                                             C / 8, k, OH, OW, tv);
+    } else {
+      maxpool_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W,
+                                                                                            C, k, OH, OW, total);
+    }
     BNN_LAUNCH_OK();
     return BNN_OK;
   });

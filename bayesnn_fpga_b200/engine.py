@@ -263,7 +263,7 @@ class Engine:
                 op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
                 op.d_b = op.bias.to(dev, torch.float32)
             elif op.kind == "head":
-                op.d_w = op.weight.to(dev, torch.float32)
+                op.d_w = op.weight.t().contiguous().to(dev, torch.float32)      # [F][C] for the head kernel
                 op.d_b = op.bias.to(dev, torch.float32)
             if op.site is not None and op.site.kind == "mask":
                 op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()

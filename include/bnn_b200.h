@@ -100,7 +100,6 @@ int bnn_conv2d_simt(const void* x, const float* w, const float* bias, const void
 int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype, int N,
                   int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
                   void* stream);
-/* Bytes of persistent workspace bnn_conv2d_tc wants (tile counters); may be 0. */
 
 /* ---- stand-alone stochastic layer (prefix -> suffix broadcast) ----
  * y[s][b][...] = drop_s(x[b][...]) for s in [0, S_local) when x_has_samples == 0 (the deterministic
@@ -120,13 +119,13 @@ int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C,
  * _get_output (results_analyzer.py:242-248): instead of S x E device->host copies the kernel keeps
  * running sums over the local samples.
  *   feat        [S_local or 1][B][HW][F]   (feat_has_samples says which)
- *   w, bias     float32 [C][F], [C]
+ *   wt, bias    float32 [F][C] (the nn.Linear weight TRANSPOSED, so that a warp reads consecutive classes), [C]
  *   sum_p, sum_logit   float32 [B][C]   (+= if accumulate != 0, else overwritten)
  *   sum_plogp          float32 [B]      sum_s sum_c p log p
  *   logits_out         nullable float32 [S_local][B][C]: per-sample logits (for parity tests)
  */
 int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
-                  const float* w, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                  const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                   float* sum_plogp, float* logits_out, int accumulate, void* stream);
 
 /* ---- statistics finaliser ----

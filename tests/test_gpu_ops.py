@@ -97,12 +97,13 @@ def test_conv_empty_and_bad_args(lib):
 
 @pytest.mark.parametrize("dt", ["fp32", "fp16"])
 @pytest.mark.parametrize("k", [2, 7])
-def test_maxpool(lib, dt, k):
+@pytest.mark.parametrize("C", [5, 64])           # scalar path / 8-channel vector path
+def test_maxpool(lib, dt, k, C):
     tdt, code = TORCH_DT[dt]
-    x = torch.randn(3, 5, 14, 14).to(tdt)
+    x = torch.randn(3, C, 14, 14).to(tdt)
     d_x = x.permute(0, 2, 3, 1).contiguous().cuda()
-    d_y = torch.empty(3, 14 // k, 14 // k, 5, dtype=tdt, device="cuda")
-    assert lib.bnn_maxpool2d(d_x.data_ptr(), d_y.data_ptr(), code, 3, 14, 14, 5, k, stream()) == 0
+    d_y = torch.empty(3, 14 // k, 14 // k, C, dtype=tdt, device="cuda")
+    assert lib.bnn_maxpool2d(d_x.data_ptr(), d_y.data_ptr(), code, 3, 14, 14, C, k, stream()) == 0
     assert torch.equal(d_y.cpu().permute(0, 3, 1, 2), F.max_pool2d(x.float(), k, k).to(tdt))
 
 
@@ -127,7 +128,7 @@ def test_exit_head_and_finalize(lib, C, F_, HW, has_samples, kind):
     masks = (torch.rand(4, F_, generator=g) > 0.5).float()
     d_masks = masks.cuda()
     dd = drop_desc(kind, p, seed, sid, s0, B, d_masks if kind == 3 else None, cnt0=1)
-    d = dict(feat=feat.cuda(), w=w.cuda(), b=bias.cuda(), sp=torch.zeros(B, C).cuda(), sl=torch.zeros(B, C).cuda(),
+    d = dict(feat=feat.cuda(), w=w.t().contiguous().cuda(), b=bias.cuda(), sp=torch.zeros(B, C).cuda(), sl=torch.zeros(B, C).cuda(),
              spl=torch.zeros(B).cuda(), lo=torch.zeros(S, B, C).cuda())
     rc = lib.bnn_exit_head(d["feat"].data_ptr(), 0, has_samples, B, S, HW, F_, C, d["w"].data_ptr(), d["b"].data_ptr(),
                            ctypes.byref(dd), d["sp"].data_ptr(), d["sl"].data_ptr(), d["spl"].data_ptr(),
