@@ -69,6 +69,8 @@ _SIGS = {
                         [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_conv2d_tc": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
                       [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_conv2d_tc_grouped": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
+                              [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     "bnn_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_maxpool2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),

@@ -54,10 +54,15 @@ struct Params {
   int M, Cout, n_tiles_n, num_tiles;
   int taps, cblocks, Cin, stride, pad;
   int OH, OW, OHW;
-  int relu;
+  // grouped outputs: the GEMM's N = groups * cout_g concatenated output channels; group g is written to yg[g]
+  // with row stride cout_g.  One group == an ordinary convolution (cout_g == Cout).
+  int groups, cout_g;
+  uint32_t relu_mask;   // bit g: ReLU on group g
+  int prefetch;         // issue L2 prefetches one tile ahead (BNN_TC_PREFETCH=0 disables)
+  uint32_t center_mask; // bit g: group g is a 1x1 kernel stored in the centre tap of the 3x3 - only that tap runs
   const float* bias;
   const void* res;
-  void* y;
+  void* yg[4];
   DropParams dp;
 };
 
@@ -110,6 +115,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       "%7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// L2 prefetch of a TMA box (no shared-memory destination, no barrier): used one tile ahead so that the operand
+// loads of the next tile hit L2 instead of paying DRAM latency inside the 4-stage ring
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -246,7 +264,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           img0[mt] = m0 / p.OHW;
           oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
         }
-        for (int tap = 0; tap < p.taps; ++tap) {
+        const bool center = (p.center_mask >> ((n_tile * BN) / p.cout_g)) & 1u;
+        const int tap_lo = center ? 4 : 0, tap_hi = center ? 5 : p.taps;
+        // ---- L2 prefetch of the NEXT tile's activation boxes (only once per row-tile: for its first channel tile)
+        {
+          const int nt = tile + gridDim.x;
+          const int nm_tile = nt / p.n_tiles_n;
+          if (p.prefetch && nt < p.num_tiles && nt - nm_tile * p.n_tiles_n == 0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const int m0 = (nm_tile * MT + mt) * BM;
+              if (m0 >= p.M) continue;
+              const int pimg = m0 / p.OHW, poh = (m0 - pimg * p.OHW) / p.OW;
+              for (int tap = 0; tap < p.taps; ++tap) {
+                const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
+                const int rh = kh - p.pad, rw = kw - p.pad;
+                if (p.stride == 1) {
+                  if (p.taps == 9 && !(kw == 1 && kh != 1)) continue;      // taps (0,1) and (2,1) cover the halo rows
+                  for (int cb = 0; cb < p.cblocks; ++cb) tma_prefetch_4d(&tmap_a, cb * BK, rw, poh + rh, pimg);
+                } else {
+                  const int hp = rh & 1, dh = (rh - hp) >> 1, wp = rw & 1, dw = (rw - wp) >> 1;
+                  if (dw != 0) continue;                                     // the dw = -1 box is a subset of dw = 0
+                  for (int cb = 0; cb < p.cblocks; ++cb)
+                    tma_prefetch_5d(&tmap_a, wp * p.Cin + cb * BK, 0, hp, poh + dh, pimg);
+                }
+              }
+            }
+          }
+        }
+        for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
           // stride 2: input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
           const int rh = kh - p.pad, rw = kw - p.pad;                 // -1, 0, +1  (0 only for 1x1)
@@ -281,10 +327,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile_mma = tile % p.n_tiles_n;
+        const int tile_kb = ((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < tile_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
@@ -323,7 +371,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int NCH = BN / 64;                          // 32-column chunks per warp (non-swapped layout)
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;                       // which half of the columns
-    T* __restrict__ y = reinterpret_cast<T*>(p.y);
     const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -335,13 +382,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr int PX = MT * BM;                         // pixels per tile (256)
       constexpr int PCH = PX / 64;                        // 32-pixel chunks per warp
       const uint16_t* __restrict__ res16 = reinterpret_cast<const uint16_t*>(p.res);
-      uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.y);
       const int64_t sample_px = (int64_t)p.dp.batch * p.OHW;          // pixels per MC sample
-      const int c = q * 32 + lane;
-      const float bias_c = __ldg(p.bias + c);
+      const int c = q * 32 + lane;                                    // channel inside the group (cout_g == BN)
       const bool has_res = res16 != nullptr;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_base = tile * PX + hf * (PX / 2);
+        const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;   // n_tile == output group
+        uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.yg[n_tile]);
+        const float bias_c = __ldg(p.bias + n_tile * BN + c);
+        const bool relu = (p.relu_mask >> n_tile) & 1u;
+        const int m_base = m_tile * PX + hf * (PX / 2);
         if (has_res) {
           // pull this warp's residual rows (32 channels = 64 bytes per pixel) into L2 while the MMAs of this tile
           // are still running: lane l touches pixels l, l+32, l+64, l+96 of the warp's 128-pixel half
@@ -401,7 +450,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) {
               float f = __uint_as_float(v[j]) + bias_c;
               if (has_res) f += unpack2<T>(rr[j]).x;
-              if (p.relu) f = fmaxf(f, 0.f);
+              if (relu) f = fmaxf(f, 0.f);
               f *= ((kw[j & 7] >> (8 * (j >> 3) + (lane & 7))) & 1u) ? fac : 0.f;
               if (j < nvalid) yp[j * BN] = (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
             }
@@ -416,7 +465,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
-      const int cbase = n_tile * BN + hf * (BN / 2);      // first output channel of this warp
+      const int cbase = n_tile * BN + hf * (BN / 2);      // first (concatenated) output channel of this warp
+      const int grp = cbase / p.cout_g;                   // output group and channel offset inside it
+      const int cgrp = cbase - grp * p.cout_g;
+      T* __restrict__ y = reinterpret_cast<T*>(p.yg[grp]);
+      const bool relu = (p.relu_mask >> grp) & 1u;
 
       // residual rows are fetched BEFORE waiting for the accumulator: the DRAM latency hides behind the MMAs
       uint4 rpre[MT][NCH][4];
@@ -425,7 +478,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int mt = 0; mt < MT; ++mt) {
           const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
           if (m < p.M) {
-            const uint4* src = reinterpret_cast<const uint4*>(res + (size_t)m * p.Cout + cbase);
+            const uint4* src = reinterpret_cast<const uint4*>(res + (size_t)m * p.cout_g + cgrp);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -463,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
           tmem_ld_wait();
           if (valid) {
-            const size_t off = (size_t)m * p.Cout + c0;
+            const size_t off = (size_t)m * p.cout_g + (cgrp + ch * 32);
             float f[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -485,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
               }
             }
-            if (p.relu) {
+            if (relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
@@ -601,31 +654,36 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 using namespace bnn;
 
-extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype,
-                             int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
-                             const bnn_drop_desc* drop, void* stream) {
+// shared runner: `groups` outputs of `cout_g` channels each (groups == 1: an ordinary convolution)
+static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
+                       void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
+                       int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream) {
   if (int rc = check_device()) return rc;
-  BNN_REQUIRE(x && w && bias && y, "bnn_conv2d_tc: null pointer");
-  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_conv2d_tc: dtype must be float16 or bfloat16");
-  BNN_REQUIRE(N >= 0 && H > 0 && W > 0, "bnn_conv2d_tc: bad geometry");
+  BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
+  BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
+  for (int g = 0; g < groups; ++g) BNN_REQUIRE(y[g] != nullptr, "%s: null output %d", who, g);
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "%s: dtype must be float16 or bfloat16", who);
+  BNN_REQUIRE(N >= 0 && H > 0 && W > 0, "%s: bad geometry", who);
+  BNN_REQUIRE(groups == 1 || (res == nullptr && (drop == nullptr || drop->kind == BNN_DROP_NONE)),
+              "%s: residual / stochastic epilogues need a single output group", who);
+  const int Cout = groups * cout_g;
   const int pad = ksize == 3 ? 1 : 0;
   const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
-  const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && Cout % 64 == 0 &&
+  const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && cout_g % 64 == 0 &&
                   (stride == 1 || (H % 2 == 0 && W % 2 == 0)) && tc::pow2(OW) && tc::pow2(OH) && OW <= 128;
   if (!ok) {
-    set_error("bnn_conv2d_tc: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", ksize, stride,
-              Cin, Cout, H, W);
+    set_error("%s: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", who, ksize, stride, Cin,
+              cout_g, H, W);
     return BNN_E_UNSUPPORTED;
   }
   if (drop && drop->kind != BNN_DROP_NONE) {
-    BNN_REQUIRE(drop->batch > 0 && N % drop->batch == 0, "bnn_conv2d_tc: N=%d not a multiple of batch=%d", N,
-                drop->batch);
+    BNN_REQUIRE(drop->batch > 0 && N % drop->batch == 0, "%s: N=%d not a multiple of batch=%d", who, N, drop->batch);
     BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", drop->p);
     BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
-                "bnn_conv2d_tc: Masksembles site without a mask table");
+                "%s: Masksembles site without a mask table", who);
   }
   if (N == 0) return BNN_OK;
-  BNN_REQUIRE((int64_t)N * OH * OW < (int64_t)1 << 31, "bnn_conv2d_tc: M overflows int32");
+  BNN_REQUIRE((int64_t)N * OH * OW < (int64_t)1 << 31, "%s: M overflows int32", who);
 
   // tile geometry: 128 consecutive output pixels = tn images x th rows x OW columns
   const int tw = OW;
@@ -646,7 +704,8 @@ extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, co
     const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
     if (int rc = tc::encode_map(&ta, dtype, 5, x, dims, strides, box)) return rc;
   }
-  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // a channel tile never straddles two output groups: BN divides cout_g
+  const int BN = cout_g % 256 == 0 ? 256 : (cout_g % 128 == 0 ? 128 : 64);
   {
     const int K = ksize * ksize * Cin;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
@@ -668,10 +727,16 @@ extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, co
   p.OH = OH;
   p.OW = OW;
   p.OHW = OH * OW;
-  p.relu = relu;
+  p.groups = groups;
+  p.cout_g = cout_g;
+  p.relu_mask = relu_mask;
+  p.center_mask = ksize == 3 ? center_mask : 0u;
+  // measured on B200 (C2): prefetching one tile ahead LOWERED throughput 29.3k -> 28.1k img/s (the extra TMA
+  // operations compete with the operand loads), so it is off unless BNN_TC_PREFETCH=1
+  p.prefetch = getenv("BNN_TC_PREFETCH") ? atoi(getenv("BNN_TC_PREFETCH")) : 0;
   p.bias = bias;
   p.res = res;
-  p.y = y;
+  for (int g = 0; g < groups; ++g) p.yg[g] = y[g];
   p.dp = make_drop_params(drop, Cout);
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -680,9 +745,10 @@ extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, co
   case BN_:                                                                                   \
     return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, __half>(ta, tb, p, st)              \
                             : tc::launch<BN_, MT_, SWAP_, __nv_bfloat16>(ta, tb, p, st);
-  // channel-wise dropout is not implemented in the transposed epilogue: those (rare) sites take the 128x128 path
+  // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
+  // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
-      Cout == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
+      cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
   if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
     switch (BN) { BNN_TC_DISPATCH(128, 2, true) }
@@ -694,4 +760,19 @@ extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, co
   }
 #undef BNN_TC_DISPATCH
   return BNN_E_UNSUPPORTED;
+}
+
+extern "C" int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype,
+                             int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
+                             const bnn_drop_desc* drop, void* stream) {
+  void* ys[1] = {y};
+  return conv_tc_run("bnn_conv2d_tc", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize, stride,
+                     drop, stream);
+}
+
+extern "C" int bnn_conv2d_tc_grouped(const void* x, const void* w, const float* bias, void* const* y, int n_groups,
+                                     uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
+                                     int cout_per_group, int ksize, int stride, void* stream) {
+  return conv_tc_run("bnn_conv2d_tc_grouped", x, w, bias, nullptr, y, n_groups, relu_mask, center_mask, dtype, N, H, W, Cin,
+                     cout_per_group, ksize, stride, nullptr, stream);
 }

@@ -177,11 +177,45 @@ class Graph:
             out.append(op)
         self.ops = out
 
+    def fuse_sibling_convs(self, eligible):
+        """Group stride-2 convolutions that read the same tensor (first conv of the next stage, its 1x1 shortcut,
+        first conv of the exit branch) into one 'convg' op: the input is fetched from HBM once.  A 1x1 stride-2
+        pad-0 conv is exactly the centre tap of a 3x3 stride-2 pad-1 conv."""
+        groups = {}
+        for op in self.ops:
+            if op.kind != "conv" or op.res is not None or op.site is not None or op.stride != 2 or not eligible(op):
+                continue
+            if not ((op.ksize == (3, 3) and op.pad == 1) or (op.ksize == (1, 1) and op.pad == 0)):
+                continue
+            groups.setdefault((op.src.id, op.dst.C, op.dst.H, op.dst.W), []).append(op)
+        for members in groups.values():
+            if not (2 <= len(members) <= 4) or not any(m.ksize == (3, 3) for m in members):
+                continue
+            ws = []
+            for m in members:
+                w = m.weight
+                if m.ksize == (1, 1):
+                    w3 = torch.zeros(w.shape[0], w.shape[1], 3, 3, dtype=w.dtype)
+                    w3[:, :, 1, 1] = w[:, :, 0, 0]
+                    w = w3
+                ws.append(w)
+            fused = Op("convg", members[0].src, None, None, torch.cat(ws), torch.cat([m.bias for m in members]),
+                       (3, 3), 2, 1, name="+".join(m.name for m in members))
+            fused.members = members
+            fused.dsts = [m.dst for m in members]
+            first = self.ops.index(members[0])
+            self.ops[first] = fused
+            for m in members[1:]:
+                self.ops.remove(m)
+
     def macs(self):
         """(prefix MACs, per-sample suffix MACs) per image - the reference's cost model
         (results_analyzer.py:632-637) evaluated on this graph."""
         pre = suf = 0
+        flat = []
         for op in self.ops:
+            flat.extend(op.members if op.kind == "convg" else [op])
+        for op in flat:
             if op.kind == "conv":
                 m = op.dst.H * op.dst.W * op.dst.C * op.src.C * op.ksize[0] * op.ksize[1]
             elif op.kind == "head":
@@ -239,8 +273,11 @@ class Engine:
         self.dcode, self.tdtype = DTYPES[dtype]
         # BNN_DISABLE_TC=1 routes the 16-bit path through the CUDA-core kernel too (debugging aid)
         self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
+        if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
+            graph.fuse_sibling_convs(self._tc_eligible)
         self.launches = 0
         self._prof = None
+        self._graphs = {}
         self._bufs = {}
         self._prepare_weights()
 
@@ -257,7 +294,12 @@ class Engine:
     def _prepare_weights(self):
         dev = self.device
         for op in self.graph.ops:
-            if op.kind == "conv":
+            if op.kind == "convg":
+                op.d_w = op.weight.permute(0, 2, 3, 1).contiguous().to(dev, self.tdtype)
+                op.d_b = op.bias.to(dev, torch.float32)
+                op.relu_mask = sum(1 << i for i, m in enumerate(op.members) if m.relu)
+                op.center_mask = sum(1 << i for i, m in enumerate(op.members) if m.ksize == (1, 1))
+            elif op.kind == "conv":
                 w = op.weight.permute(0, 2, 3, 1).contiguous()       # [Cout][KH][KW][Cin]
                 op.use_tc = self._tc_eligible(op)
                 op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
@@ -277,7 +319,7 @@ class Engine:
         acts = {}
         live = {g.input.id}
         for op in g.ops:
-            live.update(t.id for t in (op.src, op.dst, op.res) if t is not None)
+            live.update(t.id for t in (op.src, op.dst, op.res) + tuple(getattr(op, "dsts", ())) if t is not None)
         for t in g.tensors:
             if t.id not in live:
                 continue                      # e.g. the un-masked output of a conv with a fused site
@@ -295,6 +337,7 @@ class Engine:
         return st
 
     def release_buffers(self):
+        self._graphs.clear()
         self._bufs.clear()
 
     # ---- launch helpers ---------------------------------------------------------------------
@@ -358,7 +401,20 @@ class Engine:
             _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W, stream))
         sum_p, sum_l, sum_pl = self.sums_views(st, B)
         for op in g.ops:
-            if op.kind == "conv":
+            if op.kind == "convg":
+                d0 = op.dsts[0]
+                n_img = (S_local if d0.stoch else 1) * B
+                if n_img == 0:
+                    continue
+                ys = (ctypes.c_void_p * len(op.dsts))(*[acts[d.id].data_ptr() for d in op.dsts])
+                out_px = n_img * d0.H * d0.W
+                flops = sum(2 * out_px * m.dst.C * m.src.C * m.ksize[0] * m.ksize[1] for m in op.members)
+                nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * d0.C * len(op.dsts)) * es \
+                    + op.d_w.numel() * op.d_w.element_size()
+                self._launch("conv_tc", op.name, flops, nbytes, lambda: lib.bnn_conv2d_tc_grouped(
+                    _ptr(acts[op.src.id]), _ptr(op.d_w), _ptr(op.d_b), ys, len(op.dsts), op.relu_mask, op.center_mask, self.dcode,
+                    n_img, op.src.H, op.src.W, op.src.C, d0.C, 3, 2, stream))
+            elif op.kind == "conv":
                 n_img = (S_local if op.dst.stoch else 1) * B
                 if n_img == 0:
                     continue
@@ -456,15 +512,47 @@ class Engine:
                 seen.add(id(s.module))
                 s.module.cnt = (int(s.module.cnt) + S) % int(s.module.n)
 
+    def _enqueue_graphed(self, x, S, sample0, seed, want_logits, mask_offset):
+        """CUDA-graph replay of the launch sequence.  Kernel arguments (seed, sample range, Masksembles counters,
+        buffer pointers) are baked into the graph, so graphs are cached per argument tuple: the first call with a
+        tuple runs eagerly, the second captures, later ones replay (a benchmark or a sample-sharded serving loop
+        repeats its tuple; an analysis loop that reseeds every batch simply stays eager)."""
+        cnts = tuple(int(s.module.cnt) for s in self.graph.sites if s.kind == "mask")
+        key = (x.shape[0], S, sample0, seed, want_logits, mask_offset, cnts)
+        st = self._buffers(x.shape[0], S, want_logits)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "seen"
+            if len(self._graphs) > 64:
+                self._graphs.pop(next(iter(self._graphs)))
+            return self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
+        st["x"].copy_(x, non_blocking=True)
+        if entry == "seen":
+            n0 = self.launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue(st["x"], S, sample0, seed, False, want_logits, mask_offset)
+            entry = self._graphs[key] = (g, self.launches - n0)
+            self.launches = n0
+        g, n = entry
+        g.replay()
+        self.launches += n
+        return st
+
     def run(self, x, S, seed=0x5EED, sample0=0, S_total=None, want_logits=False, reduce_fn=None,
-            mask_offset=None):
+            mask_offset=None, use_graph=None):
         """S local samples starting at global sample index `sample0`; `reduce_fn(sums)` (optional)
         all-reduces the flat sums tensor across ranks before the finaliser.  Masksembles rows are
         (module.cnt + mask_offset + s) % n with mask_offset defaulting to sample0."""
         x = x.to(self.device, torch.float32)
         B = x.shape[0]
+        if use_graph is None:
+            use_graph = os.environ.get("BNN_CUDA_GRAPH", "1") != "0"
         with torch.cuda.device(self.device):
-            st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
+            if use_graph and B > 0 and S > 0 and self._prof is None:
+                st = self._enqueue_graphed(x, S, sample0, seed, want_logits, mask_offset)
+            else:
+                st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
             if reduce_fn is not None:
                 reduce_fn(st["sums"])
             S_total = S if S_total is None else S_total

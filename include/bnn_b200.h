@@ -101,6 +101,16 @@ int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* r
                   int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
                   void* stream);
 
+/* Sibling convolutions that read the SAME input with the same geometry (in the multi-exit ResNet: the first conv of
+ * stage N+1, its 1x1 shortcut embedded in the centre tap of a 3x3 kernel, and the first conv of exit branch N -
+ * resnet18.py:306,:316 and BasicBlock :35,:43) as ONE launch: the activation tile is fetched from HBM once.
+ * `w` is [n_groups * cout_per_group][k][k][Cin], `bias` [n_groups * cout_per_group], `y` a HOST array of n_groups
+ * device pointers, each output [N][OH][OW][cout_per_group]; bit g of relu_mask enables the ReLU of output g; bit g
+ * of center_mask says output g is a 1x1 kernel held in the centre tap (only that tap is multiplied). */
+int bnn_conv2d_tc_grouped(const void* x, const void* w, const float* bias, void* const* y, int n_groups,
+                          uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
+                          int cout_per_group, int ksize, int stride, void* stream);
+
 /* ---- stand-alone stochastic layer (prefix -> suffix broadcast) ----
  * y[s][b][...] = drop_s(x[b][...]) for s in [0, S_local) when x_has_samples == 0 (the deterministic
  * prefix is computed once per image and broadcast across the S samples), or drop_s(x[s][b][...])

@@ -240,3 +240,35 @@ def test_conv_tc_rejects_unsupported_geometry(lib):
     assert lib.bnn_conv2d_tc(*args(3, 64, 3, 32)) == -4         # Cin % 64 != 0 -> use the CUDA-core kernel
     assert lib.bnn_conv2d_tc(*args(64, 64, 5, 32)) == -4        # 5x5
     assert lib.bnn_conv2d_tc(*args(64, 64, 3, 12)) == -4        # 12x12 output rows do not tile 128
+
+
+@pytest.mark.parametrize("Cin,Cg,HW,G", [(64, 128, 16, 3), (128, 256, 8, 3), (256, 512, 8, 2)])
+def test_conv_tc_grouped_equals_separate_convs(lib, Cin, Cg, HW, G):
+    """sibling stride-2 convs on one input (3x3, 3x3, 1x1-in-the-centre-tap) as one launch == separate convs."""
+    N = 6
+    g = torch.Generator().manual_seed(Cg)
+    x = torch.randn(N, Cin, HW, HW, generator=g).half()
+    ws = [torch.randn(Cg, Cin, 3, 3, generator=g) / np.sqrt(9 * Cin) for _ in range(G - 1)]
+    w1 = torch.randn(Cg, Cin, 1, 1, generator=g) / np.sqrt(Cin)
+    w3 = torch.zeros(Cg, Cin, 3, 3)
+    w3[:, :, 1, 1] = w1[:, :, 0, 0]
+    wcat = torch.cat(ws + [w3]).half()
+    bias = torch.randn(G * Cg, generator=g)
+    relu_mask = (1 << (G - 1)) - 1                               # ReLU on the 3x3 outputs, not on the shortcut
+    d_x = x.permute(0, 2, 3, 1).contiguous().cuda()
+    d_w = wcat.permute(0, 2, 3, 1).contiguous().cuda()
+    d_b = bias.cuda()
+    outs = [torch.full((N, HW // 2, HW // 2, Cg), float("nan"), dtype=torch.float16, device="cuda") for _ in range(G)]
+    ys = (ctypes.c_void_p * G)(*[o.data_ptr() for o in outs])
+    rc = lib.bnn_conv2d_tc_grouped(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ys, G, relu_mask, 1 << (G - 1), 1, N,
+                                   HW, HW, Cin, Cg, 3, 2, stream())
+    assert rc == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    xd = x.double()
+    for i in range(G):
+        if i < G - 1:
+            want = F.conv2d(xd, ws[i].half().double(), bias[i * Cg:(i + 1) * Cg].double(), 2, 1).relu()
+        else:
+            want = F.conv2d(xd, w1.half().double(), bias[i * Cg:].double(), 2, 0)
+        got = outs[i].cpu().permute(0, 3, 1, 2).double()
+        assert (got - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item()), i

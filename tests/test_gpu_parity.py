@@ -193,3 +193,21 @@ def test_ece_and_argmax_on_a_dataset_sized_batch():
                logit_scale=float(np.abs(want["mean_logits"]).max()))
         assert perr <= ptol and okp and okl
         assert max(eces) <= (1e-4 if dt == "fp32" else 2e-3)
+
+
+@pytest.mark.parametrize("tag", ["resnet18_mcd_block", "resnet18_mask_block"])
+def test_cuda_graph_replay_equals_eager(tag):
+    """call 1 runs eagerly, call 2 captures a CUDA graph, call 3 replays it: identical statistics; new inputs are
+    picked up by the replay; Masksembles counters (baked into the graph key) keep rotating."""
+    model, sd, gold = build_seeded(tag)
+    model.cuda()
+    x = torch.from_numpy(gold["x"])
+    S = 4                                    # multiple of n = 4: Masksembles counters return to the same value
+    outs = [mc_predict(model, x, S, seed=5, dtype="fp16").mean_probs.clone() for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    eng = model.bnn_engine("fp16")
+    assert any(isinstance(v, tuple) for v in eng._graphs.values())          # a graph was captured
+    x2 = x.flip(0).contiguous()
+    a = mc_predict(model, x2, S, seed=5, dtype="fp16").mean_probs.clone()   # replay with a different batch
+    b = eng.run(x2, S, seed=5, use_graph=False).mean_probs
+    assert torch.equal(a, b)
