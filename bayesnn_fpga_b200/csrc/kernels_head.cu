@@ -32,8 +32,92 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// logits[ns x C] = pooled^T * W^T + bias.  Thread = (class slot cl, K-split kq); it owns CPT classes
+// (cl + j * nthr_c) x 16 samples in registers.  Per f: CPT coalesced weight loads (W^T is [F][C], served by L2 - the
+// CTAs' shared memory leaves almost no L1) and four broadcast LDS.128 of the 16 pooled samples feed 16 * CPT FMAs;
+// CPT = 4 for wide heads keeps the shared-memory pipe (the measured limiter at C = 100) off the critical path.
+template <int CPT>
+__device__ __forceinline__ void head_gemm(const float* __restrict__ pooled, float* __restrict__ part,
+                                          float* __restrict__ logits, const float* __restrict__ wt,
+                                          const float* __restrict__ bias, int F, int C, int ns, int tid) {
+  constexpr int GROUP_MAX = HEAD_THREADS * CPT;          // classes handled per pass
+  for (int cg0 = 0; cg0 < C; cg0 += GROUP_MAX) {
+    const int cgroup = min(C - cg0, GROUP_MAX);
+    int nthr_c = 1;
+    while (nthr_c * CPT < cgroup) nthr_c <<= 1;          // class slots (power of two <= 256)
+    const int ks = HEAD_THREADS / nthr_c;
+    const int cl = tid % nthr_c, kq = tid / nthr_c;
+    const int fk = (F + ks - 1) / ks;
+    const int f_lo = kq * fk, f_hi = min(F, f_lo + fk);
+    float accs[CPT][HEAD_SCHUNK];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+#pragma unroll
+      for (int i = 0; i < HEAD_SCHUNK; ++i) accs[j][i] = 0.f;
+    bool cvalid[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) cvalid[j] = cg0 + cl + j * nthr_c < C;
+    const float* wbase = wt + cg0 + cl;
+    constexpr int U = CPT == 1 ? 8 : 4;                  // independent weight loads in flight: U * CPT
+    int f = f_lo;
+    for (; f + U <= f_hi; f += U) {
+      float wv[U][CPT];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) wv[u][j] = cvalid[j] ? __ldg(wbase + (size_t)(f + u) * C + j * nthr_c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)(f + u) * HEAD_SCHUNK);
+#pragma unroll
+        for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
+          const float4 pv = pp[i];
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            accs[j][4 * i] = fmaf(wv[u][j], pv.x, accs[j][4 * i]);
+            accs[j][4 * i + 1] = fmaf(wv[u][j], pv.y, accs[j][4 * i + 1]);
+            accs[j][4 * i + 2] = fmaf(wv[u][j], pv.z, accs[j][4 * i + 2]);
+            accs[j][4 * i + 3] = fmaf(wv[u][j], pv.w, accs[j][4 * i + 3]);
+          }
+        }
+      }
+    }
+    for (; f < f_hi; ++f) {
+      const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)f * HEAD_SCHUNK);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float wv = cvalid[j] ? __ldg(wbase + (size_t)f * C + j * nthr_c) : 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
+          const float4 pv = pp[i];
+          accs[j][4 * i] = fmaf(wv, pv.x, accs[j][4 * i]);
+          accs[j][4 * i + 1] = fmaf(wv, pv.y, accs[j][4 * i + 1]);
+          accs[j][4 * i + 2] = fmaf(wv, pv.z, accs[j][4 * i + 2]);
+          accs[j][4 * i + 3] = fmaf(wv, pv.w, accs[j][4 * i + 3]);
+        }
+      }
+    }
+    // partial sums -> part[kq][sample][class slot j * nthr_c + cl]; then a fixed-order reduction over kq
+    const int cw = nthr_c * CPT;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j)
+#pragma unroll
+      for (int i = 0; i < HEAD_SCHUNK; ++i) part[(kq * HEAD_SCHUNK + i) * cw + j * nthr_c + cl] = accs[j][i];
+    __syncthreads();
+    for (int idx = tid; idx < ns * cw; idx += HEAD_THREADS) {
+      const int sl = idx / cw, cc = idx - sl * cw;
+      if (cg0 + cc < C) {
+        float a = __ldg(bias + cg0 + cc);
+        for (int k = 0; k < ks; ++k) a += part[(k * HEAD_SCHUNK + sl) * cw + cc];
+        logits[sl * C + cg0 + cc] = a;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // dynamic shared memory layout (floats):
-//   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
+//   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1)] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
 //   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
@@ -43,7 +127,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   extern __shared__ float sm[];
   float* pooled = sm;
   float* part = pooled + (size_t)HEAD_SCHUNK * F;
-  float* logits = part + HEAD_THREADS * HEAD_SCHUNK;
+  float* logits = part + HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1);
   float* acc_p = logits + (size_t)HEAD_SCHUNK * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
@@ -108,66 +192,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     }
     __syncthreads();
     // ---- phase 2: logits[ns x C] = pooled[ns x F] * W^T[F x C] + bias as a register-tiled small GEMM ----
-    // thread = (class cl of a group of Cpad classes, K-split kq): 16 sample accumulators in registers; per f one
-    // coalesced weight load (W^T is [F][C]) and four broadcast LDS.128 of the 16 pooled samples feed 16 FMAs
-    for (int cg0 = 0; cg0 < C; cg0 += HEAD_THREADS) {
-      int cpad = 1;
-      while (cpad < min(C - cg0, HEAD_THREADS)) cpad <<= 1;
-      const int ks = HEAD_THREADS / cpad;
-      const int cl = tid % cpad, kq = tid / cpad;
-      const int c = cg0 + cl;
-      const int fk = (F + ks - 1) / ks;
-      const int f_lo = kq * fk, f_hi = min(F, f_lo + fk);
-      float accs[HEAD_SCHUNK];
-#pragma unroll
-      for (int i = 0; i < HEAD_SCHUNK; ++i) accs[i] = 0.f;
-      if (c < C) {
-        // the weights come from L2 (the CTAs' shared memory leaves almost no L1): keep 8 loads in flight
-        constexpr int U = 8;
-        int f = f_lo;
-        for (; f + U <= f_hi; f += U) {
-          float wv[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) wv[u] = __ldg(wt + (size_t)(f + u) * C + c);
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)(f + u) * HEAD_SCHUNK);
-#pragma unroll
-            for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
-              const float4 pv = pp[i];
-              accs[4 * i] = fmaf(wv[u], pv.x, accs[4 * i]);
-              accs[4 * i + 1] = fmaf(wv[u], pv.y, accs[4 * i + 1]);
-              accs[4 * i + 2] = fmaf(wv[u], pv.z, accs[4 * i + 2]);
-              accs[4 * i + 3] = fmaf(wv[u], pv.w, accs[4 * i + 3]);
-            }
-          }
-        }
-        for (; f < f_hi; ++f) {
-          const float wv = __ldg(wt + (size_t)f * C + c);
-          const float4* pp = reinterpret_cast<const float4*>(pooled + (size_t)f * HEAD_SCHUNK);
-#pragma unroll
-          for (int i = 0; i < HEAD_SCHUNK / 4; ++i) {
-            const float4 pv = pp[i];
-            accs[4 * i] = fmaf(wv, pv.x, accs[4 * i]);
-            accs[4 * i + 1] = fmaf(wv, pv.y, accs[4 * i + 1]);
-            accs[4 * i + 2] = fmaf(wv, pv.z, accs[4 * i + 2]);
-            accs[4 * i + 3] = fmaf(wv, pv.w, accs[4 * i + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < HEAD_SCHUNK; ++i) part[(kq * HEAD_SCHUNK + i) * cpad + cl] = accs[i];
-      __syncthreads();
-      for (int idx = tid; idx < ns * cpad; idx += HEAD_THREADS) {
-        const int sl = idx / cpad, cc = idx - sl * cpad;
-        if (cg0 + cc < C) {
-          float a = __ldg(bias + cg0 + cc);
-          for (int k = 0; k < ks; ++k) a += part[(k * HEAD_SCHUNK + sl) * cpad + cc];
-          logits[sl * C + cg0 + cc] = a;
-        }
-      }
-      __syncthreads();
-    }
+    if (C > 32)
+      head_gemm<4>(pooled, part, logits, wt, bias, F, C, ns, tid);
+    else
+      head_gemm<1>(pooled, part, logits, wt, bias, F, C, ns, tid);
     // ---- phase 3a: softmax statistics per sample (one warp per sample) -----------------------
     for (int sl = warp; sl < ns; sl += HEAD_WARPS) {
       const float* lg = logits + sl * C;
@@ -300,7 +328,8 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
                 "bnn_exit_head: Masksembles site without a mask table");
   }
   if (B == 0) return BNN_OK;
-  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_THREADS * HEAD_SCHUNK + (size_t)HEAD_SCHUNK * C +
+  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1) +
+                       (size_t)HEAD_SCHUNK * C +
                        2 * (size_t)C + HEAD_WARPS + 2 * HEAD_SCHUNK) *
                       sizeof(float);
   BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);

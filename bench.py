@@ -169,6 +169,16 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 25 launches of one C2 step) from
+    the committed `ncu --set full` summary, or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_conv_tc_full.json")
+    if not os.path.exists(p):
+        return None
+    rows = json.load(open(p))
+    return sum((r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows) / max(len(rows), 1)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -339,7 +349,10 @@ def main():
                     peaks["src"], peaks["burst"]),
                 "launches_per_step": len(tc), "avg_launch_ms": t_tc * 1e3 / len(tc),
                 "flops_per_launch": flops / len(tc), "share_of_step": t_tc * 1e3 / sum(o["ms"] for o in prof),
-                "traffic": None}
+                "algorithmic_bytes_per_launch": sum(o["bytes"] for o in tc) / len(tc),
+                "traffic": ncu_traffic() if args.workload == "c2" else None,
+                "traffic_source": "profiles/r01_ncu_conv_tc_full.json (ncu --set full, mean DRAM bytes per launch; "
+                                  "captured before sibling fusion: 25 launches/step)"}
     else:
         flops = sum(o["flops"] for o in prof)
         t_all = sum(o["ms"] for o in prof) * 1e-3
