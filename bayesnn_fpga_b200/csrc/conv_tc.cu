@@ -58,7 +58,6 @@ struct Params {
   // with row stride cout_g.  One group == an ordinary convolution (cout_g == Cout).
   int groups, cout_g;
   uint32_t relu_mask;   // bit g: ReLU on group g
-  int prefetch;         // issue L2 prefetches one tile ahead (BNN_TC_PREFETCH=0 disables)
   uint32_t center_mask; // bit g: group g is a 1x1 kernel stored in the centre tap of the 3x3 - only that tap runs
   const float* bias;
   const void* res;
@@ -100,6 +99,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// half of a weight tile, written to the same shared-memory offset of BOTH CTAs of the pair; each destination
+// CTA's barrier (same offset) receives the bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+      "%5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -115,19 +124,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       "%7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
-}
-
-// L2 prefetch of a TMA box (no shared-memory destination, no barrier): used one tile ahead so that the operand
-// loads of the next tile hit L2 instead of paying DRAM latency inside the 4-stage ring
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
-               "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
-               "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -160,6 +156,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -205,7 +213,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // layers also issue 128 x 256 x 16 MMAs (a 128 x 128 MMA re-reads its operands from shared memory twice as often
 // per FLOP and measured ~55% tensor-pipe utilisation).  The accumulator is then D^T: TMEM lanes = channels,
 // columns = pixels, and the epilogue writes 2-byte elements that coalesce across the warp's 32 channels.
-template <int BN, int MT, bool SWAP, typename T>
+// MC2: the kernel runs as clusters of two CTAs that work on two adjacent row-tiles with the SAME weights; each CTA
+// fetches half of every weight k-block and multicasts it into both shared memories (L2->SM weight traffic halves:
+// 48 KB -> 32 KB per k-block at BN = 256).  A stage is reused only after the MMAs of BOTH CTAs released it.
+template <int BN, int MT, bool SWAP, bool MC2, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   constexpr int STAGES = stages_for(BN, MT);
@@ -229,13 +240,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.cblocks;
+  uint32_t cta_rank = 0;
+  if constexpr (MC2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  // scheduling unit: a CTA (tile = (row-tile, channel tile)) or a CTA pair (tile = (row-tile pair, channel tile))
+  const int sched_id = MC2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = MC2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC2 ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -246,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to it
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -254,44 +271,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+        const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
+        const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
         int img0[MT], oh0[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           int m0 = (m_tile * MT + mt) * BM;
-          if (m0 >= p.M) m0 = m_tile * MT * BM;       // row-tile past the end: reload the first one, never stored
+          if (m0 >= p.M) m0 = 0;                      // row-tile past the end: load something valid, never stored
           img0[mt] = m0 / p.OHW;
           oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
         }
         const bool center = (p.center_mask >> ((n_tile * BN) / p.cout_g)) & 1u;
         const int tap_lo = center ? 4 : 0, tap_hi = center ? 5 : p.taps;
-        // ---- L2 prefetch of the NEXT tile's activation boxes (only once per row-tile: for its first channel tile)
-        {
-          const int nt = tile + gridDim.x;
-          const int nm_tile = nt / p.n_tiles_n;
-          if (p.prefetch && nt < p.num_tiles && nt - nm_tile * p.n_tiles_n == 0) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const int m0 = (nm_tile * MT + mt) * BM;
-              if (m0 >= p.M) continue;
-              const int pimg = m0 / p.OHW, poh = (m0 - pimg * p.OHW) / p.OW;
-              for (int tap = 0; tap < p.taps; ++tap) {
-                const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
-                const int rh = kh - p.pad, rw = kw - p.pad;
-                if (p.stride == 1) {
-                  if (p.taps == 9 && !(kw == 1 && kh != 1)) continue;      // taps (0,1) and (2,1) cover the halo rows
-                  for (int cb = 0; cb < p.cblocks; ++cb) tma_prefetch_4d(&tmap_a, cb * BK, rw, poh + rh, pimg);
-                } else {
-                  const int hp = rh & 1, dh = (rh - hp) >> 1, wp = rw & 1, dw = (rw - wp) >> 1;
-                  if (dw != 0) continue;                                     // the dw = -1 box is a subset of dw = 0
-                  for (int cb = 0; cb < p.cblocks; ++cb)
-                    tma_prefetch_5d(&tmap_a, wp * p.Cin + cb * BK, 0, hp, poh + dh, pimg);
-                }
-              }
-            }
-          }
-        }
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
           // stride 2: input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
@@ -309,7 +301,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               else
                 tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
             }
-            tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK, n_tile * BN);
+            if constexpr (MC2)
+              tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
+                             (tap * p.cblocks + cb) * BK, n_tile * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
+            else
+              tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK, n_tile * BN);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -326,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int n_tile_mma = tile % p.n_tiles_n;
         const int tile_kb = ((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
@@ -354,7 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-          umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+          if constexpr (MC2)
+            umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs (the peer writes into it)
+          else
+            umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -385,8 +384,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t sample_px = (int64_t)p.dp.batch * p.OHW;          // pixels per MC sample
       const int c = q * 32 + lane;                                    // channel inside the group (cout_g == BN)
       const bool has_res = res16 != nullptr;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;   // n_tile == output group
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+        const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;   // n_tile == output group
+        const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
         uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.yg[n_tile]);
         const float bias_c = __ldg(p.bias + n_tile * BN + c);
         const bool relu = (p.relu_mask >> n_tile) & 1u;
@@ -463,8 +463,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
     } else
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles_n, n_tile = tile - m_tile * p.n_tiles_n;
+    for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+      const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
+      const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
       const int cbase = n_tile * BN + hf * (BN / 2);      // first (concatenated) output channel of this warp
       const int grp = cbase / p.cout_g;                   // output group and channel offset inside it
       const int cgrp = cbase - grp * p.cout_g;
@@ -586,6 +587,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC2) cluster_sync_all();   // nobody exits while its peer may still multicast into it / signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -631,18 +633,37 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, typename T>
+template <int BN, int MT, bool SWAP, bool MC2, typename T>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
   static bool configured = false;
   constexpr int smem = smem_bytes(BN, MT);
+  auto kern = conv_tc_kernel<BN, MT, SWAP, MC2, T>;
   if (!configured) {
-    BNN_CUDA_OK(
-        cudaFuncSetAttribute(conv_tc_kernel<BN, MT, SWAP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  p.num_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * p.n_tiles_n;
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_tc_kernel<BN, MT, SWAP, T><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  const int m_tiles = (p.M + MT * BM - 1) / (MT * BM);
+  if (MC2) {
+    p.num_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;                 // pair-tiles
+    int grid = 2 * p.num_tiles < (sm_count() & ~1) ? 2 * p.num_tiles : (sm_count() & ~1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  } else {
+    p.num_tiles = m_tiles * p.n_tiles_n;
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+  }
   BNN_LAUNCH_OK();
   return BNN_OK;
 }
@@ -706,11 +727,16 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   }
   // a channel tile never straddles two output groups: BN divides cout_g
   const int BN = cout_g % 256 == 0 ? 256 : (cout_g % 128 == 0 ? 128 : 64);
+  // CTA pairs with weight multicast: BN = 256 kernels with at least one pair of row-tiles per SM pair
+  // (BNN_TC_MC_MIN_TILES overrides the threshold so that unit tests can drive the paired kernel with small shapes)
+  const int64_t mc_min = getenv("BNN_TC_MC_MIN_TILES") ? atoll(getenv("BNN_TC_MC_MIN_TILES")) : 2 * (int64_t)sm_count();
+  const bool mc2 = BN == 256 && getenv("BNN_TC_NOMC") == nullptr &&
+                   ((int64_t)N * OH * OW + tc::BM - 1) / tc::BM >= mc_min;
   {
     const int K = ksize * ksize * Cin;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)BN};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)(mc2 ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
   }
 
@@ -731,9 +757,6 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   p.cout_g = cout_g;
   p.relu_mask = relu_mask;
   p.center_mask = ksize == 3 ? center_mask : 0u;
-  // measured on B200 (C2): prefetching one tile ahead LOWERED throughput 29.3k -> 28.1k img/s (the extra TMA
-  // operations compete with the operand loads), so it is off unless BNN_TC_PREFETCH=1
-  p.prefetch = getenv("BNN_TC_PREFETCH") ? atoi(getenv("BNN_TC_PREFETCH")) : 0;
   p.bias = bias;
   p.res = res;
   for (int g = 0; g < groups; ++g) p.yg[g] = y[g];
@@ -741,22 +764,25 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   cudaStream_t st = (cudaStream_t)stream;
 
   // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
-#define BNN_TC_DISPATCH(BN_, MT_, SWAP_)                                                      \
-  case BN_:                                                                                   \
-    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, __half>(ta, tb, p, st)              \
-                            : tc::launch<BN_, MT_, SWAP_, __nv_bfloat16>(ta, tb, p, st);
+#define BNN_TC_DISPATCH(BN_, MT_, SWAP_, MC2_)                                                      \
+  case BN_:                                                                                         \
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, MC2_, __half>(ta, tb, p, st)              \
+                            : tc::launch<BN_, MT_, SWAP_, MC2_, __nv_bfloat16>(ta, tb, p, st);
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
       cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
   if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
-    switch (BN) { BNN_TC_DISPATCH(128, 2, true) }
+    switch (BN) { BNN_TC_DISPATCH(128, 2, true, false) }
+  }
+  if (mc2) {
+    switch (BN) { BNN_TC_DISPATCH(256, 1, false, true) }
   }
   switch (BN) {
-    BNN_TC_DISPATCH(256, 1, false)
-    BNN_TC_DISPATCH(128, 2, false)
-    BNN_TC_DISPATCH(64, 2, false)
+    BNN_TC_DISPATCH(256, 1, false, false)
+    BNN_TC_DISPATCH(128, 2, false, false)
+    BNN_TC_DISPATCH(64, 2, false, false)
   }
 #undef BNN_TC_DISPATCH
   return BNN_E_UNSUPPORTED;

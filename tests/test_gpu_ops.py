@@ -216,6 +216,17 @@ def test_conv_tc_matches_fp64_conv_of_the_rounded_operands(lib, shape, dt):
     assert err <= (1e-3 if dt == "fp16" else 8e-3) * scale
 
 
+@pytest.mark.parametrize("shape", [s for s in TC_SHAPES if s[4] % 256 == 0])
+def test_conv_tc_cta_pair_multicast(lib, shape, monkeypatch):
+    """the CTA-pair kernel (weight halves multicast into both CTAs) on small shapes incl. an odd number of row-tiles."""
+    monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    got, want = _conv_case(lib, "tc", "fp16", *shape)
+    assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+    monkeypatch.setenv("BNN_TC_NOMC", "1")
+    ref, _ = _conv_case(lib, "tc", "fp16", *shape)
+    assert torch.equal(got, ref)                                  # bit-identical to the single-CTA kernel
+
+
 @pytest.mark.parametrize("kind", [1, 2, 3])
 def test_conv_tc_fused_site(lib, kind):
     N_img, B, S, C, HW = 12, 4, 3, 128, 8
