@@ -70,7 +70,7 @@ def oracle_forward_fn(kind):
     return lambda sd, x, site: nets.vgg19_forward(sd, x, site, True, (2, 3, 4))
 
 
-def time_cpu_reference(kind, classes, S_nominal, budget_images=32, passes=2):
+def time_cpu_reference(kind, classes, S_nominal, budget_images=256, passes=4):
     """The reference's algorithm (results_analyzer.py:236-270: S sequential full forward passes, softmax per exit
     per pass, fp64 host means) through the oracle port, torch's own dropout RNG, all host threads.
     Bounded sample: `budget_images` images x `passes` passes, scaled linearly to S_nominal passes."""
@@ -194,7 +194,7 @@ def reference_arm(args, wl):
     if rank != 0:
         return
     warm, reps = max(args.warmup, 1), max(args.steps, 1)
-    # bounded so that the whole run ends within a few minutes: each step = 16 images x 1 pass, scaled to S
+    # bounded so that the whole run ends within a few minutes: each step = 64 images x 2 passes, scaled to S
     import torch
     from oracle import nets, stats
     torch.set_num_threads(os.cpu_count() or 1)
@@ -202,7 +202,7 @@ def reference_arm(args, wl):
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
     spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.5, tables)
-    nb, passes = 16, 1
+    nb, passes = 64, 2
     x = torch.randn(nb, 3, 32, 32)
     fwd = oracle_forward_fn(kind)
 
