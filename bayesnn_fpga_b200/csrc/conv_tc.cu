@@ -46,6 +46,13 @@ __host__ __device__ constexpr int stages_for(int bn, int mt) {
   return (200 * 1024) / (mt * A_TILE_BYTES + b_tile_bytes(bn)) > 8 ? 8
                                                                   : (200 * 1024) / (mt * A_TILE_BYTES + b_tile_bytes(bn));
 }
+__host__ __device__ constexpr int stages_for_bytes(int stage_bytes) {
+  return (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
+}
+__host__ __device__ constexpr int smem_bytes_pair(int bn, int mt, int pair) {
+  const int stage = mt * A_TILE_BYTES + (pair == 2 ? b_tile_bytes(bn) / 2 : b_tile_bytes(bn));
+  return stages_for_bytes(stage) * stage + 1024 + 256;
+}
 __host__ __device__ constexpr int smem_bytes(int bn, int mt) {
   return stages_for(bn, mt) * (mt * A_TILE_BYTES + b_tile_bytes(bn)) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
@@ -158,6 +165,63 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants ----
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: rank 0 of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// arrive on the barrier at this offset in the LEADER CTA of the pair (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
+}
+
 // same, arriving on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -197,6 +261,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // instruction descriptor for kind::f16: fp32 accumulator, A/B type, both K-major, M = 128, N = BN
 template <typename T>
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int bn) {
+  const uint32_t ab = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+  return (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <typename T>
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   const uint32_t ab = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = f16, 1 = bf16
   return (1u << 4)                 // D format f32
@@ -216,12 +285,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // MC2: the kernel runs as clusters of two CTAs that work on two adjacent row-tiles with the SAME weights; each CTA
 // fetches half of every weight k-block and multicasts it into both shared memories (L2->SM weight traffic halves:
 // 48 KB -> 32 KB per k-block at BN = 256).  A stage is reused only after the MMAs of BOTH CTAs released it.
-template <int BN, int MT, bool SWAP, bool MC2, typename T>
+// PAIR == 2 (CG2): the MMA itself spans the pair - tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = BN.
+// Each CTA keeps only ITS half of the weight k-block in shared memory (the tensor cores of the two SMs exchange the
+// halves), so a stage shrinks to 32 KB (6 stages) and weight reads from shared memory halve.  TMA loads of both
+// CTAs signal the LEADER's full barrier; the leader's MMA thread commits (multicast) to the stage-empty and
+// accumulator-full barriers of both CTAs; both epilogues arrive on the leader's accumulator-empty barrier.
+template <int BN, int MT, bool SWAP, int PAIR, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  constexpr int STAGES = stages_for(BN, MT);
+  constexpr bool MC2 = PAIR == 1;
+  constexpr bool CG2 = PAIR == 2;
+  constexpr bool PAIRED = PAIR != 0;
   constexpr int A_STAGE = MT * A_TILE_BYTES;
-  constexpr int B_TILE = b_tile_bytes(BN);
+  constexpr int B_TILE = CG2 ? b_tile_bytes(BN) / 2 : b_tile_bytes(BN);   // bytes of weights in THIS CTA's stage
+  constexpr int STAGES = stages_for_bytes(A_STAGE + B_TILE);
   constexpr int STAGE_BYTES = A_STAGE + B_TILE;
   constexpr int ACC_COLS = MT * BN;                 // one accumulator set: MT row-tiles of BN columns
   constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered (power of two, <= 512)
@@ -241,10 +318,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.cblocks;
   uint32_t cta_rank = 0;
-  if constexpr (MC2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  if constexpr (PAIRED) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   // scheduling unit: a CTA (tile = (row-tile, channel tile)) or a CTA pair (tile = (row-tile pair, channel tile))
-  const int sched_id = MC2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int sched_n = MC2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int sched_id = PAIRED ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIRED ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -255,14 +332,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);         // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (warp == 1) {
+    if constexpr (CG2) tmem_alloc_2sm<TMEM_COLS>(tmem_ptr); else tmem_alloc<TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to it
+  if constexpr (PAIRED) cluster_sync_all();   // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -273,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
-        const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
+        const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
         int img0[MT], oh0[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -292,20 +371,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int wp = rw & 1, dw = (rw - wp) >> 1;
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if constexpr (CG2) {
+              // both CTAs' loads complete on the leader's barrier: it expects the bytes of the pair
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
-              if (p.stride == 1)
-                tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+              for (int mt = 0; mt < MT; ++mt) {
+                uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
+                if (p.stride == 1)
+                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                else
+                  tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh,
+                                  img0[mt]);
+              }
+              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK,
+                              n_tile * BN + (int)cta_rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
+                if (p.stride == 1)
+                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                else
+                  tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
+              }
+              if constexpr (MC2)
+                tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
+                               (tap * p.cblocks + cb) * BK, n_tile * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
               else
-                tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
+                tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK,
+                            n_tile * BN);
             }
-            if constexpr (MC2)
-              tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
-                             (tap * p.cblocks + cb) * BK, n_tile * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
-            else
-              tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK, n_tile * BN);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -316,8 +412,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<T>(SWAP ? MT * BM : BN);
+    if (lane == 0 && !(CG2 && cta_rank != 0)) {         // CG2: only the leader CTA issues MMAs
+      constexpr uint32_t idesc = CG2 ? make_idesc_m<T>(2 * BM, BN) : make_idesc<T>(SWAP ? MT * BM : BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -332,7 +428,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
-          if (SWAP) {
+          if (CG2) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+          } else if (SWAP) {
             // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
             const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
 #pragma unroll
@@ -350,7 +455,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-          if constexpr (MC2)
+          if constexpr (CG2)
+            umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
+          else if constexpr (MC2)
             umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs (the peer writes into it)
           else
             umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
@@ -359,7 +466,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);                     // accumulators complete -> epilogue
+        if constexpr (CG2)
+          umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)3);   // accumulators complete in both CTAs -> both epilogues
+        else
+          umma_commit(&tmem_full[acc]);                   // accumulators complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -386,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool has_res = res16 != nullptr;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;   // n_tile == output group
-        const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
+        const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
         uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.yg[n_tile]);
         const float bias_c = __ldg(p.bias + n_tile * BN + c);
         const bool relu = (p.relu_mask >> n_tile) & 1u;
@@ -465,7 +575,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else
     for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
       const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
-      const int m_tile = MC2 ? 2 * m_unit + (int)cta_rank : m_unit;
+      const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
       const int cbase = n_tile * BN + hf * (BN / 2);      // first (concatenated) output channel of this warp
       const int grp = cbase / p.cout_g;                   // output group and channel offset inside it
       const int cgrp = cbase - grp * p.cout_g;
@@ -579,7 +689,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -587,10 +699,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC2) cluster_sync_all();   // nobody exits while its peer may still multicast into it / signal it
+  if constexpr (PAIRED) cluster_sync_all();   // nobody exits while its peer may still multicast into it / signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (CG2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -633,11 +745,12 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, bool MC2, typename T>
+template <int BN, int MT, bool SWAP, int PAIR, typename T>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
   static bool configured = false;
-  constexpr int smem = smem_bytes(BN, MT);
-  auto kern = conv_tc_kernel<BN, MT, SWAP, MC2, T>;
+  constexpr int smem = smem_bytes_pair(BN, MT, PAIR);
+  constexpr bool MC2 = PAIR != 0;
+  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, T>;
   if (!configured) {
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -730,13 +843,16 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // CTA pairs with weight multicast: BN = 256 kernels with at least one pair of row-tiles per SM pair
   // (BNN_TC_MC_MIN_TILES overrides the threshold so that unit tests can drive the paired kernel with small shapes)
   const int64_t mc_min = getenv("BNN_TC_MC_MIN_TILES") ? atoll(getenv("BNN_TC_MC_MIN_TILES")) : 2 * (int64_t)sm_count();
-  const bool mc2 = BN == 256 && getenv("BNN_TC_NOMC") == nullptr &&
-                   ((int64_t)N * OH * OW + tc::BM - 1) / tc::BM >= mc_min;
+  const bool mc2_any = getenv("BNN_TC_NOMC") == nullptr && ((int64_t)N * OH * OW + tc::BM - 1) / tc::BM >= mc_min;
+  const bool mc2 = BN == 256 && mc2_any;
+  const bool cg2_narrow_box = mc2_any && BN < 256 && getenv("BNN_TC_CG2_NARROW") &&
+                              atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
+                              !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
   {
     const int K = ksize * ksize * Cin;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)(mc2 ? BN / 2 : BN)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
   }
 
@@ -764,25 +880,36 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   cudaStream_t st = (cudaStream_t)stream;
 
   // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
-#define BNN_TC_DISPATCH(BN_, MT_, SWAP_, MC2_)                                                      \
-  case BN_:                                                                                         \
-    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, MC2_, __half>(ta, tb, p, st)              \
-                            : tc::launch<BN_, MT_, SWAP_, MC2_, __nv_bfloat16>(ta, tb, p, st);
+#define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_)                                                      \
+  case BN_:                                                                                          \
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, __half>(ta, tb, p, st)              \
+                            : tc::launch<BN_, MT_, SWAP_, PAIR_, __nv_bfloat16>(ta, tb, p, st);
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
       cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
+  const bool cg2 = mc2_any && !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
+  const bool cg2_narrow = getenv("BNN_TC_CG2_NARROW") && atoi(getenv("BNN_TC_CG2_NARROW")) == 1;   // experiment
+  if (cg2 && cg2_narrow && BN < 256) {
+    switch (BN) {
+      BNN_TC_DISPATCH(128, 2, false, 2)
+      BNN_TC_DISPATCH(64, 2, false, 2)
+    }
+  }
   if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
-    switch (BN) { BNN_TC_DISPATCH(128, 2, true, false) }
+    switch (BN) { BNN_TC_DISPATCH(128, 2, true, 0) }
+  }
+  if (cg2 && BN == 256) {
+    switch (BN) { BNN_TC_DISPATCH(256, 1, false, 2) }
   }
   if (mc2) {
-    switch (BN) { BNN_TC_DISPATCH(256, 1, false, true) }
+    switch (BN) { BNN_TC_DISPATCH(256, 1, false, 1) }
   }
   switch (BN) {
-    BNN_TC_DISPATCH(256, 1, false, false)
-    BNN_TC_DISPATCH(128, 2, false, false)
-    BNN_TC_DISPATCH(64, 2, false, false)
+    BNN_TC_DISPATCH(256, 1, false, 0)
+    BNN_TC_DISPATCH(128, 2, false, 0)
+    BNN_TC_DISPATCH(64, 2, false, 0)
   }
 #undef BNN_TC_DISPATCH
   return BNN_E_UNSUPPORTED;

@@ -216,15 +216,27 @@ def test_conv_tc_matches_fp64_conv_of_the_rounded_operands(lib, shape, dt):
     assert err <= (1e-3 if dt == "fp16" else 8e-3) * scale
 
 
+@pytest.mark.parametrize("cg2", ["0", "1"])
 @pytest.mark.parametrize("shape", [s for s in TC_SHAPES if s[4] % 256 == 0])
-def test_conv_tc_cta_pair_multicast(lib, shape, monkeypatch):
-    """the CTA-pair kernel (weight halves multicast into both CTAs) on small shapes incl. an odd number of row-tiles."""
+def test_conv_tc_cta_pair_multicast(lib, shape, cg2, monkeypatch):
+    """the CTA-pair kernels on small shapes incl. an odd number of row-tiles: cg2=0 weight halves TMA-multicast into
+    both CTAs, 1-CTA MMAs; cg2=1 tcgen05.mma.cta_group::2 (M = 256 over the pair, each CTA keeps half the weights)."""
     monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    monkeypatch.setenv("BNN_TC_CG2", cg2)
     got, want = _conv_case(lib, "tc", "fp16", *shape)
     assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
     monkeypatch.setenv("BNN_TC_NOMC", "1")
     ref, _ = _conv_case(lib, "tc", "fp16", *shape)
     assert torch.equal(got, ref)                                  # bit-identical to the single-CTA kernel
+
+
+@pytest.mark.parametrize("shape", [s for s in TC_SHAPES if s[4] % 256 != 0])
+def test_conv_tc_cta_group2_narrow(lib, shape, monkeypatch):
+    """cta_group::2 with 128 / 64 output channels (two row-tiles per CTA share each weight half)."""
+    monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    monkeypatch.setenv("BNN_TC_CG2_NARROW", "1")
+    got, want = _conv_case(lib, "tc", "fp16", *shape)
+    assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
 
 
 @pytest.mark.parametrize("kind", [1, 2, 3])
