@@ -388,6 +388,7 @@ def main():
                        "batch_per_gpu": B, "global_batch": images_per_step, "S": S, "exits": E, "classes": classes,
                        "partition": "samples" if shard_samples else ("batch" if world > 1 else "none"),
                        "l2": "per-step activation working set (GiB) >> 126 MB L2; no explicit flush",
+                       "cuda_graph": os.environ.get("BNN_CUDA_GRAPH", "1") != "0",
                        "algorithmic_gflop_per_image": 2e-9 * (pre_macs + S * suf_macs)},
             "tflops_whole_step": step_flops * (world if not shard_samples else world) / (ms / args.steps * 1e-3) / 1e12,
             "frac_of_tensor_peak_whole_step": step_flops / (ms / args.steps * 1e-3) / 1e12 / peaks["sustained"],
