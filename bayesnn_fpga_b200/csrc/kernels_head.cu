@@ -309,6 +309,53 @@ __global__ void calibration_kernel(const float* __restrict__ probs, const int32_
   atomicAdd(&bin_stats[bin * 3 + 2], (float)hit);
 }
 
+// per-image NLL / Brier (MSE) / top-1 hit, block-reduced in a fixed order; partial[block][3]
+__global__ void __launch_bounds__(256) dataset_metrics_kernel(const float* __restrict__ probs,
+                                                              const int32_t* __restrict__ labels, int N, int C,
+                                                              float* __restrict__ partial) {
+  __shared__ float sh[3][256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float nll = 0.f, mse = 0.f, hit = 0.f;
+  if (i < N) {
+    const float* p = probs + (size_t)i * C;
+    const int y = labels[i];
+    int best = 0;
+    float bp = p[0];
+    for (int c = 0; c < C; ++c) {
+      const float v = p[c];
+      const float t = c == y ? 1.f : 0.f;
+      mse += (v - t) * (v - t);
+      if (v > bp) {
+        bp = v;
+        best = c;
+      }
+    }
+    // results_analyzer.py:499-500: clip to [1e-256, 1 - 1e-256] in float64; in float32 the lower clip is the
+    // smallest normal and the upper clip is 1
+    nll = -logf(fmaxf(p[y], 1.17549435e-38f));
+    hit = best == y ? 1.f : 0.f;
+  }
+  sh[0][threadIdx.x] = nll;
+  sh[1][threadIdx.x] = mse;
+  sh[2][threadIdx.x] = hit;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void dataset_metrics_reduce_kernel(const float* __restrict__ partial, int blocks, float inv_n,
+                                              float* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= 3) return;
+  double a = 0.0;
+  for (int b = 0; b < blocks; ++b) a += (double)partial[b * 3 + k];
+  out[k] = (float)(a * inv_n);
+}
+
 }  // namespace bnn
 
 using namespace bnn;
@@ -384,6 +431,19 @@ int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C
   BNN_CUDA_OK(cudaMemsetAsync(bin_stats, 0, sizeof(float) * 3 * n_bins, st));
   if (N == 0) return BNN_OK;
   calibration_kernel<<<(N + 127) / 128, 128, 0, st>>>(probs, labels, N, C, n_bins, conf, correct, bin_stats);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+int bnn_dataset_metrics(const float* probs, const int32_t* labels, int N, int C, float* workspace, float* out,
+                        void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(probs && labels && workspace && out && N > 0 && C > 0, "bnn_dataset_metrics: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (N + 255) / 256;
+  dataset_metrics_kernel<<<blocks, 256, 0, st>>>(probs, labels, N, C, workspace);
+  BNN_LAUNCH_OK();
+  dataset_metrics_reduce_kernel<<<1, 32, 0, st>>>(workspace, blocks, 1.f / (float)N, out);
   BNN_LAUNCH_OK();
   return BNN_OK;
 }

@@ -139,12 +139,27 @@ class FullAnalysis:
                     * float(inside.mean())
         return total
 
+    def dataset_metrics(self, p, label_index):
+        """(nll, mse, accuracy) of results_analyzer.py:497-503 computed on the device (`bnn_dataset_metrics`)."""
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.require_device()
+            dp = torch.as_tensor(np.ascontiguousarray(p), dtype=torch.float32, device=self.device)
+            dl = torch.as_tensor(np.ascontiguousarray(label_index), dtype=torch.int32, device=self.device)
+            N, C = dp.shape
+            if N == 0:
+                return 0.0, 0.0, 0.0
+            ws = torch.empty(3 * ((N + 255) // 256), dtype=torch.float32, device=self.device)
+            out = torch.empty(3, dtype=torch.float32, device=self.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.bnn_dataset_metrics(dp.data_ptr(), dl.data_ptr(), N, C, ws.data_ptr(), out.data_ptr(), stream))
+            nll, mse, acc = out.cpu().tolist()
+        return nll, mse, acc
+
     def ece_eval_binary(self, p, label):
-        """(ece, nll, mse, accuracy) like :497-505 with the histogram ECE in place of the KDE one."""
-        mse = np.mean(np.sum((p - label) ** 2, 1))
-        pc = np.clip(p, 1e-256, 1 - 1e-256)
-        nll = -np.sum(label * np.log(pc)) / p.shape[0]
-        accu = float(np.mean(np.argmax(pc, 1) == np.argmax(label, 1)))
+        """(ece, nll, mse, accuracy) like :497-505 with the histogram ECE in place of the KDE one (KDEpy is not
+        available); everything is computed on the device."""
+        nll, mse, accu = self.dataset_metrics(p, np.argmax(label, axis=1))
         return self.ece_hist_binary(p, label), nll, mse, accu
 
     def entropy(self, probs):

@@ -156,6 +156,12 @@ int bnn_finalize(const float* sum_p, const float* sum_logit, const float* sum_pl
 int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C, int n_bins, float* conf,
                          int32_t* correct, float* bin_stats, void* stream);
 
+/* Dataset-level scores of ece_eval_binary (results_analyzer.py:497-503) on the device:
+ * out[0] = NLL = -mean log p[label], out[1] = MSE = mean sum_c (p_c - onehot_c)^2, out[2] = top-1 accuracy.
+ * workspace: float32 [3 * ceil(N / 256)] (fixed-order two-stage reduction: deterministic). */
+int bnn_dataset_metrics(const float* probs, const int32_t* labels, int N, int C, float* workspace, float* out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

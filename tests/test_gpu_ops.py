@@ -187,6 +187,14 @@ def test_calibration_bins_and_ece(lib):
         assert abs(got - float(z["ece%d" % k])) < 1e-4            # reference's own ece_hist_binary value
         assert abs(fa.ece_width(p, lab) - stats.ece_width(p.astype(np.float32), lab)) < 1e-5
     assert fa.ece_width(np.zeros((0, 10)), np.zeros(0, dtype=np.int64)) == 0.0        # empty dataset
+    # NLL / MSE / accuracy of ece_eval_binary (results_analyzer.py:497-503) on the device vs the float64 restatement
+    for k in range(3):
+        p, lab = z["p%d" % k], z["label%d" % k]
+        onehot = np.eye(p.shape[1])[lab]
+        nll, mse, acc = stats.nll_mse_acc(p, onehot)
+        ece, g_nll, g_mse, g_acc = fa.ece_eval_binary(p, onehot)
+        assert abs(g_nll - nll) < 1e-5 * max(1.0, nll) and abs(g_mse - mse) < 1e-6 and abs(g_acc - acc) < 1e-7
+        assert abs(ece - float(z["ece%d" % k])) < 1e-4
 
 
 TC_SHAPES = [
