@@ -25,7 +25,8 @@ class DropDesc(ctypes.Structure):
     """struct bnn_drop_desc"""
     _fields_ = [("kind", ctypes.c_int), ("p", ctypes.c_float), ("seed", ctypes.c_uint64),
                 ("stream_id", ctypes.c_uint32), ("sample0", ctypes.c_uint32), ("batch", ctypes.c_int),
-                ("masks", ctypes.c_void_p), ("n_masks", ctypes.c_int), ("cnt0", ctypes.c_int)]
+                ("masks", ctypes.c_void_p), ("n_masks", ctypes.c_int), ("cnt0", ctypes.c_int),
+                ("compact_pos", ctypes.c_void_p), ("compact_idx", ctypes.c_void_p), ("compact_c", ctypes.c_int)]
 
 
 def _stale():
@@ -71,6 +72,8 @@ _SIGS = {
                       [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_conv2d_tc_grouped": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
                               [ctypes.c_int] * 8 + [ctypes.c_void_p]),
+    "bnn_conv2d_tc_gathered": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
+                               [ctypes.c_int] * 10 + [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "bnn_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_maxpool2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),

@@ -66,6 +66,13 @@ struct Params {
   int groups, cout_g;
   uint32_t relu_mask;   // bit g: ReLU on group g
   uint32_t center_mask; // bit g: group g is a 1x1 kernel stored in the centre tap of the 3x3 - only that tap runs
+  // Masksembles gathered K (bnn_conv2d_tc_gathered): the input holds only the kept channels of each sample's mask
+  // (Cin = kept count rounded up to 16), so the last channel block of a tap issues `last_ksteps` (< 4) MMA k-steps,
+  // and the weights come in one pre-gathered set per mask row: rows [r * Cout, (r + 1) * Cout) for a tile of sample s,
+  // r = (wsel_cnt0 + s) % wsel_n.  wsel_n == 0: one weight set.
+  int last_ksteps;
+  int wsel_n, wsel_cnt0, wsel_sample_px;
+  int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
   const float* bias;
   const void* res;
   void* yg[4];
@@ -290,7 +297,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // halves), so a stage shrinks to 32 KB (6 stages) and weight reads from shared memory halve.  TMA loads of both
 // CTAs signal the LEADER's full barrier; the leader's MMA thread commits (multicast) to the stage-empty and
 // accumulator-full barriers of both CTAs; both epilogues arrive on the leader's accumulator-empty barrier.
-template <int BN, int MT, bool SWAP, int PAIR, typename T>
+// COMPACT (non-swapped epilogue only; the swapped one decides at run time): a fused Masksembles site may store
+// only the kept channels of each sample's mask (DropParams::compact_pos), 2 bytes at a time.
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   constexpr bool MC2 = PAIR == 1;
@@ -360,9 +369,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (m0 >= p.M) m0 = 0;                      // row-tile past the end: load something valid, never stored
           img0[mt] = m0 / p.OHW;
           oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
+          if (p.a_img_mod > 0) img0[mt] %= p.a_img_mod;
         }
         const bool center = (p.center_mask >> ((n_tile * BN) / p.cout_g)) & 1u;
         const int tap_lo = center ? 4 : 0, tap_hi = center ? 5 : p.taps;
+        // weight set of this tile's MC sample (host guarantees that a tile / tile pair never straddles two samples)
+        int wrow = n_tile * BN;
+        if (p.wsel_n > 0) {
+          int m0 = m_tile * MT * BM;
+          if (m0 >= p.M) m0 = 0;
+          wrow += ((p.wsel_cnt0 + m0 / p.wsel_sample_px) % p.wsel_n) * p.Cout;
+        }
         for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int kh = p.taps == 1 ? p.pad : tap / 3, kw = p.taps == 1 ? p.pad : tap - (tap / 3) * 3;
           // stride 2: input row 2*oh + kh - pad -> (half-row index, row parity); same for columns
@@ -383,8 +400,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh,
                                   img0[mt]);
               }
-              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK,
-                              n_tile * BN + (int)cta_rank * (BN / 2));
+              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK,
+                              wrow + (int)cta_rank * (BN / 2));
             } else {
               mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
@@ -397,10 +414,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
               if constexpr (MC2)
                 tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
-                               (tap * p.cblocks + cb) * BK, n_tile * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
+                               tap * p.Cin + cb * BK, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
               else
-                tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], (tap * p.cblocks + cb) * BK,
-                            n_tile * BN);
+                tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK, wrow);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -424,7 +440,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        int cb = 0;
         for (int kb = 0; kb < tile_kb; ++kb) {
+          // gathered K: the last channel block of a tap holds fewer than 64 valid channels
+          const int ksteps = (++cb == p.cblocks) ? p.last_ksteps : BK / UMMA_K;
+          if (cb == p.cblocks) cb = 0;
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
@@ -434,15 +454,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
+                if (k < ksteps)
+                  umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k),
+                               idesc, (kb | k) != 0 ? 1u : 0u);
             }
           } else if (SWAP) {
             // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
             const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              if (k < ksteps)
+                umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           } else {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -450,8 +472,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+                if (k < ksteps)
+                  umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
               }
             }
           }
@@ -526,6 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t kw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
                             0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
           float fac = 1.f;
+          int cpos = 0;                                   // Masksembles gathered layout: slot of channel c, -1 = dropped
           if (p.dp.kind == BNN_DROP_ELEMENT) {
             // a 32-pixel chunk lies inside one MC sample whenever sample_px % 32 == 0 (host-checked)
             const uint32_t s_local = (uint32_t)((int64_t)m0 / sample_px);
@@ -545,6 +569,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int64_t s_local = (int64_t)m0 / sample_px;
             const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
             fac = __ldg(p.dp.masks + (size_t)mrow * BN + c);
+            if (p.dp.compact_pos != nullptr) cpos = (int)__ldg(p.dp.compact_pos + (size_t)mrow * BN + c);
           }
           const uint16_t* rp = res16 + off0;
           uint16_t* yp = y16 + off0;
@@ -555,15 +580,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) rr[j] = (j < nvalid) ? (uint32_t)__ldg(rp + j * BN) : 0u;
           }
           tmem_ld_wait();
-          if (nvalid > 0) {
+          auto value = [&](int j) -> uint16_t {
+            float f = __uint_as_float(v[j]) + bias_c;
+            if (has_res) f += unpack2<T>(rr[j]).x;
+            if (relu) f = fmaxf(f, 0.f);
+            f *= ((kw[j & 7] >> (8 * (j >> 3) + (lane & 7))) & 1u) ? fac : 0.f;
+            return (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
+          };
+          if (nvalid > 0 && p.dp.compact_pos == nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float f = __uint_as_float(v[j]) + bias_c;
-              if (has_res) f += unpack2<T>(rr[j]).x;
-              if (relu) f = fmaxf(f, 0.f);
-              f *= ((kw[j & 7] >> (8 * (j >> 3) + (lane & 7))) & 1u) ? fac : 0.f;
-              if (j < nvalid) yp[j * BN] = (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) yp[j * BN] = value(j);
+          } else if (nvalid > 0 && cpos >= 0) {
+            // kept channels only, row stride = compact_c: the kept lanes of the warp write one contiguous run
+            const int kc = p.dp.compact_c;
+            uint16_t* yc = y16 + (size_t)m0 * kc + cpos;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) yc[j * kc] = value(j);
           }
         }
         tc_fence_before();
@@ -665,6 +699,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int j = 0; j < 32; ++j) f[j] *= ((bits >> j) & 1u) ? p.dp.scale : 0.f;
             } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
               const int mrow = (int)(((int64_t)p.dp.cnt0 + p.dp.sample0 + s_local) % p.dp.n_masks);
+              if constexpr (COMPACT) {
+                if (p.dp.compact_pos != nullptr) {
+                  // gathered layout: channel c0 + j goes to slot pos[j] of this pixel's compact row (-1: dropped)
+                  const uint4* pp = reinterpret_cast<const uint4*>(p.dp.compact_pos + (size_t)mrow * p.Cout + c0);
+                  uint16_t* yc = reinterpret_cast<uint16_t*>(y) + (size_t)m * p.dp.compact_c;
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const uint4 pw4 = __ldg(pp + j4);
+                    const uint32_t pw[4] = {pw4.x, pw4.y, pw4.z, pw4.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                      const int pos = (int)(int16_t)((t & 1) ? (pw[t >> 1] >> 16) : (pw[t >> 1] & 0xffffu));
+                      if (pos >= 0) yc[pos] = (uint16_t)(pack2<T>(f[8 * j4 + t], 0.f) & 0xffffu);
+                    }
+                  }
+                  continue;
+                }
+              }
               const float* mk = p.dp.masks + (size_t)mrow * p.Cout + c0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -745,12 +797,12 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, int PAIR, typename T>
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, typename T>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
   static bool configured = false;
   constexpr int smem = smem_bytes_pair(BN, MT, PAIR);
   constexpr bool MC2 = PAIR != 0;
-  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, T>;
+  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, T>;
   if (!configured) {
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -789,9 +841,15 @@ static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 using namespace bnn;
 
 // shared runner: `groups` outputs of `cout_g` channels each (groups == 1: an ordinary convolution)
+struct GatherSel {
+  int n_masks, cnt0, batch;   // weight set of image n: (cnt0 + n / batch) % n_masks; cnt0 already includes sample0
+  int x_has_samples;          // 0: x holds `batch` images shared by all samples
+};
+
 static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
-                       int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream) {
+                       int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
+                       const GatherSel* gsel = nullptr) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
@@ -803,7 +861,8 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const int Cout = groups * cout_g;
   const int pad = ksize == 3 ? 1 : 0;
   const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
-  const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && cout_g % 64 == 0 &&
+  const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) &&
+                  (gsel ? (Cin % 16 == 0 && Cin > 0) : Cin % 64 == 0) && cout_g % 64 == 0 &&
                   (stride == 1 || (H % 2 == 0 && W % 2 == 0)) && tc::pow2(OW) && tc::pow2(OH) && OW <= 128;
   if (!ok) {
     set_error("%s: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", who, ksize, stride, Cin,
@@ -816,6 +875,19 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
                 "%s: Masksembles site without a mask table", who);
   }
+  if (gsel) {
+    BNN_REQUIRE(gsel->n_masks > 0 && gsel->batch > 0 && N % gsel->batch == 0, "%s: bad mask rotation (n=%d batch=%d N=%d)",
+                who, gsel->n_masks, gsel->batch, N);
+    BNN_REQUIRE(((int64_t)gsel->batch * OH * OW) % (2 * tc::BM) == 0,
+                "%s: batch * OH * OW = %lld must be a multiple of %d (one weight set per MMA tile pair)", who,
+                (long long)gsel->batch * OH * OW, 2 * tc::BM);
+  }
+  const bool compact_out = drop && drop->kind == BNN_DROP_MASKSEMBLES && drop->compact_pos != nullptr;
+  if (compact_out) {
+    BNN_REQUIRE(drop->compact_c > 0 && drop->compact_c % 8 == 0 && drop->compact_c <= Cout,
+                "%s: compact row length %d must be a positive multiple of 8 and <= Cout", who, drop->compact_c);
+    BNN_REQUIRE(cout_g == 128 || cout_g % 256 == 0, "%s: compact Masksembles output needs Cout = 128 or a multiple of 256", who);
+  }
   if (N == 0) return BNN_OK;
   BNN_REQUIRE((int64_t)N * OH * OW < (int64_t)1 << 31, "%s: M overflows int32", who);
 
@@ -826,13 +898,14 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
 
   CUtensorMap ta, tb;
   const cuuint64_t eb = 2;
+  const int N_in = (gsel && !gsel->x_has_samples) ? gsel->batch : N;     // images held by x
   if (stride == 1) {
-    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N_in};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)H * W * Cin * eb};
     const cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
     if (int rc = tc::encode_map(&ta, dtype, 4, x, dims, strides, box)) return rc;
   } else {
-    const cuuint64_t dims[5] = {(cuuint64_t)2 * Cin, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+    const cuuint64_t dims[5] = {(cuuint64_t)2 * Cin, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N_in};
     const cuuint64_t strides[4] = {(cuuint64_t)2 * Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)2 * W * Cin * eb,
                                    (cuuint64_t)H * W * Cin * eb};
     const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
@@ -844,13 +917,15 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // (BNN_TC_MC_MIN_TILES overrides the threshold so that unit tests can drive the paired kernel with small shapes)
   const int64_t mc_min = getenv("BNN_TC_MC_MIN_TILES") ? atoll(getenv("BNN_TC_MC_MIN_TILES")) : 2 * (int64_t)sm_count();
   const bool mc2_any = getenv("BNN_TC_NOMC") == nullptr && ((int64_t)N * OH * OW + tc::BM - 1) / tc::BM >= mc_min;
-  const bool mc2 = BN == 256 && mc2_any;
-  const bool cg2_narrow_box = mc2_any && BN < 256 && getenv("BNN_TC_CG2_NARROW") &&
+  const bool cg2 = mc2_any && !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
+  // (the compact-store epilogue exists for the single-CTA and the cta_group::2 kernels, not for the multicast one)
+  const bool mc2 = BN == 256 && mc2_any && !(compact_out && !cg2);
+  const bool cg2_narrow_box = mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
   {
     const int K = ksize * ksize * Cin;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
     const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
@@ -862,8 +937,15 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   p.n_tiles_n = Cout / BN;
   p.num_tiles = ((p.M + tc::BM - 1) / tc::BM) * p.n_tiles_n;
   p.taps = ksize * ksize;
-  p.cblocks = Cin / tc::BK;
+  p.cblocks = (Cin + tc::BK - 1) / tc::BK;
   p.Cin = Cin;
+  p.last_ksteps = (Cin - (p.cblocks - 1) * tc::BK) / tc::UMMA_K;
+  if (gsel) {
+    p.wsel_n = gsel->n_masks;
+    p.wsel_cnt0 = ((gsel->cnt0 % gsel->n_masks) + gsel->n_masks) % gsel->n_masks;
+    p.wsel_sample_px = gsel->batch * OH * OW;
+    p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
+  }
   p.stride = stride;
   p.pad = pad;
   p.OH = OH;
@@ -880,17 +962,28 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   cudaStream_t st = (cudaStream_t)stream;
 
   // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
-#define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_)                                                      \
+#define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_)                                           \
   case BN_:                                                                                          \
-    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, __half>(ta, tb, p, st)              \
-                            : tc::launch<BN_, MT_, SWAP_, PAIR_, __nv_bfloat16>(ta, tb, p, st);
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, __half>(ta, tb, p, st)    \
+                            : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, __nv_bfloat16>(ta, tb, p, st);
+#define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_) BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, false)
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
       cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
-  const bool cg2 = mc2_any && !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
-  const bool cg2_narrow = getenv("BNN_TC_CG2_NARROW") && atoi(getenv("BNN_TC_CG2_NARROW")) == 1;   // experiment
+  const bool cg2_narrow = cg2_narrow_box;   // experiment
+  if (compact_out && BN == 256) {
+    // compact Masksembles stores: dedicated instantiations so that the other kernels keep their code size
+    if (cg2 && mc2) {
+      switch (BN) { BNN_TC_DISPATCH_C(256, 1, false, 2, true) }
+    }
+    switch (BN) { BNN_TC_DISPATCH_C(256, 1, false, 0, true) }
+  }
+  if (compact_out && !(swap_ok && getenv("BNN_TC_NOSWAP") == nullptr)) {
+    set_error("%s: compact Masksembles output is not available for this geometry", who);
+    return BNN_E_UNSUPPORTED;
+  }
   if (cg2 && cg2_narrow && BN < 256) {
     switch (BN) {
       BNN_TC_DISPATCH(128, 2, false, 2)
@@ -900,7 +993,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
     switch (BN) { BNN_TC_DISPATCH(128, 2, true, 0) }
   }
-  if (cg2 && BN == 256) {
+  if (cg2 && mc2) {
     switch (BN) { BNN_TC_DISPATCH(256, 1, false, 2) }
   }
   if (mc2) {
@@ -912,6 +1005,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     BNN_TC_DISPATCH(64, 2, false, 0)
   }
 #undef BNN_TC_DISPATCH
+#undef BNN_TC_DISPATCH_C
   return BNN_E_UNSUPPORTED;
 }
 
@@ -928,4 +1022,14 @@ extern "C" int bnn_conv2d_tc_grouped(const void* x, const void* w, const float* 
                                      int cout_per_group, int ksize, int stride, void* stream) {
   return conv_tc_run("bnn_conv2d_tc_grouped", x, w, bias, nullptr, y, n_groups, relu_mask, center_mask, dtype, N, H, W, Cin,
                      cout_per_group, ksize, stride, nullptr, stream);
+}
+
+extern "C" int bnn_conv2d_tc_gathered(const void* x, const void* w, const float* bias, void* const* y, int n_groups,
+                                      uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Kc,
+                                      int cout_per_group, int ksize, int stride, int n_masks, int cnt0,
+                                      uint32_t sample0, int batch, int x_has_samples, void* stream) {
+  BNN_REQUIRE(n_masks > 0, "bnn_conv2d_tc_gathered: n_masks must be positive");
+  GatherSel g{n_masks, (int)(((int64_t)cnt0 + (int64_t)sample0) % n_masks), batch, x_has_samples};
+  return conv_tc_run("bnn_conv2d_tc_gathered", x, w, bias, nullptr, y, n_groups, relu_mask, center_mask, dtype, N, H, W, Kc,
+                     cout_per_group, ksize, stride, nullptr, stream, &g);
 }

@@ -339,6 +339,34 @@ __global__ void __launch_bounds__(256) maxpool_vec8_kernel(const T* __restrict__
   *reinterpret_cast<Vec8<T>*>(y + i * 8) = o;
 }
 
+
+// Masksembles "gathered" layout: y[s][b][px][j] = x[s or 0][b][px][idx[row(s)][j]] for the kept channels of sample
+// s's mask row (utils.py:165-168 rotation), zeros in the padding slots.  One thread = 8 consecutive output slots of
+// one pixel (one 16-byte store in 16-bit storage); the pixel's input channels come from one or two cache lines.
+template <typename T>
+__global__ void __launch_bounds__(256) masksembles_compact_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                  int64_t pixels, int C, int S_local,
+                                                                  int x_has_samples, DropParams dp) {
+  const int oct = dp.compact_c >> 3;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)S_local * pixels * oct) return;
+  const int j8 = (int)(t % oct);
+  const int64_t sp = t / oct;
+  const int64_t px = sp % pixels;
+  const int s = (int)(sp / pixels);
+  const int row = (int)(((int64_t)dp.cnt0 + dp.sample0 + s) % dp.n_masks);
+  const uint4 iw = __ldg(reinterpret_cast<const uint4*>(dp.compact_idx + (size_t)row * dp.compact_c) + j8);
+  const uint32_t w[4] = {iw.x, iw.y, iw.z, iw.w};
+  const T* xp = x + ((x_has_samples ? (int64_t)s * pixels : 0) + px) * C;
+  Vec8<T> out;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = (int)(int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu));
+    out.v[k] = idx >= 0 ? xp[idx] : from_f32<T>(0.f);
+  }
+  *reinterpret_cast<Vec8<T>*>(y + (sp * dp.compact_c + (int64_t)j8 * 8)) = out;
+}
+
 template <typename F>
 static int dispatch_dtype(int dtype, F&& f) {
   switch (dtype) {
@@ -444,6 +472,19 @@ int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int
   const int64_t n_per = per_image * drop->batch;
   if (n_per == 0 || S_local == 0) return BNN_OK;
   const DropParams dp = make_drop_params(drop, C);
+  if (dp.compact_pos != nullptr) {
+    BNN_REQUIRE(dp.compact_idx != nullptr && dp.compact_c > 0 && dp.compact_c % 8 == 0 && C < 32768,
+                "bnn_dropout: bad compact layout (compact_c=%d, C=%d)", dp.compact_c, C);
+    const int64_t pixels = n_per / C;
+    const int64_t nthr = (int64_t)S_local * pixels * (dp.compact_c / 8);
+    return dispatch_dtype(dtype, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      masksembles_compact_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+          (const T*)x, (T*)y, pixels, C, S_local, x_has_samples, dp);
+      BNN_LAUNCH_OK();
+      return BNN_OK;
+    });
+  }
   const int64_t threads = (n_per + 7) / 8;
   return dispatch_dtype(dtype, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;

@@ -67,6 +67,12 @@ struct DropParams {
   const float* masks;
   int n_masks, cnt0;
   int channels;     // row length of `masks`
+  // Masksembles gathered layout (optional): slot of channel c among the kept channels of mask row r (int16
+  // [n_masks][channels], -1 = dropped), the inverse table (int16 [n_masks][compact_c], -1 = padding) and the
+  // row length of the compact output
+  const int16_t* compact_pos;
+  const int16_t* compact_idx;
+  int compact_c;
 };
 
 inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
@@ -87,6 +93,11 @@ inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
   q.n_masks = d->n_masks;
   q.cnt0 = d->cnt0;
   q.channels = channels;
+  if (d->kind == BNN_DROP_MASKSEMBLES && d->compact_pos != nullptr) {
+    q.compact_pos = d->compact_pos;
+    q.compact_idx = d->compact_idx;
+    q.compact_c = d->compact_c;
+  }
   return q;
 }
 

@@ -257,7 +257,7 @@ def _ptr(t):
 class Engine:
     """Executes a :class:`Graph` on the current CUDA device through the C ABI."""
 
-    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True):
+    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True, mask_gather=None):
         if dtype not in DTYPES:
             raise ValueError("dtype must be one of %s" % sorted(DTYPES))
         if not torch.cuda.is_available():
@@ -280,6 +280,13 @@ class Engine:
         self._graphs = {}
         self._bufs = {}
         self._prepare_weights()
+        # Masksembles2D as smaller / re-weighted GEMMs.  0: dense 0/1 multiplies everywhere (the reference's form);
+        # 1 (default): the site at the prefix boundary moves into per-mask weight sets of its consumers;
+        # 2: additionally, sites fused into a producer's epilogue store the gathered (kept-channels-only) layout.
+        self.gather = {}
+        self.gather_mode = int(os.environ.get("BNN_MASK_GATHER", "1")) if mask_gather is None else int(mask_gather)
+        if self.use_tc and self.gather_mode > 0:
+            self._plan_gather()
 
     # ---- plan-time weight packing -----------------------------------------------------------
     def _tc_eligible(self, op):
@@ -310,6 +317,82 @@ class Engine:
             if op.site is not None and op.site.kind == "mask":
                 op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()
 
+    # ---- Masksembles gathered layout ----------------------------------------------------------
+    def _plan_gather(self):
+        """Masksembles2D sites whose output is read by tensor-core convolutions only (north star (3); the reference
+        multiplies by a 0/1 table and convolves the zeros, utils.py:165-169).
+
+        * "weights": the site sits at the prefix boundary (its input has no sample dimension).  W (m . x) ==
+          (W . m) x, so the consumers read the ONE deterministic tensor through per-mask weight sets whose dropped
+          input channels are zero: the S masked copies are never written or read and the site launch disappears.
+        * "compact" (gather_mode 2): the site is fused into its producer's epilogue, which stores only the channels
+          the sample's mask keeps (kept count rounded up to 16); the consumers run a smaller GEMM over those channels
+          with weights gathered per mask row.
+        Whether a given batch size can use it is decided in :meth:`_gather_ids` (an MMA tile pair must not straddle
+        two samples, one weight set per tile)."""
+        g, dev = self.graph, self.device
+        for op in g.ops:
+            site = op.site
+            if op.kind not in ("site", "conv") or site is None or site.kind != "mask" or op.dst is None:
+                continue
+            t = op.dst
+            if op.kind == "site":
+                mode = "weights" if not op.src.stoch else None
+            else:
+                mode = "compact" if (self.gather_mode >= 2 and op.use_tc and (t.C == 128 or t.C % 256 == 0)) else None
+            if mode is None:
+                continue
+            readers = [o for o in g.ops if o.src is t or o.res is t]
+            if not readers or any(o.kind not in ("conv", "convg") or o.res is not None or o.site is not None
+                                  or (o.kind == "conv" and not o.use_tc) for o in readers):
+                continue
+            masks = site.module.masks.detach().cpu().numpy() != 0                   # [n, C]
+            n, C = masks.shape
+            if C != t.C or C >= 32768:
+                continue
+            kept = [np.flatnonzero(masks[r]) for r in range(n)]
+            info = {"site": site, "mode": mode, "kept": [len(k) for k in kept], "n": n, "readers": readers, "op": op}
+            if mode == "compact":
+                kc = (max(len(k) for k in kept) + 15) // 16 * 16
+                if kc >= C:
+                    continue                                                        # nothing to save
+                pos = np.full((n, C), -1, np.int16)
+                idx = np.full((n, kc), -1, np.int16)
+                for r, k in enumerate(kept):
+                    pos[r, k] = np.arange(len(k), dtype=np.int16)
+                    idx[r, :len(k)] = k
+                info.update(kc=kc, pos=torch.from_numpy(pos).to(dev), idx=torch.from_numpy(idx).to(dev))
+            else:
+                info.update(kc=C)
+            for o in readers:
+                w = o.weight                                                        # OIHW fp32 (grouped: concatenated)
+                wg = torch.zeros((n, w.shape[0], w.shape[2], w.shape[3], info["kc"]), dtype=torch.float32)
+                for r, k in enumerate(kept):
+                    kk = torch.from_numpy(k)
+                    if mode == "compact":
+                        wg[r, :, :, :, :len(k)] = w[:, kk, :, :].permute(0, 2, 3, 1)
+                    else:
+                        wg[r][:, :, :, kk] = w[:, kk, :, :].permute(0, 2, 3, 1)     # dropped columns stay zero
+                o.d_wg = wg.contiguous().to(dev, self.tdtype)
+                o.gather = info
+            self.gather[t.id] = info
+
+    def _gather_ids(self, B):
+        """{tensor id: "weights" | "compact"} for batch size B."""
+        out = {}
+        for tid, info in self.gather.items():
+            t = self.graph.tensors[tid]
+            ok = (B * t.H * t.W) % 32 == 0
+            for o in info["readers"]:
+                d = o.dsts[0] if o.kind == "convg" else o.dst
+                ok = ok and (B * d.H * d.W) % 256 == 0
+            if ok:
+                out[tid] = info["mode"]
+        return out
+
+    def _compact_ids(self, B):
+        return {tid for tid, m in self._gather_ids(B).items() if m == "compact"}
+
     # ---- buffers ----------------------------------------------------------------------------
     def _buffers(self, B, S_local, want_logits):
         key = (B, S_local, want_logits)
@@ -317,13 +400,19 @@ class Engine:
             return self._bufs[key]
         g, dev = self.graph, self.device
         acts = {}
+        gmode = self._gather_ids(B)
+        compact = {tid for tid, m in gmode.items() if m == "compact"}
         live = {g.input.id}
         for op in g.ops:
             live.update(t.id for t in (op.src, op.dst, op.res) + tuple(getattr(op, "dsts", ())) if t is not None)
         for t in g.tensors:
-            if t.id not in live:
+            if t.id not in live or gmode.get(t.id) == "weights":
                 continue                      # e.g. the un-masked output of a conv with a fused site
             n = (S_local if t.stoch else 1) * B
+            if t.id in compact:
+                # gathered layout; zero-filled once: the padding slots [kept, kc) are never written
+                acts[t.id] = torch.zeros((n, t.H, t.W, self.gather[t.id]["kc"]), dtype=self.tdtype, device=dev)
+                continue
             acts[t.id] = torch.empty((n, t.H, t.W, t.C), dtype=self.tdtype, device=dev)
         E, C = g.n_exits, g.n_classes
         st = {
@@ -332,6 +421,8 @@ class Engine:
             "out": torch.empty((4 * E * B * C + 3 * E * B,), dtype=torch.float32, device=dev),
             "logits": (torch.empty((E, S_local, B, C), dtype=torch.float32, device=dev) if want_logits else None),
             "acts": acts,
+            "compact": compact,
+            "gmode": gmode,
         }
         self._bufs[key] = st
         return st
@@ -341,7 +432,7 @@ class Engine:
         self._bufs.clear()
 
     # ---- launch helpers ---------------------------------------------------------------------
-    def _drop_desc(self, op_site, d_masks, B, sample0, seed, mask_offset=None):
+    def _drop_desc(self, op_site, d_masks, B, sample0, seed, mask_offset=None, compact=None):
         d = _lib.DropDesc()
         if op_site is None:
             d.kind = _lib.DROP_NONE
@@ -359,7 +450,38 @@ class Engine:
             # kernel row = (cnt0 + sample0 + s) % n; we want (module.cnt + mask_offset + s) % n
             off = sample0 if mask_offset is None else mask_offset
             d.cnt0 = (int(op_site.module.cnt) + off - sample0) % d.n_masks
+            if compact is not None:
+                d.compact_pos = compact["pos"].data_ptr()
+                d.compact_idx = compact["idx"].data_ptr()
+                d.compact_c = compact["kc"]
         return d
+
+    def _gathered_call(self, op, st, B, S_local, sample0, mask_offset, stream):
+        """(call, flops, bytes) of a convolution (group) that reads a tensor in the gathered layout."""
+        info, lib, acts = op.gather, self.lib, st["acts"]
+        dsts = op.dsts if op.kind == "convg" else [op.dst]
+        members = op.members if op.kind == "convg" else [op]
+        d0 = dsts[0]
+        n_img = S_local * B
+        ys = (ctypes.c_void_p * len(dsts))(*[acts[d.id].data_ptr() for d in dsts])
+        relu_mask = op.relu_mask if op.kind == "convg" else int(op.relu)
+        center_mask = op.center_mask if op.kind == "convg" else 0
+        ksize = 3 if op.kind == "convg" else op.ksize[0]
+        off = sample0 if mask_offset is None else mask_offset
+        cnt0 = (int(info["site"].module.cnt) + off) % info["n"]
+        out_px = n_img * d0.H * d0.W
+        # "weights" mode: read the site's deterministic INPUT (B images) - the masked copies do not exist
+        src = info["op"].src if info["mode"] == "weights" else op.src
+        has_samples = 0 if info["mode"] == "weights" else 1
+        kept = sum(info["kept"]) / len(info["kept"])                 # algorithmic: the channels a mask keeps
+        flops = sum(2 * out_px * m.dst.C * kept * m.ksize[0] * m.ksize[1] for m in members)
+        es = 2
+        nbytes = ((n_img if has_samples else B) * op.src.H * op.src.W * info["kc"] + out_px * d0.C * len(dsts)) * es \
+            + op.d_wg.numel() * op.d_wg.element_size()
+        call = lambda: lib.bnn_conv2d_tc_gathered(
+            _ptr(acts[src.id]), _ptr(op.d_wg), _ptr(op.d_b), ys, len(dsts), relu_mask, center_mask, self.dcode, n_img,
+            op.src.H, op.src.W, info["kc"], d0.C, ksize, op.stride, info["n"], cnt0, 0, B, has_samples, stream)
+        return call, flops, nbytes
 
     def sums_views(self, st, B):
         E, C = self.graph.n_exits, self.graph.n_classes
@@ -400,8 +522,17 @@ class Engine:
         self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc(
             _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W, stream))
         sum_p, sum_l, sum_pl = self.sums_views(st, B)
+        compact, gmode = st["compact"], st["gmode"]
         for op in g.ops:
-            if op.kind == "convg":
+            if op.kind in ("conv", "convg") and op.src.id in gmode:
+                if S_local == 0:
+                    continue
+                call, flops, nbytes = self._gathered_call(op, st, B, S_local, sample0, mask_offset, stream)
+                tag = " [gathered K]" if gmode[op.src.id] == "compact" else " [per-mask weights]"
+                self._launch("conv_tc", op.name + tag, flops, nbytes, call)
+            elif op.kind == "site" and gmode.get(op.dst.id) == "weights":
+                continue                      # folded into the consumers' weight sets
+            elif op.kind == "convg":
                 d0 = op.dsts[0]
                 n_img = (S_local if d0.stoch else 1) * B
                 if n_img == 0:
@@ -424,7 +555,8 @@ class Engine:
                 res = acts[op.res.id] if op.res is not None else None
                 if op.res is not None and op.dst.stoch and not op.res.stoch:
                     raise NotImplementedError("conv %s: deterministic residual into stochastic output" % op.name)
-                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset,
+                                     self.gather[op.dst.id] if op.dst.id in compact else None)
                 kh, kw = op.ksize
                 out_px = n_img * op.dst.H * op.dst.W
                 flops = 2 * out_px * op.dst.C * op.src.C * kh * kw
@@ -443,9 +575,13 @@ class Engine:
             elif op.kind == "site":
                 if S_local == 0:
                     continue
-                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
+                dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset,
+                                     self.gather[op.dst.id] if op.dst.id in compact else None)
                 per_image = op.src.H * op.src.W * op.src.C
                 nbytes = B * per_image * es * ((S_local if op.src.stoch else 1) + S_local)
+                if op.dst.id in compact:
+                    nbytes = B * per_image * es * (S_local if op.src.stoch else 1) \
+                        + B * S_local * op.src.H * op.src.W * self.gather[op.dst.id]["kc"] * es
                 self._launch("dropout", op.name, 0, nbytes, lambda: lib.bnn_dropout(
                     _ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, per_image, op.src.C, S_local,
                     int(op.src.stoch), ctypes.byref(dd), stream))

@@ -91,6 +91,16 @@ typedef struct bnn_drop_desc {
   const float* masks;   /* MASKSEMBLES: float32 [n_masks][C] on the device */
   int n_masks;
   int cnt0;             /* MASKSEMBLES: value of the module's rotating `cnt` at sample 0 */
+  /* MASKSEMBLES, optional "gathered" output layout (all NULL / 0: dense output, dropped channels stored as zeros).
+   * With compact_pos set the output has compact_c (= kept channels rounded up to 16) channels per pixel and holds
+   * only the channels the sample's mask keeps, in increasing channel order; dropped channels are never written
+   * and the consuming convolutions (bnn_conv2d_tc_gathered) never read them.  The padding slots
+   * [kept, compact_c) are not written either: the caller zero-fills the buffer once.
+   *   compact_pos  int16 [n_masks][C]          slot of channel c under mask row r, -1 if dropped
+   *   compact_idx  int16 [n_masks][compact_c]  channel held by slot j under mask row r, -1 for padding */
+  const int16_t* compact_pos;
+  const int16_t* compact_idx;
+  int compact_c;
 } bnn_drop_desc;
 
 int bnn_conv2d_simt(const void* x, const float* w, const float* bias, const void* res, void* y, int dtype, int N,
@@ -110,6 +120,22 @@ int bnn_conv2d_tc(const void* x, const void* w, const float* bias, const void* r
 int bnn_conv2d_tc_grouped(const void* x, const void* w, const float* bias, void* const* y, int n_groups,
                           uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                           int cout_per_group, int ksize, int stride, void* stream);
+
+/* Masksembles "gathered" convolution (north star (3): structured channel masks become smaller GEMMs and dropped
+ * channels are never read from HBM).  Same as bnn_conv2d_tc_grouped, but
+ *   x  is [N][H][W][Kc]: the compact output of a Masksembles2D site (bnn_drop_desc.compact_pos), Kc % 16 == 0;
+ *   w  is [n_masks][n_groups * cout_per_group][k][k][Kc]: one weight set per mask row, input channels gathered
+ *      with the same kept-channel list (zeros in the padding slots);
+ *   image n belongs to local sample n / batch and uses weight set (cnt0 + sample0 + n / batch) % n_masks - the
+ *      rotation of Masksembles2D.forward (utils.py:165-168).
+ * x_has_samples == 0: x holds only `batch` images - the deterministic prefix in front of the first Masksembles2D
+ *   site - and every sample reads them through its own weight set whose dropped input channels are zero
+ *   (W (m . x) == (W . m) x): the S masked copies of the prefix tensor are never materialised (Kc == C then).
+ * batch * OH * OW must be a multiple of 256 (an MMA tile pair never straddles two samples). */
+int bnn_conv2d_tc_gathered(const void* x, const void* w, const float* bias, void* const* y, int n_groups,
+                           uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Kc,
+                           int cout_per_group, int ksize, int stride, int n_masks, int cnt0, uint32_t sample0,
+                           int batch, int x_has_samples, void* stream);
 
 /* ---- stand-alone stochastic layer (prefix -> suffix broadcast) ----
  * y[s][b][...] = drop_s(x[b][...]) for s in [0, S_local) when x_has_samples == 0 (the deterministic

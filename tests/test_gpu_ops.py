@@ -303,3 +303,151 @@ def test_conv_tc_grouped_equals_separate_convs(lib, Cin, Cg, HW, G):
             want = F.conv2d(xd, w1.half().double(), bias[i * Cg:].double(), 2, 0)
         got = outs[i].cpu().permute(0, 3, 1, 2).double()
         assert (got - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item()), i
+
+
+# ---- Masksembles gathered layout (bnn_drop_desc.compact_*, bnn_conv2d_tc_gathered) -------------------------
+def _mask_tables(n, C, kept, seed):
+    """n random 0/1 rows with `kept` ones each + the pos / idx tables of the gathered layout."""
+    rng = np.random.RandomState(seed)
+    kc = (kept + 15) // 16 * 16
+    masks = np.zeros((n, C), np.float32)
+    pos = np.full((n, C), -1, np.int16)
+    idx = np.full((n, kc), -1, np.int16)
+    for r in range(n):
+        k = np.sort(rng.choice(C, kept, replace=False))
+        masks[r, k] = 1
+        pos[r, k] = np.arange(kept)
+        idx[r, :kept] = k
+    return masks, pos, idx, kc
+
+
+def _compact_desc(masks, pos, idx, kc, B, sample0, cnt0):
+    dm, dp, di = torch.from_numpy(masks).cuda(), torch.from_numpy(pos).cuda(), torch.from_numpy(idx).cuda()
+    dd = drop_desc(3, 0.0, 0, 0, sample0, B, dm, cnt0=cnt0)
+    dd.compact_pos, dd.compact_idx, dd.compact_c = dp.data_ptr(), di.data_ptr(), kc
+    return dd, (dm, dp, di)
+
+
+@pytest.mark.parametrize("x_has_samples", [0, 1])
+def test_masksembles_compact_site(lib, x_has_samples):
+    """stand-alone site in the gathered layout == the dense masked tensor with the dropped channels removed."""
+    B, S, H, C, kept, n, s0, cnt0 = 3, 5, 4, 64, 34, 4, 2, 3
+    masks, pos, idx, kc = _mask_tables(n, C, kept, 1)
+    x = torch.randn((S if x_has_samples else 1) * B, H, H, C).half().cuda()
+    y = torch.zeros(S * B, H, H, kc, dtype=torch.float16, device="cuda")
+    dd, keep = _compact_desc(masks, pos, idx, kc, B, s0, cnt0)
+    assert lib.bnn_dropout(x.data_ptr(), y.data_ptr(), 1, H * H * C, C, S, x_has_samples, ctypes.byref(dd),
+                           stream()) == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    xs = x.view(-1, B, H, H, C).cpu()
+    for s in range(S):
+        r = (cnt0 + s0 + s) % n
+        want = xs[s if x_has_samples else 0][..., idx[r, :kept].astype(np.int64)]
+        got = y.view(S, B, H, H, kc)[s].cpu()
+        assert torch.equal(got[..., :kept], want) and (got[..., kept:] == 0).all()
+
+
+@pytest.mark.parametrize("Cout,M_img,pair", [(128, 16, "0"), (256, 16, "0"), (256, 28, "cg2"), (256, 28, "mc2")])
+def test_conv_tc_fused_compact_epilogue(lib, Cout, M_img, pair, monkeypatch):
+    """conv + residual + ReLU + Masksembles2D stored in the gathered layout == the dense fused epilogue with the
+    dropped channels removed (bit-exact: same arithmetic, different addresses)."""
+    if pair != "0":         # swapped / single-CTA / cta_group::2 / (multicast has no compact epilogue: single-CTA runs)
+        monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+        monkeypatch.setenv("BNN_TC_CG2", "1" if pair == "cg2" else "0")
+    B, H, Cin, n, s0, cnt0 = 4, 8, 64, 4, 1, 2
+    S = M_img // B
+    kept = {128: 68, 256: 136}[Cout]
+    masks, pos, idx, kc = _mask_tables(n, Cout, kept, Cout)
+    g = torch.Generator().manual_seed(Cout + M_img)
+    x = torch.randn(S * B, H, H, Cin, generator=g).half().cuda()
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / 24).half().cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(S * B, H, H, Cout, generator=g).half().cuda()
+    dense = torch.empty(S * B, H, H, Cout, dtype=torch.float16, device="cuda")
+    comp = torch.zeros(S * B, H, H, kc, dtype=torch.float16, device="cuda")
+    dd_c, keep = _compact_desc(masks, pos, idx, kc, B, s0, cnt0)
+    dd_d = drop_desc(3, 0.0, 0, 0, s0, B, keep[0], cnt0=cnt0)
+    for dd, y in ((dd_d, dense), (dd_c, comp)):
+        assert lib.bnn_conv2d_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), res.data_ptr(), y.data_ptr(), 1, S * B, H, H,
+                                 Cin, Cout, 3, 1, 1, ctypes.byref(dd), stream()) == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    dv, cv = dense.view(S, B, H, H, Cout).cpu(), comp.view(S, B, H, H, kc).cpu()
+    for s in range(S):
+        r = (cnt0 + s0 + s) % n
+        assert torch.equal(cv[s][..., :kept], dv[s][..., idx[r, :kept].astype(np.int64)]), s
+        assert (cv[s][..., kept:] == 0).all()
+    assert dv.abs().sum() > 0
+
+
+@pytest.mark.parametrize("C,kept,cout_g,groups,stride,H,B", [
+    (64, 34, 128, 3, 2, 16, 4),       # site 1 of the ResNet: layer2.0.conv1 + shortcut (centre tap) + ex1conv1
+    (128, 68, 256, 3, 2, 8, 16),      # site 2
+    (256, 136, 512, 3, 2, 8, 16),     # site 3: three channel blocks, the last one 16 channels wide
+    (256, 136, 256, 1, 1, 8, 8),      # stride 1, single output
+    (128, 68, 64, 1, 1, 16, 2),       # 64-channel tile kernel
+    (256, 136, 512, 1, 2, 16, -4),    # B = 4 with the CTA-pair kernels forced: cta_group::2
+    (256, 136, 256, 2, 2, 16, -8),
+])
+def test_conv_tc_gathered_vs_dense(lib, C, kept, cout_g, groups, stride, H, B, monkeypatch):
+    """gathered-K convolution on the compact tensor == the grouped convolution on the dense masked tensor (same
+    products; the tensor cores sum them in a different order) and == float64 torch."""
+    if B < 0:
+        monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+        B = -B
+    n, S, s0, cnt0 = 4, 3, 1, 2
+    masks, pos, idx, kc = _mask_tables(n, C, kept, C + cout_g)
+    g = torch.Generator().manual_seed(C * 7 + cout_g)
+    Cout = groups * cout_g
+    xd = torch.randn(S, B, H, H, C, generator=g).half()
+    for s in range(S):
+        xd[s] *= torch.from_numpy(masks[(cnt0 + s0 + s) % n])
+    w = (torch.randn(Cout, 3, 3, C, generator=g) / np.sqrt(9 * kept)).half()
+    center_mask = 0b010 if groups >= 2 else 0
+    if center_mask:
+        w[cout_g:2 * cout_g, [0, 0, 0, 1, 1, 2, 2, 2], [0, 1, 2, 0, 2, 0, 1, 2]] = 0     # a 1x1 kernel in the centre tap
+    b = torch.randn(Cout, generator=g)
+    relu_mask = 0b101 if groups >= 2 else 1
+    OH = H // stride
+    xc = torch.zeros(S, B, H, H, kc, dtype=torch.float16)
+    wg = torch.zeros(n, Cout, 3, 3, kc, dtype=torch.float16)
+    for r in range(n):
+        wg[r, ..., :kept] = w[..., idx[r, :kept].astype(np.int64)]
+    for s in range(S):
+        xc[s, ..., :kept] = xd[s][..., idx[(cnt0 + s0 + s) % n, :kept].astype(np.int64)]
+    xc[..., kept:] = 7.0            # padding slots may hold anything finite: their weights are zero
+    d = [t.cuda() for t in (xd, w, b, xc, wg)]
+    outs = {}
+    for name in ("dense", "gathered"):
+        ys = [torch.full((S * B, OH, OH, cout_g), float("nan"), dtype=torch.float16, device="cuda") for _ in range(groups)]
+        yp = (ctypes.c_void_p * groups)(*[y.data_ptr() for y in ys])
+        if name == "dense":
+            rc = lib.bnn_conv2d_tc_grouped(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), yp, groups, relu_mask,
+                                           center_mask, 1, S * B, H, H, C, cout_g, 3, stride, stream())
+        else:
+            rc = lib.bnn_conv2d_tc_gathered(d[3].data_ptr(), d[4].data_ptr(), d[2].data_ptr(), yp, groups, relu_mask,
+                                            center_mask, 1, S * B, H, H, kc, cout_g, 3, stride, n, cnt0, s0, B, 1, stream())
+        assert rc == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        outs[name] = torch.cat([y.cpu().float() for y in ys], -1)
+    want = F.conv2d(xd.view(S * B, H, H, C).permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double(),
+                    stride, 1).permute(0, 2, 3, 1)
+    for gi in range(groups):
+        if (relu_mask >> gi) & 1:
+            want[..., gi * cout_g:(gi + 1) * cout_g].relu_()
+    scale = max(1.0, want.abs().max().item())
+    e_ref = (outs["gathered"].double() - want).abs().max().item()
+    e_dense = (outs["gathered"] - outs["dense"]).abs().max().item()
+    report(test="conv_tc_gathered", C=C, kept=kept, cout=Cout, err_vs_f64=e_ref, err_vs_dense=e_dense)
+    assert e_ref <= 2e-3 * scale and e_dense <= 2e-3 * scale
+
+
+def test_conv_tc_gathered_bad_args(lib):
+    y = torch.zeros(16, device="cuda")
+    yp = (ctypes.c_void_p * 1)(y.data_ptr())
+    # batch * OH * OW not a multiple of 256: a tile pair would straddle two samples
+    assert lib.bnn_conv2d_tc_gathered(y.data_ptr(), y.data_ptr(), y.data_ptr(), yp, 1, 0, 0, 1, 6, 8, 8, 48, 64, 3, 1, 4,
+                                      0, 0, 3, 1, stream()) == -1
+    assert b"multiple of 256" in lib.bnn_last_error()
+    # Kc must be a multiple of 16
+    assert lib.bnn_conv2d_tc_gathered(y.data_ptr(), y.data_ptr(), y.data_ptr(), yp, 1, 0, 0, 1, 8, 8, 8, 40, 64, 3, 1, 4,
+                                      0, 0, 4, 1, stream()) == -4

@@ -211,3 +211,49 @@ def test_cuda_graph_replay_equals_eager(tag):
     a = mc_predict(model, x2, S, seed=5, dtype="fp16").mean_probs.clone()   # replay with a different batch
     b = eng.run(x2, S, seed=5, use_graph=False).mean_probs
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("S,cnt0,s0", [(4, 0, 0), (6, 3, 2)])
+def test_masksembles_gathered_gemm_vs_oracle(S, cnt0, s0, mode, monkeypatch):
+    """BASELINE config 3 (Masksembles, 4 masks, scale 2) at a batch size where every Masksembles2D site runs in the
+    gathered layout: dropped channels are neither stored nor read, the consumers are smaller GEMMs with per-mask
+    weight sets.  Checked against the oracle (== the live reference, fixtures) and against the dense-mask path."""
+    tag, B = "resnet18_mask_block", 16
+    model, sd, gold = build_seeded(tag)
+    model.cuda()
+    x = seeded.seeded_input((B, 3, 32, 32), seed=5)
+    for m in model.modules():
+        if hasattr(m, "cnt"):
+            m.cnt = cnt0
+    # mode 1 (default): the boundary site becomes per-mask weight sets; mode 2: + gathered layout for fused sites
+    eng = model.bnn_engine("fp16", rebuild=True, mask_gather=mode)
+    modes = sorted(eng._gather_ids(B).values())
+    assert modes == (["weights"] if mode == 1 else ["compact", "compact", "weights"])
+    assert len(eng._gather_ids(2)) == 1       # B*OH*OW % 256 != 0 behind sites 2 and 3: those stay dense at B = 2
+    assert sorted(i["kc"] for i in eng.gather.values()) == ([64] if mode == 1 else [64, 80, 144])   # 68/128, 136/256 kept
+    r = eng.run(x, S, seed=0x5EED, sample0=s0, want_logits=True, use_graph=False)
+    got = {k: getattr(r, k).double().cpu().numpy() for k in ("mean_probs", "mean_logits", "ens_probs", "all_logits")}
+    mp = r.mean_probs.clone()
+    names = _launch_names(eng, x, S)
+    assert any("per-mask weights" in n for n in names) and not any(n == "layer1.1" for n in names)
+    assert any("gathered" in n for n in names) == (mode == 2)
+    want = oracle_run(tag, sd, x, S, 0x5EED, 0.5, cnt0=cnt0, sample0=s0)
+    scale = max(1.0, float(np.abs(want["all_logits"]).max()))
+    e = {k: float(np.abs(got[k] - want[k]).max()) for k in got}
+    for m in model.modules():
+        if hasattr(m, "cnt"):
+            m.cnt = cnt0
+    dense = model.bnn_engine("fp16", rebuild=True, mask_gather=0)
+    assert not dense.gather
+    rd = dense.run(x, S, seed=0x5EED, sample0=s0, want_logits=True, use_graph=False)
+    e["probs_vs_dense_path"] = float((mp - rd.mean_probs).abs().max())
+    report(test="masksembles_gathered", mode=mode, S=S, cnt0=cnt0, sample0=s0, logit_scale=scale, **e)
+    assert e["mean_probs"] <= 1e-3 and e["ens_probs"] <= 1e-3 and e["mean_logits"] <= 1e-3 * scale
+    assert e["probs_vs_dense_path"] <= 1e-3
+    ok, _ = _argmax_agrees(got["mean_probs"], want["mean_probs"], 2e-3)
+    assert ok
+
+
+def _launch_names(eng, x, S):
+    return [o["name"] for o in eng.profile_step(x.cuda(), S)]
