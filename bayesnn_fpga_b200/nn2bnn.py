@@ -5,7 +5,16 @@ Same type map and the same recursive ``named_children`` walk.  The reference's e
 ``UnboundLocalError`` as shipped (``pred`` is printed before assignment, nn2bnn.py:25; SURVEY.md A.3);
 the intended semantics - mean over ``nSamples`` stochastic passes of the RAW model output
 (nn2bnn.py:26-27) - is what this class implements.
+
+Eval mode runs the converted network through the fused plan (``lowering.lower_module`` -> ``engine.Engine``): the
+layers in front of the first wrapped leaf once per image, the rest once per sample, the mean accumulated on the
+device.  The masks are the ones ``nSamples`` successive stand-alone forward calls would draw (every wrapper keeps its
+own Philox stream and call counter), so both forms agree to rounding.  A network the lowering cannot express falls
+back - with a warning - to those stand-alone calls (each leaf through torch, each dropout through ``bnn_dropout``).
 """
+import warnings
+
+import torch
 import torch.nn as nn
 
 from .Dropouts import BayesianDropout, BayesianDropout2D, BayesianDropout3D
@@ -29,11 +38,57 @@ def _convert_model(model, p):
 class MCDropout(nn.Module):
     """Monte-Carlo-dropout wrapper: training -> one stochastic pass; eval -> mean of ``nSamples`` passes."""
 
-    def __init__(self, model, nSamples=10, p=0.5):
+    def __init__(self, model, nSamples=10, p=0.5, dtype="fp32", fused=True):
         super().__init__()
         self.model = _convert_model(model, p)
         self.nSamples = nSamples
         self.p = p
+        self.bnn_dtype = dtype          # "fp32": exact CUDA-core path; "fp16" / "bf16": tensor cores
+        self.bnn_fused = fused
+        self.__dict__["_bnn_plans"] = {}
+
+    def train(self, mode=True):
+        self.__dict__["_bnn_plans"] = {}      # parameters may change while training: re-plan at the next eval
+        return super().train(mode)
+
+    def _site_modules(self):
+        return [m for m in self.model.modules() if hasattr(m, "bnn_calls")]
+
+    def _plan(self, shape, device):
+        """(engine, site modules) for inputs [B, *shape], or None when the network cannot be lowered."""
+        key = (tuple(shape), self.bnn_dtype, str(device))
+        plans = self.__dict__["_bnn_plans"]
+        if key not in plans:
+            from . import engine, lowering
+            try:
+                graph, sites = lowering.lower_module(self.model, shape)
+                plans[key] = (engine.Engine(graph, dtype=self.bnn_dtype, device=device), [m for _, m in sites])
+            except NotImplementedError as e:
+                warnings.warn("nn2bnn.MCDropout: running %d stand-alone passes instead of the fused plan: %s" % (
+                    self.nSamples, e))
+                plans[key] = None
+        return plans[key]
+
+    def _forward_fused(self, x):
+        flat = x.dim() == 2
+        shape = (x.shape[1], 1, 1) if flat else tuple(x.shape[1:])
+        if len(shape) != 3 or not x.is_cuda:
+            return None
+        plan = self._plan(shape, x.device)
+        if plan is None:
+            return None
+        eng, mods = plan
+        sites = self._site_modules()
+        seeds = {int(m.bnn_seed) for m in sites}
+        calls = {int(m.bnn_calls) for m in sites}
+        if len(seeds) > 1 or len(calls) > 1:
+            return None                      # wrappers were driven individually: keep their own streams exact
+        r = eng.run(x.reshape(x.shape[0], *shape).float(), self.nSamples, seed=seeds.pop() if seeds else 0,
+                    sample0=calls.pop() if calls else 0, S_total=self.nSamples)
+        for m in sites:
+            m.bnn_calls += self.nSamples
+        outs = [r.mean_logits[e].clone() for e in eng.graph.out_order]
+        return outs[0] if len(outs) == 1 else outs
 
     def reseed(self, seed):
         """Make the run reproducible: site k of the converted model gets Philox stream k."""
@@ -47,6 +102,10 @@ class MCDropout(nn.Module):
     def forward(self, x):
         if self.training:
             return self.model(x)
+        if self.bnn_fused:
+            out = self._forward_fused(x)
+            if out is not None:
+                return out
         pred = [self.model(x) for _ in range(self.nSamples)]
         return sum(pred) / len(pred)
 

@@ -34,6 +34,23 @@ def allreduce_sums(flat, group=None):
     return flat
 
 
+def _generic_engine(model, x, dtype, engine_kwargs):
+    """Plan for an arbitrary nn.Module (lowering.lower_module), cached on the module per input shape / dtype."""
+    from . import engine, lowering
+    flat = x.dim() == 2
+    shape = (int(x.shape[1]), 1, 1) if flat else tuple(int(v) for v in x.shape[1:])
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("bayesnn_fpga_b200 runs on a CUDA (sm_100) device only; there is no CPU fallback - call "
+                           "model.cuda() first")
+    cache = model.__dict__.setdefault("_bnn_generic_engines", {})
+    key = (shape, dtype, tuple(sorted((engine_kwargs or {}).items())))
+    if key not in cache:
+        graph, _ = lowering.lower_module(model, shape)
+        cache[key] = engine.Engine(graph, dtype=dtype or "fp16", device=dev, **(engine_kwargs or {}))
+    return cache[key], shape
+
+
 def mc_predict(model, x, S, seed=0x5EED, dtype=None, want_logits=False, distributed=False, group=None,
                engine_kwargs=None):
     """S stochastic passes of `model` over the batch `x` ([B, C, H, W] float32, host or device).
@@ -45,7 +62,13 @@ def mc_predict(model, x, S, seed=0x5EED, dtype=None, want_logits=False, distribu
     """
     if S <= 0:
         raise ValueError("S must be positive, got %d" % S)
-    eng = model.bnn_engine(dtype, **(engine_kwargs or {}))
+    if hasattr(model, "bnn_engine"):
+        eng = model.bnn_engine(dtype, **(engine_kwargs or {}))
+    else:
+        # any other nn.Module (e.g. the output of nn2bnn._convert_model, or a user network holding MCDropout /
+        # Masksembles modules): traced and lowered to the same plan; exits = the module's outputs in return order
+        eng, shape = _generic_engine(model, x, dtype, engine_kwargs)
+        x = x.reshape(x.shape[0], *shape)
     sample0, s_local, reduce_fn = 0, S, None
     if distributed:
         import torch.distributed as dist

@@ -1,0 +1,109 @@
+"""GPU: arbitrary nn.Modules through the fused plan (lowering.lower_module) - SURVEY.md 8(f) rank 2.
+
+Oracle: the same architecture on the CPU in float64 with the oracle's Philox masks injected at every stochastic
+module (tests/nets_generic.py), i.e. the converter's eval semantics `mean over nSamples passes of the raw output`
+(Hardware_Artifact/converter/pytorch/nn2bnn.py:26-27).  Tolerances: fp32 path 1e-5 * max(1, |out|), fp16 tensor-core
+path 2e-3 * max(1, |out|) on raw outputs (logits).
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from bayesnn_fpga_b200 import mc_predict, nn2bnn
+from bayesnn_fpga_b200.Dropouts import BayesianDropout, BayesianDropout2D, MCDropout
+from tests.gpu_util import report
+from tests.nets_generic import InjectedDropout, SmallResNet, plain_cnn, randomize_bn, reference_mean
+
+pytestmark = pytest.mark.gpu
+
+
+def _converted_reference(bnn, seed):
+    """CPU twin of a converted nn.Sequential: every wrapper becomes layer -> InjectedDropout with its stream."""
+    layers, sites = [], []
+    for m in bnn.model:
+        if isinstance(m, (BayesianDropout, BayesianDropout2D)):
+            d = InjectedDropout(m.p, m.bnn_stream, seed, "channel" if isinstance(m, BayesianDropout2D) else "element")
+            layers += [copy.deepcopy(m.layer).cpu(), d]
+            sites.append(d)
+        else:
+            layers.append(copy.deepcopy(m).cpu())
+    return nn.Sequential(*layers), sites
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("fp16", 2e-3)])
+def test_converted_cnn_fused_plan_vs_injected_reference(dtype, tol):
+    torch.manual_seed(0)
+    S, seed, B = 6, 77, 5
+    bnn = nn2bnn.MCDropout(plain_cnn(), nSamples=S, p=0.25, dtype=dtype).reseed(seed).cuda().eval()
+    ref, sites = _converted_reference(bnn, seed)
+    x = torch.randn(B, 1, 28, 28)
+    want = reference_mean(ref, x, sites, S)[0]
+    got = bnn(x.cuda())
+    assert bnn._plan((1, 28, 28), x.cuda().device) is not None            # the fused plan ran, not the fallback
+    scale = max(1.0, want.abs().max().item())
+    err = (got.double().cpu() - want).abs().max().item()
+    report(test="converted_cnn_fused", dtype=dtype, err=err, scale=scale)
+    assert err <= tol * scale
+    # a second call draws the NEXT nSamples samples, like further stand-alone forward calls would
+    want2 = reference_mean(ref, x, sites, S, sample0=S)[0]
+    err2 = (bnn(x.cuda()).double().cpu() - want2).abs().max().item()
+    assert err2 <= tol * scale and (want2 - want).abs().max().item() > 100 * tol
+
+
+def test_converted_cnn_fused_equals_standalone_passes():
+    """same masks, same arithmetic up to rounding: fused plan vs nSamples stand-alone passes (torch layers +
+    bnn_dropout)."""
+    torch.manual_seed(1)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = plain_cnn().cuda()
+        a = nn2bnn.MCDropout(copy.deepcopy(net), nSamples=5, p=0.5).reseed(9).eval()
+        b = nn2bnn.MCDropout(copy.deepcopy(net), nSamples=5, p=0.5, fused=False).reseed(9).eval()
+        x = torch.randn(4, 1, 28, 28, device="cuda")
+        ya, yb = a(x), b(x)
+        assert (ya - yb).abs().max().item() <= 1e-5 * max(1.0, yb.abs().max().item())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("fp16", 2e-3)])
+def test_residual_network_with_sites_vs_injected_reference(dtype, tol):
+    """BatchNorm folding, residual adds traced shortcut-last, global-pool heads, two outputs, prefix/suffix split."""
+    torch.manual_seed(2)
+    S, seed, B = 5, 0xBEEF, 6
+    model = randomize_bn(SmallResNet(lambda p: MCDropout(p))).cuda().eval()
+    streams = [m.bnn_stream for m in (model.d1, model.d2, model.d3)]
+    ref_sites = []
+
+    def drop(p):
+        d = InjectedDropout(p, streams[len(ref_sites)], seed)
+        ref_sites.append(d)
+        return d
+    ref = SmallResNet(drop)
+    ref.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    x = torch.randn(B, 3, 16, 16)
+    want = reference_mean(ref, x, ref_sites, S)
+    r = mc_predict(model, x.cuda(), S, seed=seed, dtype=dtype)
+    eng = model.__dict__["_bnn_generic_engines"][((3, 16, 16), dtype, ())]
+    pre, suf = eng.graph.macs()
+    assert pre > 0 and suf > 0 and eng.graph.out_order == [0, 1]
+    for e, w in enumerate(want):
+        scale = max(1.0, w.abs().max().item())
+        err = (r.mean_logits[e].double().cpu() - w).abs().max().item()
+        report(test="generic_resnet", dtype=dtype, exit=e, err=err, scale=scale)
+        assert err <= tol * scale
+    # softmax statistics come with it
+    assert torch.allclose(r.mean_probs.sum(-1), torch.ones_like(r.mean_probs.sum(-1)), atol=1e-4)
+
+
+def test_unsupported_network_falls_back_with_warning():
+    net = nn.Sequential(nn.Linear(6, 8), nn.Sigmoid(), nn.Linear(8, 3)).cuda()
+    bnn = nn2bnn.MCDropout(net, nSamples=3, p=0.5).reseed(4).eval()
+    x = torch.randn(5, 6, device="cuda")
+    with pytest.warns(UserWarning, match="stand-alone passes"):
+        y = bnn(x)
+    assert y.shape == (5, 3) and torch.isfinite(y).all()

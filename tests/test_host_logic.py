@@ -147,3 +147,69 @@ def test_model_attributes_read_by_analyzers():
     l = lenet.LeNetMCEarlyExit()
     g = l._bnn_graph()
     assert g.n_exits == 2 and g.n_classes == 10 and [s.name for s in g.sites] == ["bayes_2nd_exit", "bayes_1st_exit"]
+
+
+# ---- generic lowering (the converter's output through the fused plan) ----------------
+def _hook_macs(model, x):
+    macs = []
+
+    def hook(m, i, o):
+        if isinstance(m, nn.Conv2d):
+            macs.append(o[0].numel() * m.in_channels * m.kernel_size[0] * m.kernel_size[1])
+        elif isinstance(m, nn.Linear):
+            macs.append(m.in_features * m.out_features)
+    hs = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, (nn.Conv2d, nn.Linear))]
+    with torch.no_grad():
+        model(x)
+    for h in hs:
+        h.remove()
+    return sum(macs)
+
+
+def test_lowering_residual_network_structure_and_macs():
+    from bayesnn_fpga_b200 import lowering
+    from tests.nets_generic import SmallResNet
+    net = SmallResNet(lambda p: nn.Dropout(p)).eval()          # nn.Dropout is an eval-mode no-op: all prefix
+    g, sites = lowering.lower_module(net, (3, 16, 16))
+    assert not sites and g.n_exits == 2
+    kinds = [(o.kind, o.name) for o in g.ops]
+    # BN folded, ReLU / residual fused; the 1x1 shortcut is emitted before the conv that adds it; both global pools
+    # disappear into exit heads
+    assert kinds == [("conv", "stem"), ("conv", "b1_conv1"), ("conv", "b1_conv2"), ("head", "aux_fc"),
+                     ("conv", "b2_conv1"), ("conv", "b2_down_0"), ("conv", "b2_conv2"), ("head", "fc")]
+    by = {o.name: o for o in g.ops}
+    assert by["b1_conv2"].res is by["stem"].dst and by["b2_conv2"].res is by["b2_down_0"].dst
+    assert by["b2_conv2"].relu and not by["b2_down_0"].relu and by["aux_fc"].src is by["b1_conv2"].dst
+    pre, suf = g.macs()
+    assert suf == 0 and pre == _hook_macs(net, torch.zeros(1, 3, 16, 16))
+
+
+def test_lowering_converted_network_prefix_suffix():
+    from bayesnn_fpga_b200 import lowering
+    from tests.nets_generic import plain_cnn
+    bnn = nn2bnn.MCDropout(plain_cnn(), nSamples=4, p=0.25).reseed(7)
+    g, sites = lowering.lower_module(bnn.model, (1, 28, 28))
+    assert [s.stream for s, _ in sites] == list(range(6)) and [s.kind for s, _ in sites] == ["mc2d", "mc", "mc2d", "mc", "mc", "mc"]
+    convs = [o for o in g.ops if o.kind == "conv"]
+    assert all(o.relu for o in convs[:3]) and not convs[3].relu            # relu(drop(maxpool(drop(conv)))) commutes
+    pre, suf = g.macs()
+    assert pre == 28 * 28 * 8 * 25                                         # only the first conv is deterministic
+    assert pre + suf == _hook_macs(plain_cnn(), torch.zeros(1, 1, 28, 28)) + 10 * 10   # + the identity output head
+    g.fuse_sites()
+    assert sum(o.kind == "site" for o in g.ops) == 3                       # boundary site + the two behind max-pools
+
+
+def test_lowering_rejects_what_it_cannot_express():
+    from bayesnn_fpga_b200 import lowering
+
+    class Odd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(3, 4, 3, padding=1)
+
+        def forward(self, x):
+            return torch.sigmoid(self.c(x)).mean((2, 3))
+    with pytest.raises(NotImplementedError, match="sigmoid"):
+        lowering.lower_module(Odd(), (3, 8, 8))
+    with pytest.raises(NotImplementedError, match="kernel == stride"):
+        lowering.lower_module(nn.Sequential(nn.Conv2d(3, 4, 3), nn.MaxPool2d(3, 2), nn.Flatten(), nn.Linear(4, 2)), (3, 9, 9))
