@@ -74,6 +74,12 @@ _SIGS = {
                               [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     "bnn_conv2d_tc_gathered": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
                                [ctypes.c_int] * 10 + [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "bnn_confidence_exit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bnn_top_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bnn_kde_triweight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
     "bnn_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_maxpool2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),

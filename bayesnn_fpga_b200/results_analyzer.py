@@ -5,10 +5,14 @@
 
 ``_get_output`` returns the reference's 5-tuple but computes it with ONE fused ``mc_predict`` call
 (prefix once, S samples in the GEMM M dimension, sums on the device) and a single device->host copy
-instead of 2*E*S synchronising copies.  Dataset-level calibration statistics are computed on the
-device (``bnn_calibration_bins``); the equal-mass binning of ``ece_hist_binary`` sorts the N confidences
-with torch.sort (plumbing) and bins on the host exactly like the reference.  The KDE-ECE
-(:351-443) needs KDEpy and stays out of scope.
+instead of 2*E*S synchronising copies.  Dataset-level statistics are computed on the device:
+``bnn_calibration_bins`` (histogram ECEs; the equal-mass binning of ``ece_hist_binary`` sorts the N confidences
+with torch.sort - plumbing - and bins on the host exactly like the reference), ``bnn_dataset_metrics`` (NLL / MSE /
+accuracy, :497-503), ``bnn_top_label`` + ``bnn_kde_triweight`` (the KDE-ECE of ``ece_kde_binary`` :351-443, with the
+density estimate evaluated exactly instead of through KDEpy's FFT approximation, which is not installed) and
+``bnn_confidence_exit`` (confidence-threshold early exiting :606-631; the FLOP accounting of ``flop_saver`` /
+``flop_saver_ensembled`` :639-726 is the per-exit image histogram dotted with the reference's cost table).
+``all_experiments`` (:288-337) computes the reference's per-exit lists without writing its log files.
 """
 import ctypes
 
@@ -156,13 +160,202 @@ class FullAnalysis:
             nll, mse, acc = out.cpu().tolist()
         return nll, mse, acc
 
-    def ece_eval_binary(self, p, label):
-        """(ece, nll, mse, accuracy) like :497-505 with the histogram ECE in place of the KDE one (KDEpy is not
-        available); everything is computed on the device."""
-        nll, mse, accu = self.dataset_metrics(p, np.argmax(label, axis=1))
-        return self.ece_hist_binary(p, label), nll, mse, accu
-
     def entropy(self, probs):
         """bayes_hw/metric_utils.py:3-6 on mean probabilities [N, C]."""
         probs = np.asarray(probs)
         return float(-np.sum(np.log(probs + 1e-8) * probs) / probs.shape[0])
+
+    # ---- KDE-ECE ------------------------------------------------------------------------------------
+    def ece_kde_binary(self, p, label, p_int=None, order=1):
+        """Top-label KDE-ECE like results_analyzer.py:351-443 (multi-class branch, p_int = p): confidences,
+        bandwidth moments and both mirrored triweight density estimates on the device, the 2^14-point carry-forward
+        integration (:426-443) on the host."""
+        if p_int is not None:
+            raise NotImplementedError("ece_kde_binary: a separate integration set p_int is not supported")
+        p = np.asarray(p)
+        if p.shape[1] == 2:
+            raise NotImplementedError("ece_kde_binary: the binary joint-calibration branch is not supported")
+        lib = _lib.load()
+        G = 2 ** 14
+        x_int = np.linspace(-0.6, 1.6, num=G)
+        with torch.cuda.device(self.device):
+            _lib.require_device()
+            dp = torch.as_tensor(np.ascontiguousarray(p), dtype=torch.float32, device=self.device)
+            dl = torch.as_tensor(np.ascontiguousarray(np.argmax(label, axis=1)), dtype=torch.int32, device=self.device)
+            N, C = dp.shape
+            conf = torch.empty(N, dtype=torch.float32, device=self.device)
+            hit = torch.empty(N, dtype=torch.int32, device=self.device)
+            st = torch.zeros(3, dtype=torch.float64, device=self.device)
+            dens = torch.zeros((2, G), dtype=torch.float64, device=self.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.bnn_top_label(dp.data_ptr(), dl.data_ptr(), N, C, conf.data_ptr(), hit.data_ptr(),
+                                         st.data_ptr(), stream))
+            n1, s1, s2 = st.cpu().tolist()
+            var = max(s2 / n1 - (s1 / n1) ** 2, 0.0) if n1 > 0 else 0.0
+            std = var ** 0.5
+            kbw = (std if std > 1e-12 else 0.0000000000000001) * (N * 2) ** -0.2          # :389-393
+            dx = float(x_int[1] - x_int[0])
+            if n1 > 0:
+                _lib.check(lib.bnn_kde_triweight(conf.data_ptr(), hit.data_ptr(), N, kbw, float(n1), float(x_int[0]), dx, G,
+                                                 0.0, 1.0, dens[0].data_ptr(), stream))
+            _lib.check(lib.bnn_kde_triweight(conf.data_ptr(), None, N, kbw, float(N), float(x_int[0]), dx, G, 0.0, 1.0,
+                                             dens[1].data_ptr(), stream))
+            pp = dens.cpu().numpy()
+        return _kde_ece_integrate(x_int, pp[0], pp[1], n1 / N, order)
+
+    def ece_eval_binary(self, p, label):
+        """(ece, nll, mse, accuracy) like :497-505 - the ECE is the KDE-ECE, everything computed on the device."""
+        nll, mse, accu = self.dataset_metrics(p, np.argmax(label, axis=1))
+        return self.ece_kde_binary(p, label), nll, mse, accu
+
+    # ---- per-exit experiments (:288-337) --------------------------------------------------------------
+    def all_experiments(self, experiment_id=None):
+        """The per-exit lists of results_analyzer.py:288-336 (correct / cumulative / destructive-overthinking /
+        unique counts, ECE, NLL, MSE, accuracy for single exits and cumulative ensembles); the reference then
+        writes them to log files (`saver`), which is left to the caller."""
+        layers = sorted(self.layer_correct.keys())
+        for prefix, preds, correct, wrong in (("", self.preds, self.layer_correct, self.layer_wrong),
+                                              ("ensemble_", self.ensemble_preds, self.ensemble_layer_correct,
+                                               self.ensemble_layer_wrong)):
+            end_wrong = wrong[layers[-1]]
+            cum = set()
+            cols = {k: [] for k in ("cur_correct", "cum_correct", "overthinking", "unique", "ece", "nll", "mse", "accu")}
+            for layer in layers:
+                cur = correct[layer]
+                cols["unique"].append(len(cur - cum))
+                cum = cum | cur
+                cols["cur_correct"].append(len(cur))
+                cols["cum_correct"].append(len(cum))
+                cols["overthinking"].append(len(cur & end_wrong))
+                ece, nll, mse, accu = self.ece_eval_binary(preds[layer], self.labels)
+                for k, v in (("ece", ece), ("nll", nll), ("mse", mse), ("accu", accu)):
+                    cols[k].append(v)
+            names = {"cur_correct": "cur_correct_saver", "cum_correct": "cum_correct_saver",
+                     "overthinking": "destructive_overthinking", "unique": "unique_correct_saver" if not prefix else "unique_correct",
+                     "ece": "ece_saver", "nll": "nll_saver", "mse": "mse_saver", "accu": "accu_saver"}
+            for k, v in cols.items():
+                setattr(self, prefix + names[k], v)
+        return self
+
+    # ---- confidence-threshold early exiting and FLOP accounting (:568-735) ----------------------------
+    _FLOPS = {      # get_flops_per_module :568-580
+        "vgg19": ([40173568, 56950784, 132448256, 132284416, 37789696], [14227456, 9467904, 4728832, 0, 0], [51200] * 5),
+        "resnet18": ([154402816, 135036928, 134627328, 134422528], [56909824, 37871616, 18915328, 0], [51200] * 4),
+    }
+
+    def get_model_type(self):
+        names = {c.__name__ for c in type(self.model).__mro__}
+        if "VGG" in names:
+            return "vgg19"
+        if "ResNet" in names:
+            return "resnet18"
+        raise ValueError
+
+    def get_dropout_type(self):
+        """:582-596 -> (exit_only, dropout_rate, mc_passes)."""
+        try:
+            exit_only = True
+            if self.model.dropout_exit and self.model.dropout is None:
+                exit_only = True
+            elif self.model.dropout is not None:
+                exit_only = False
+            return exit_only, self.model.dropout_p, 10
+        except AttributeError:
+            return True, 0, 1
+
+    def get_flops_per_module(self):
+        self.model_type = getattr(self, "model_type", None) or self.get_model_type()
+        self.flops_per_layer, self.flop_per_exit_convs, self.flops_per_exit = [list(v) for v in self._FLOPS[self.model_type]]
+        self.n_exits = len(self.flops_per_layer)
+        self.baseline_flops = sum(self.flops_per_layer) + self.flop_per_exit_convs[-1] + self.flops_per_exit[-1]
+
+    def is_confident(self, p_evals, threshold, layer, instance, diff=False):
+        row = np.asarray(p_evals[layer][instance])
+        if diff:
+            top2 = np.sort(row)[-2:]
+            return abs(top2[1] - top2[0]) > threshold
+        return np.max(row).item() > threshold
+
+    def _exit_scan(self, threshold, p_evals, diff):
+        """bnn_confidence_exit over [E, N, C] -> (exit index per instance, chosen predictions, images per exit)."""
+        lib = _lib.load()
+        p_evals = np.asarray(p_evals)
+        E, N, C = p_evals.shape
+        with torch.cuda.device(self.device):
+            _lib.require_device()
+            dp = torch.as_tensor(np.ascontiguousarray(p_evals), dtype=torch.float32, device=self.device)
+            idx = torch.empty(N, dtype=torch.int32, device=self.device)
+            best = torch.empty((N, C), dtype=torch.float32, device=self.device)
+            hist = torch.zeros(E, dtype=torch.int32, device=self.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.bnn_confidence_exit(dp.data_ptr(), E, N, C, min(1, E - 1), float(threshold), int(bool(diff)),
+                                               idx.data_ptr(), best.data_ptr(), hist.data_ptr(), stream))
+            return idx.cpu().numpy(), best.cpu().numpy().astype(np.float64), hist.cpu().numpy()
+
+    def confidence_exiting(self, threshold, p_evals, labels, diff=False):
+        """-> (accuracy, ece, nll) of the predictions taken at the first confident exit (:606-630)."""
+        _, best, _ = self._exit_scan(threshold, p_evals, diff)
+        ece, nll, mse, accu = self.ece_eval_binary(best, labels)
+        return accu, ece, nll
+
+    def get_flops_standard_exit(self, layer, mc_passes, ensemble=False):
+        if ensemble:
+            return sum(self.flops_per_layer[:layer + 1]) + sum(self.flop_per_exit_convs[:layer + 1]) + \
+                sum(self.flops_per_exit[:layer + 1]) * mc_passes
+        return sum(self.flops_per_layer[:layer + 1]) + self.flop_per_exit_convs[layer] + self.flops_per_exit[layer] * mc_passes
+
+    def _exit_cost(self, layer, mc_passes, ensembled):
+        block = sum(self.flops_per_layer[:layer + 1])
+        if not ensembled:
+            if self.exit_only:
+                return block + self.flop_per_exit_convs[layer] + mc_passes * self.flops_per_exit[layer]
+            return mc_passes * (block + self.flop_per_exit_convs[layer] + self.flops_per_exit[layer])
+        if self.exit_only:
+            return block + sum(self.flop_per_exit_convs[:layer + 1]) + mc_passes * sum(self.flops_per_exit[:layer + 1])
+        return mc_passes * (block + sum(self.flop_per_exit_convs[:layer + 1]) + sum(self.flops_per_exit[:layer + 1]))
+
+    def flop_saver(self, threshold, p_evals, labels, mc_passes=10, diff=False):
+        """Total FLOPs of confidence-threshold exiting over the dataset (:639-672)."""
+        _, _, hist = self._exit_scan(threshold, p_evals, diff)
+        return int(sum(int(n) * self._exit_cost(l, mc_passes, False) for l, n in enumerate(hist)))
+
+    def flop_saver_ensembled(self, threshold, p_evals, labels, mc_passes=10, diff=False):
+        """Same with cumulative-exit ensembles: all earlier exit branches are paid too (:674-726)."""
+        _, _, hist = self._exit_scan(threshold, p_evals, diff)
+        return int(sum(int(n) * self._exit_cost(l, mc_passes, True) for l, n in enumerate(hist)))
+
+    def get_confidence_exiting_values(self, model_num=None, thresholds=(0.1, 0.15, 0.25, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95,
+                                                                         0.99, 0.999)):
+        """:543-566 on the predictions held by this object (the reference re-reads them from the .npy file `saver`
+        wrote).  -> list of dicts with accuracy / ece / nll / flops relative to the baseline network."""
+        self.model_type = self.get_model_type()
+        self.exit_only, dropout_rate, mc_passes = self.get_dropout_type()
+        self.get_flops_per_module()
+        rows = []
+        n = self.labels.shape[0]
+        for thr in thresholds:
+            for name, pe, fl in (("single", self.preds, self.flop_saver), ("ensemble", self.ensemble_preds,
+                                                                            self.flop_saver_ensembled)):
+                accu, ece, nll = self.confidence_exiting(thr, pe, self.labels)
+                rows.append(dict(kind=name, threshold=thr, dropout_rate=dropout_rate, accuracy=accu, ece=ece, nll=nll,
+                                 flops=fl(thr, pe, self.labels, mc_passes=mc_passes) / (self.baseline_flops * n)))
+        return rows
+
+
+def _kde_ece_integrate(x_int, pp1, pp2, perc, order=1):
+    """results_analyzer.py:426-443, vectorised: integrand |conf - min(perc*pp1/pp2, 1)|^order * pp2 where a density
+    exceeds 1e-6, else the previous integrand value carried forward (index > 1), then the ratio of trapezoid
+    integrals over [0, 1]."""
+    live = np.maximum(pp1, pp2) > 1e-6
+    with np.errstate(divide="ignore", invalid="ignore"):
+        accu = np.minimum(perc * pp1 / pp2, 1.0)
+        val = np.abs(x_int - accu) ** order * pp2
+    val = np.where(np.isnan(accu), 0.0, val)
+    idx = np.where(live, np.arange(x_int.shape[0]), -1)
+    idx[:2] = np.where(live[:2], idx[:2], np.arange(2))          # i <= 1 without density: stays 0 (own slot)
+    val = np.where(live, val, 0.0)
+    last = np.maximum.accumulate(idx)
+    integral = val[last]
+    ind = (x_int >= 0.0) & (x_int <= 1.0)
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    return float(trapz(integral[ind], x_int[ind]) / trapz(pp2[ind], x_int[ind]))

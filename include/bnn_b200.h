@@ -188,6 +188,29 @@ int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C
 int bnn_dataset_metrics(const float* probs, const int32_t* labels, int N, int C, float* workspace, float* out,
                         void* stream);
 
+/* ---- confidence-threshold early exiting (results_analyzer.py:606-631 confidence_exiting, :728-735 is_confident) ----
+ * probs [E][N][C] float32 (mean predictions of every exit).  Image i leaves at the first exit e in
+ * [first_exit, E-1) with max_c p > threshold (diff == 0) or top1 - top2 > threshold (diff != 0), else at E-1; the
+ * reference starts its scan at exit 1 (`for layer in range(1, self.n_exits)`), pass first_exit = 1 to mirror it.
+ * exit_idx int32 [N]; best_probs float32 [N][C] = the chosen exit's prediction; exit_hist int32 [E] = images per
+ * exit (zeroed by the call) - the FLOP accounting of flop_saver / flop_saver_ensembled (:639-726) is a dot product
+ * of this histogram with the per-exit cost table. */
+int bnn_confidence_exit(const float* probs, int E, int N, int C, int first_exit, float threshold, int diff,
+                        int32_t* exit_idx, float* best_probs, int32_t* exit_hist, void* stream);
+
+/* ---- KDE-ECE building blocks (ece_kde_binary, results_analyzer.py:351-443) ----
+ * bnn_top_label: conf[i] = p[i][argmax] / sum_c p[i][c] (:374-380, :412-419), correct[i], and
+ *   stats (double [3], zeroed by the call) = (#correct, sum conf over correct, sum conf^2 over correct) for the
+ *   bandwidth rule std(conf | correct) * (2N)^-0.2 (:389-392).
+ * bnn_kde_triweight: density of `data` (only entries with flags[i] != 0 when flags is given) mirrored about lo / hi
+ *   (mirror_1d :339-349), triweight kernel of standard deviation `bw`, on the grid x0 + j*dx, j < G; zero outside
+ *   (lo, hi) and doubled (:403-406); n_points = number of un-mirrored points used.  The estimate is evaluated
+ *   EXACTLY; the reference uses KDEpy's FFTKDE (linear binning + FFT convolution) for the same estimator. */
+int bnn_top_label(const float* probs, const int32_t* labels, int N, int C, float* conf, int32_t* correct,
+                  double* stats, void* stream);
+int bnn_kde_triweight(const float* data, const int32_t* flags, int n, double bw, double n_points, double x0,
+                      double dx, int G, double lo, double hi, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,145 @@ def nll_mse_acc(p, label_onehot):
     nll = -np.sum(label_onehot * np.log(pc)) / p.shape[0]
     acc = np.mean(np.argmax(pc, 1) == np.argmax(label_onehot, 1))
     return nll, mse, acc
+
+
+# ---- confidence-threshold early exiting and FLOP accounting (results_analyzer.py:568-580, :606-735) -----------
+FLOP_TABLES = {     # get_flops_per_module :568-580
+    "vgg19": dict(n_exits=5, flops_per_layer=[40173568, 56950784, 132448256, 132284416, 37789696],
+                  flop_per_exit_convs=[14227456, 9467904, 4728832, 0, 0], flops_per_exit=[51200] * 5),
+    "resnet18": dict(n_exits=4, flops_per_layer=[154402816, 135036928, 134627328, 134422528],
+                     flop_per_exit_convs=[56909824, 37871616, 18915328, 0], flops_per_exit=[51200] * 4),
+}
+
+
+def baseline_flops(model_type):
+    t = FLOP_TABLES[model_type]
+    return sum(t["flops_per_layer"]) + t["flop_per_exit_convs"][-1] + t["flops_per_exit"][-1]      # :580
+
+
+def is_confident(p_row, threshold, diff=False):
+    """:728-735 - max p > threshold, or |top1 - top2| > threshold."""
+    if diff:
+        top2 = np.sort(p_row)[-2:]
+        return abs(top2[1] - top2[0]) > threshold
+    return np.max(p_row) > threshold
+
+
+def exit_indices(threshold, p_evals, n_exits, diff=False, first_exit=1):
+    """The exit every instance leaves at in confidence_exiting / flop_saver (:606-631): the scan starts at exit
+    `first_exit` = 1 (`for layer in range(1, self.n_exits)`), the last exit takes whatever is left."""
+    N = p_evals.shape[1]
+    out = np.full(N, n_exits - 1, dtype=np.int64)
+    for i in range(N):
+        for layer in range(first_exit, n_exits - 1):
+            if is_confident(p_evals[layer][i], threshold, diff):
+                out[i] = layer
+                break
+    return out
+
+
+def confidence_exiting_preds(threshold, p_evals, n_exits, diff=False):
+    """best_preds of :606-629: every instance's prediction at the exit it leaves at."""
+    idx = exit_indices(threshold, p_evals, n_exits, diff)
+    return p_evals[idx, np.arange(p_evals.shape[1])], idx
+
+
+def exit_flops(model_type, layer, mc_passes, exit_only, ensembled):
+    """Cost charged to ONE instance leaving at `layer` by flop_saver (:639-672) / flop_saver_ensembled (:674-726)."""
+    t = FLOP_TABLES[model_type]
+    block = sum(t["flops_per_layer"][:layer + 1])
+    if not ensembled:
+        if exit_only:
+            return block + t["flop_per_exit_convs"][layer] + mc_passes * t["flops_per_exit"][layer]
+        return mc_passes * (block + t["flop_per_exit_convs"][layer] + t["flops_per_exit"][layer])
+    f = block
+    if exit_only:
+        for prev in range(layer + 1):
+            f += t["flop_per_exit_convs"][prev] + mc_passes * t["flops_per_exit"][prev]
+        return f
+    for prev in range(layer + 1):
+        f += t["flop_per_exit_convs"][prev] + t["flops_per_exit"][prev]
+    return f * mc_passes
+
+
+def flop_saver(model_type, threshold, p_evals, mc_passes=10, diff=False, exit_only=True, ensembled=False):
+    t = FLOP_TABLES[model_type]
+    idx = exit_indices(threshold, p_evals, t["n_exits"], diff)
+    return sum(exit_flops(model_type, int(l), mc_passes, exit_only, ensembled) for l in idx)
+
+
+def flops_standard_exit(model_type, layer, mc_passes, ensemble=False):
+    """get_flops_standard_exit :632-637."""
+    t = FLOP_TABLES[model_type]
+    if ensemble:
+        return sum(t["flops_per_layer"][:layer + 1]) + sum(t["flop_per_exit_convs"][:layer + 1]) + \
+            sum(t["flops_per_exit"][:layer + 1]) * mc_passes
+    return sum(t["flops_per_layer"][:layer + 1]) + t["flop_per_exit_convs"][layer] + t["flops_per_exit"][layer] * mc_passes
+
+
+# ---- KDE-ECE (results_analyzer.py:339-443) ----------------------------------------------------------------------
+def mirror_1d(d, lo, hi):
+    """:339-349 with both bounds: reflect the points below the midpoint about lo, the others about hi."""
+    mid = (lo + hi) / 2
+    return np.concatenate(((2 * lo - d[d < mid]).reshape(-1, 1), d, (2 * hi - d[d >= mid]).reshape(-1, 1)))
+
+
+def kde_triweight_exact(data, bw, grid):
+    """The estimator KDEpy's FFTKDE(bw, 'triweight').fit(data).evaluate(grid) approximates by linear binning + FFT:
+    (1/n) sum_d K((x - d) / h) / h, K(u) = 35/32 (1 - u^2)^3 on |u| < 1, h = bw / sqrt(var K) = 3 bw
+    (KDEpy scales every kernel so that `bw` is its standard deviation; triweight variance = 1/9)."""
+    data = np.asarray(data, dtype=np.float64).reshape(-1)
+    h = 3.0 * bw
+    out = np.zeros(grid.shape[0])
+    for lo in range(0, grid.shape[0], 1024):
+        u = (grid[lo:lo + 1024, None] - data[None, :]) / h
+        w = np.clip(1.0 - u * u, 0.0, None)
+        out[lo:lo + 1024] = (w ** 3).sum(1)
+    return out * (35.0 / 32.0) / (h * data.shape[0])
+
+
+def ece_kde(p, label_onehot, order=1, kde=kde_triweight_exact):
+    """ece_kde_binary :351-443, multi-class (top-label) branch, p_int = p.  `kde(data, bw, grid)` stands in for
+    KDEpy (not installed: parity of this statistic is pinned against the reference's own source with this exact
+    estimator injected as `FFTKDE`, tests/golden/make_golden_analysis.py)."""
+    p = np.clip(np.asarray(p, dtype=np.float64), 1e-256, 1 - 1e-256)
+    x_int = np.linspace(-0.6, 1.6, num=2 ** 14)
+    N = p.shape[0]
+    label_index = np.argmax(label_onehot, axis=1)
+    pred = np.argmax(p, axis=1)
+    label_binary = (pred == label_index).astype(np.float64).reshape(-1, 1)
+    # the reference keeps p_b in a float32 torch tensor (torch.zeros(N,1), :373)
+    p_b = (p[np.arange(N), pred] / p.sum(1)).astype(np.float32).reshape(-1, 1)
+    dconf_1 = p_b[label_binary[:, 0] == 1].reshape(-1, 1)
+    if np.std(dconf_1) != 0:
+        kbw = np.std(dconf_1) * (N * 2) ** -0.2
+    else:
+        kbw = 0.0000000000000001 * (N * 2) ** -0.2
+    pp1 = kde(mirror_1d(dconf_1, 0.0, 1.0), kbw, x_int)
+    pp1[(x_int <= 0.0) | (x_int >= 1.0)] = 0
+    pp1 = pp1 * 2
+    p_int = p / p.sum(1)[:, None]
+    pred_b_int = p_int[np.arange(N), np.argmax(p_int, axis=1)].reshape(-1, 1)
+    pp2 = kde(mirror_1d(pred_b_int, 0.0, 1.0), kbw, x_int)
+    pp2[(x_int <= 0.0) | (x_int >= 1.0)] = 0
+    pp2 = pp2 * 2
+    perc = np.mean(label_binary)
+    return kde_ece_integrate(x_int, pp1, pp2, perc, order)
+
+
+def kde_ece_integrate(x_int, pp1, pp2, perc, order=1):
+    """:426-443 - |conf - accuracy(conf)|^order weighted by the confidence density; where both densities vanish the
+    previous integrand value is carried forward (the reference's sequential `integral[i] = integral[i-1]`)."""
+    integral = np.zeros(x_int.shape)
+    for i in range(x_int.shape[0]):
+        conf = x_int[i]
+        if max(pp1[i], pp2[i]) > 1e-6:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                accu = np.min([perc * pp1[i] / pp2[i], 1.0])
+            if not np.isnan(accu):
+                integral[i] = np.abs(conf - accu) ** order * pp2[i]
+        elif i > 1:
+            integral[i] = integral[i - 1]
+    ind = np.where((x_int >= 0.0) & (x_int <= 1.0))
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    return trapz(integral[ind], x_int[ind]) / trapz(pp2[ind], x_int[ind])

@@ -194,7 +194,7 @@ def test_calibration_bins_and_ece(lib):
         nll, mse, acc = stats.nll_mse_acc(p, onehot)
         ece, g_nll, g_mse, g_acc = fa.ece_eval_binary(p, onehot)
         assert abs(g_nll - nll) < 1e-5 * max(1.0, nll) and abs(g_mse - mse) < 1e-6 and abs(g_acc - acc) < 1e-7
-        assert abs(ece - float(z["ece%d" % k])) < 1e-4
+        assert abs(ece - stats.ece_kde(p, onehot)) < 1e-4         # the ECE of ece_eval_binary is the KDE one (:503)
 
 
 TC_SHAPES = [
@@ -451,3 +451,58 @@ def test_conv_tc_gathered_bad_args(lib):
     # Kc must be a multiple of 16
     assert lib.bnn_conv2d_tc_gathered(y.data_ptr(), y.data_ptr(), y.data_ptr(), yp, 1, 0, 0, 1, 8, 8, 8, 40, 64, 3, 1, 4,
                                       0, 0, 4, 1, stream()) == -4
+
+
+def test_full_analysis_confidence_exiting_flops_and_kde_ece(lib):
+    """FullAnalysis.confidence_exiting / flop_saver / flop_saver_ensembled / ece_eval_binary on the device vs the
+    values frozen from the reference's own source (tests/golden/analysis.npz)."""
+    from bayesnn_fpga_b200.results_analyzer import FullAnalysis
+    from tests.cases import GOLDEN
+    z = np.load(GOLDEN + "/analysis.npz")
+
+    class Dummy:
+        n_exits, out_dim = 1, 10
+    for k, mt in enumerate(["resnet18", "vgg19"]):
+        p_evals, lab = z["p%d" % k], z["lab%d" % k]
+        E, N, C = p_evals.shape
+        onehot = np.eye(C)[lab]
+        fa = FullAnalysis(Dummy(), None, run=False)
+        fa.model_type = mt
+        fa.get_flops_per_module()
+        assert fa.baseline_flops == stats.baseline_flops(mt) and fa.n_exits == E
+        for r, row in enumerate(z["rows%d" % k]):
+            thr, diff = float(row[0]), bool(row[1])
+            idx, best, hist = fa._exit_scan(thr, p_evals, diff)
+            assert (idx == z["exit%d_%d" % (k, r)]).all() and hist.sum() == N and hist[0] == 0
+            accu, ece, nll = fa.confidence_exiting(thr, p_evals, onehot, diff=diff)
+            report(test="confidence_exiting", model=mt, thr=thr, diff=diff, d_acc=abs(accu - row[2]), d_ece=abs(ece - row[3]),
+                   d_nll=abs(nll - row[4]))
+            assert abs(accu - row[2]) < 1e-6 and abs(ece - row[3]) < 1e-4 and abs(nll - row[4]) < 1e-5 * max(1.0, row[4])
+            got = []
+            for eo in (True, False):
+                fa.exit_only = eo
+                got += [fa.flop_saver(thr, p_evals, onehot, mc_passes=10, diff=diff),
+                        fa.flop_saver_ensembled(thr, p_evals, onehot, mc_passes=10, diff=diff)]
+            assert [float(v) for v in got] == list(row[5:9])
+            for layer in range(E):
+                assert fa.get_flops_standard_exit(layer, 10, True) == stats.flops_standard_exit(mt, layer, 10, True)
+        for e in range(E):
+            ece, nll, mse, accu = fa.ece_eval_binary(p_evals[e], onehot)
+            w = z["per_exit%d" % k][e]
+            report(test="kde_ece", model=mt, exit=e, ece=ece, want=float(w[0]))
+            assert abs(ece - w[0]) < 1e-4 and abs(nll - w[1]) < 1e-5 * max(1.0, w[1]) and abs(mse - w[2]) < 1e-6 \
+                and abs(accu - w[3]) < 1e-6
+    # the KDE kernel alone against the float64 estimator, incl. flags and mirroring
+    rng = np.random.RandomState(3)
+    data = rng.beta(5, 2, 700).astype(np.float32)
+    flags = (rng.rand(700) > 0.4).astype(np.int32)
+    G, x0, dx, bw = 4096, -0.6, 2.2 / 4095, 0.013
+    out = torch.zeros(G, dtype=torch.float64, device="cuda")
+    d_data, d_flags = torch.from_numpy(data).cuda(), torch.from_numpy(flags).cuda()
+    assert lib.bnn_kde_triweight(d_data.data_ptr(), d_flags.data_ptr(), 700, bw, float(flags.sum()), x0, dx, G, 0.0, 1.0,
+                                 out.data_ptr(), stream()) == 0, lib.bnn_last_error()
+    grid = x0 + dx * np.arange(G)
+    sel = data[flags != 0].astype(np.float64).reshape(-1, 1)
+    want = stats.kde_triweight_exact(stats.mirror_1d(sel, 0.0, 1.0), bw, grid) * 2
+    want[(grid <= 0) | (grid >= 1)] = 0
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-9 * max(1.0, want.max())

@@ -94,3 +94,30 @@ def test_entropy_and_ece_width_definitions():
     p = np.array([[0.75, 0.25]] * 4)
     assert abs(stats.ece_width(p, np.array([0, 0, 0, 1]))) < 1e-12
     assert abs(stats.ece_width(p, np.array([0, 0, 1, 1])) - 0.25) < 1e-12
+
+
+def test_analysis_statistics_oracle_matches_reference_fixture():
+    """confidence exiting, FLOP accounting and KDE-ECE restatements vs values frozen from the reference's own source
+    (tests/golden/make_golden_analysis.py; KDEpy's FFTKDE replaced by the exact estimator it approximates)."""
+    z = np.load(GOLDEN + "/analysis.npz")
+    for k, mt in enumerate(["resnet18", "vgg19"]):
+        p_evals, lab = z["p%d" % k], z["lab%d" % k]
+        E, N, C = p_evals.shape
+        onehot = np.eye(C)[lab]
+        rows = z["rows%d" % k]
+        for r, row in enumerate(rows):
+            thr, diff = float(row[0]), bool(row[1])
+            best, idx = stats.confidence_exiting_preds(thr, p_evals, E, diff)
+            assert (idx == z["exit%d_%d" % (k, r)]).all()
+            nll, mse, acc = stats.nll_mse_acc(best, onehot)
+            assert abs(acc - row[2]) < 1e-12 and abs(nll - row[4]) < 1e-12
+            want_fl = row[5:9]
+            got_fl = [stats.flop_saver(mt, thr, p_evals, 10, diff, eo, ens) for eo in (True, False) for ens in (False, True)]
+            assert [float(v) for v in got_fl] == list(want_fl)
+        assert idx.min() >= 1                                   # the reference never exits at exit 0 (:612)
+        if k == 0:                                              # KDE-ECE: one exit is enough for the CPU suite
+            assert abs(stats.ece_kde(p_evals[1], onehot) - z["per_exit%d" % k][1, 0]) < 1e-12
+    # the exact estimator integrates to one and reproduces a closed form at a single point
+    grid = np.linspace(-1, 1, 4001)
+    dens = stats.kde_triweight_exact(np.array([0.0]), 0.1, grid)
+    assert abs(np.sum(dens) * (grid[1] - grid[0]) - 1.0) < 1e-6 and abs(dens[2000] - 35.0 / 32.0 / 0.3) < 1e-12
