@@ -14,11 +14,11 @@
 //               dense box of one (row parity, column parity) plane: box (64, tw, 1, th, tn)
 //   Tiles are 128 consecutive output pixels (tw = OW, th rows, tn images) x BN output channels.
 //
-// CTA = 6 warps, persistent over tiles:
+// CTA = 2 + EW warps (EW = 8 epilogue warps, 16 for the swapped dropout epilogue), persistent over tiles:
 //   warp 0  : TMA producer (one elected lane) - A box + W box per k-block into a STAGES-deep smem ring
 //   warp 1  : TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators
 //             in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2-5: epilogue - tcgen05.ld 32 lanes x 32 columns -> + folded-BN bias -> + residual -> ReLU ->
+//   warps 2.. : epilogue - tcgen05.ld 32 lanes x 32 columns -> + folded-BN bias -> + residual -> ReLU ->
 //             Philox dropout / Masksembles mask -> 16-bit pack -> 64-byte row stores
 #include <cuda.h>
 #include <stdlib.h>
@@ -36,8 +36,11 @@ namespace tc {
 constexpr int BM = 128;          // rows (output pixels) per tile
 constexpr int BK = 64;           // K elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp + MMA warp + 8 epilogue warps
+// EW = epilogue warps.  The operand-swapped kernel's epilogue with a fused element-wise dropout (Philox bits exchanged
+// by shuffles, residual, 2-byte stores) is latency-bound with two warps per scheduler - ncu: 47 % tensor-pipe activity
+// on layer2.0.1.conv2 - and runs 16 epilogue warps (0.86 -> 0.74 ms at C2); the plain epilogues are FASTER with 8
+// (measured: 16 warps cost 4-7 % on the layers without dropout), so EW is a template parameter chosen per launch.
+__host__ __device__ constexpr int num_threads(int ew) { return 64 + ew * 32; }
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
 __host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * BK * 2; }
@@ -299,8 +302,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // accumulator-full barriers of both CTAs; both epilogues arrive on the leader's accumulator-empty barrier.
 // COMPACT (non-swapped epilogue only; the swapped one decides at run time): a fused Masksembles site may store
 // only the kept channels of each sample's mask (DropParams::compact_pos), 2 bytes at a time.
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, typename T>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
+__global__ void __launch_bounds__(num_threads(EW), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   constexpr bool MC2 = PAIR == 1;
   constexpr bool CG2 = PAIR == 2;
@@ -341,7 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty[i], CG2 ? 2 * EW : EW);   // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -512,7 +515,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // which keeps this fully unrolled loop small (the first version, with run-time strides and per-pixel
       // 64-bit address arithmetic, was 100 KB of code and instruction-cache bound).
       constexpr int PX = MT * BM;                         // pixels per tile (256)
-      constexpr int PCH = PX / 64;                        // 32-pixel chunks per warp
+      constexpr int NHF = EW / 4;             // warps per TMEM lane group: each takes PX / NHF pixels
+      constexpr int PCH = PX / (32 * NHF);                // 32-pixel chunks per warp
       const uint16_t* __restrict__ res16 = reinterpret_cast<const uint16_t*>(p.res);
       const int64_t sample_px = (int64_t)p.dp.batch * p.OHW;          // pixels per MC sample
       const int c = q * 32 + lane;                                    // channel inside the group (cout_g == BN)
@@ -523,19 +527,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.yg[n_tile]);
         const float bias_c = __ldg(p.bias + n_tile * BN + c);
         const bool relu = (p.relu_mask >> n_tile) & 1u;
-        const int m_base = m_tile * PX + hf * (PX / 2);
+        const int m_base = m_tile * PX + hf * (PX / NHF);
         if (has_res) {
           // pull this warp's residual rows (32 channels = 64 bytes per pixel) into L2 while the MMAs of this tile
           // are still running: lane l touches pixels l, l+32, l+64, l+96 of the warp's 128-pixel half
 #pragma unroll
-          for (int i = 0; i < PX / 64; ++i) {
+          for (int i = 0; i < PCH; ++i) {
             const int m = m_base + i * 32 + lane;
             if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(res16 + (size_t)m * BN + q * 32));
           }
         }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + hf * (PX / 2));
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + hf * (PX / NHF));
 #pragma unroll 1
         for (int ch = 0; ch < PCH; ++ch) {
           const int m0 = m_base + ch * 32;
@@ -580,6 +584,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) rr[j] = (j < nvalid) ? (uint32_t)__ldg(rp + j * BN) : 0u;
           }
           tmem_ld_wait();
+          if (p.dp.kind == BNN_DROP_NONE && nvalid >= 32) {
+            // fast path (no stochastic site, full chunk): ncu's source page showed the general path below issue-bound
+            // on per-element predicates and keep-bit selects (stall_selected + stall_math + stall_not_selected > 40 %
+            // of the samples on the sibling-group launch); here an element is FADD [+ residual] + FMNMX + F2FP + STG
+            const float lo = relu ? 0.f : -INFINITY;
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float f = fmaxf(__uint_as_float(v[j]) + bias_c + unpack2<T>(rr[j]).x, lo);
+                yp[j * BN] = (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float f = fmaxf(__uint_as_float(v[j]) + bias_c, lo);
+                yp[j * BN] = (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
+              }
+            }
+            continue;
+          }
           auto value = [&](int j) -> uint16_t {
             float f = __uint_as_float(v[j]) + bias_c;
             if (has_res) f += unpack2<T>(rr[j]).x;
@@ -613,7 +637,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int cbase = n_tile * BN + hf * (BN / 2);      // first (concatenated) output channel of this warp
       const int grp = cbase / p.cout_g;                   // output group and channel offset inside it
       const int cgrp = cbase - grp * p.cout_g;
-      T* __restrict__ y = reinterpret_cast<T*>(p.yg[grp]);
+      // 128-channel groups paired into 256-column tiles: an odd group count leaves the last half-tile without output
+      const bool dead = grp >= p.groups;
+      T* __restrict__ y = reinterpret_cast<T*>(p.yg[dead ? 0 : grp]);
       const bool relu = (p.relu_mask >> grp) & 1u;
 
       // residual rows are fetched BEFORE waiting for the accumulator: the DRAM latency hides behind the MMAs
@@ -637,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
-        const bool valid = m < p.M;
+        const bool valid = m < p.M && !dead;
         // stochastic-site coordinates of this output pixel
         int s_local = 0;
         uint64_t e_base = 0;
@@ -658,7 +684,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int c0 = cbase + ch * 32;
           float4 bia[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + (dead ? 0 : c0)) + j);
           tmem_ld_wait();
           if (valid) {
             const size_t off = (size_t)m * p.cout_g + (cgrp + ch * 32);
@@ -797,12 +823,12 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, typename T>
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
   static bool configured = false;
   constexpr int smem = smem_bytes_pair(BN, MT, PAIR);
   constexpr bool MC2 = PAIR != 0;
-  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, T>;
+  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T>;
   if (!configured) {
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -813,7 +839,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
     int grid = 2 * p.num_tiles < (sm_count() & ~1) ? 2 * p.num_tiles : (sm_count() & ~1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(num_threads(EW));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -827,7 +853,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
   } else {
     p.num_tiles = m_tiles * p.n_tiles_n;
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+    kern<<<grid, num_threads(EW), smem, st>>>(ta, tb, p);
   }
   BNN_LAUNCH_OK();
   return BNN_OK;
@@ -911,8 +937,22 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
     if (int rc = tc::encode_map(&ta, dtype, 5, x, dims, strides, box)) return rc;
   }
-  // a channel tile never straddles two output groups: BN divides cout_g
-  const int BN = cout_g % 256 == 0 ? 256 : (cout_g % 128 == 0 ? 128 : 64);
+  // a channel tile never straddles two output groups: BN divides cout_g ...
+  int BN = cout_g % 256 == 0 ? 256 : (cout_g % 128 == 0 ? 128 : 64);
+  // ... except, as an EXPERIMENT (BNN_TC_PAIR_GROUPS=1, off by default), sibling groups of exactly 128 channels
+  // PAIRED into 256-column tiles of the cta_group::2 kernel (each epilogue half-tile is one group): the activation
+  // tile is loaded once per two groups and a k-block moves 32 KB per 2.1 MMAC through L2 -> SM instead of the swapped
+  // kernel's 48 KB.  Measured on the sibling launch behind the first site (K = 576): 1.42 ms vs 0.77 ms - with only 9
+  // k-blocks per tile the row-per-thread epilogue of the 256-column kernel (16-byte stores into 32 different rows per
+  // instruction) becomes the bottleneck, so the swapped kernel stays the default for 128-channel groups.  Both groups
+  // of a pair must agree on the centre-tap flag; an odd group count leaves a half-tile of zero weights (TMA
+  // zero-fills the rows past Cout) that the epilogue skips.
+  if (groups >= 2 && cout_g == 128 && getenv("BNN_TC_PAIR_GROUPS") && atoi(getenv("BNN_TC_PAIR_GROUPS")) == 1) {
+    bool ok_pairs = true;
+    for (int g = 0; g + 1 < groups; g += 2)
+      ok_pairs = ok_pairs && (((center_mask >> g) & 1u) == ((center_mask >> (g + 1)) & 1u) || ksize != 3);
+    if (ok_pairs) BN = 256;
+  }
   // CTA pairs with weight multicast: BN = 256 kernels with at least one pair of row-tiles per SM pair
   // (BNN_TC_MC_MIN_TILES overrides the threshold so that unit tests can drive the paired kernel with small shapes)
   const int64_t mc_min = getenv("BNN_TC_MC_MIN_TILES") ? atoll(getenv("BNN_TC_MC_MIN_TILES")) : 2 * (int64_t)sm_count();
@@ -934,7 +974,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   tc::Params p{};
   p.M = N * OH * OW;
   p.Cout = Cout;
-  p.n_tiles_n = Cout / BN;
+  p.n_tiles_n = (Cout + BN - 1) / BN;
   p.num_tiles = ((p.M + tc::BM - 1) / tc::BM) * p.n_tiles_n;
   p.taps = ksize * ksize;
   p.cblocks = (Cin + tc::BK - 1) / tc::BK;
@@ -962,10 +1002,11 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   cudaStream_t st = (cudaStream_t)stream;
 
   // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
-#define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_)                                           \
-  case BN_:                                                                                          \
-    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, __half>(ta, tb, p, st)    \
-                            : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, __nv_bfloat16>(ta, tb, p, st);
+#define BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_)                                          \
+  case BN_:                                                                                              \
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __half>(ta, tb, p, st)   \
+                            : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __nv_bfloat16>(ta, tb, p, st);
+#define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_) BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, 8)
 #define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_) BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, false)
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
@@ -991,6 +1032,11 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     }
   }
   if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
+    const bool wide_epi = drop && drop->kind == BNN_DROP_ELEMENT &&
+                          !(getenv("BNN_TC_SWAP_EPI") && atoi(getenv("BNN_TC_SWAP_EPI")) == 8);
+    if (wide_epi) {
+      switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 0, false, 16) }
+    }
     switch (BN) { BNN_TC_DISPATCH(128, 2, true, 0) }
   }
   if (cg2 && mc2) {
@@ -1006,6 +1052,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   }
 #undef BNN_TC_DISPATCH
 #undef BNN_TC_DISPATCH_C
+#undef BNN_TC_DISPATCH_E
   return BNN_E_UNSUPPORTED;
 }
 

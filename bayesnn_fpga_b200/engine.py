@@ -257,7 +257,7 @@ def _ptr(t):
 class Engine:
     """Executes a :class:`Graph` on the current CUDA device through the C ABI."""
 
-    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True, mask_gather=None):
+    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True, mask_gather=None, sample_chunk=None):
         if dtype not in DTYPES:
             raise ValueError("dtype must be one of %s" % sorted(DTYPES))
         if not torch.cuda.is_available():
@@ -275,6 +275,7 @@ class Engine:
         self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
         if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
             graph.fuse_sibling_convs(self._tc_eligible)
+        self.sample_chunk = int(os.environ.get("BNN_SAMPLE_CHUNK", "0")) if sample_chunk is None else int(sample_chunk)
         self.launches = 0
         self._prof = None
         self._graphs = {}
@@ -402,13 +403,14 @@ class Engine:
         acts = {}
         gmode = self._gather_ids(B)
         compact = {tid for tid, m in gmode.items() if m == "compact"}
+        chunk = S_local if self.sample_chunk <= 0 else min(S_local, self.sample_chunk)
         live = {g.input.id}
         for op in g.ops:
             live.update(t.id for t in (op.src, op.dst, op.res) + tuple(getattr(op, "dsts", ())) if t is not None)
         for t in g.tensors:
             if t.id not in live or gmode.get(t.id) == "weights":
                 continue                      # e.g. the un-masked output of a conv with a fused site
-            n = (S_local if t.stoch else 1) * B
+            n = (chunk if t.stoch else 1) * B
             if t.id in compact:
                 # gathered layout; zero-filled once: the padding slots [kept, kc) are never written
                 acts[t.id] = torch.zeros((n, t.H, t.W, self.gather[t.id]["kc"]), dtype=self.tdtype, device=dev)
@@ -423,6 +425,7 @@ class Engine:
             "acts": acts,
             "compact": compact,
             "gmode": gmode,
+            "chunk": chunk,
         }
         self._bufs[key] = st
         return st
@@ -521,9 +524,28 @@ class Engine:
         n_in = B * g.input.C * g.input.H * g.input.W
         self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc(
             _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W, stream))
+        # deterministic prefix once; everything behind the first stochastic site in chunks of `chunk` samples so that
+        # the activations handed from one layer to the next stay L2-resident (126 MB) instead of round-tripping HBM
+        chunk = st["chunk"]
+        self._run_ops(st, B, S_local, sample0, seed, accumulate, mask_offset, stream, "det", 0)
+        for c in range(0, S_local, max(chunk, 1)):
+            self._run_ops(st, B, min(chunk, S_local - c), sample0 + c, seed, accumulate or c > 0,
+                          None if mask_offset is None else mask_offset + c, stream, "stoch", c)
+        return st
+
+    def _run_ops(self, st, B, S_local, sample0, seed, accumulate, mask_offset, stream, phase, s_off):
+        """Enqueue the ops of one phase: "det" = ops on tensors without a sample dimension (and the heads that read
+        them, which loop over all samples themselves), "stoch" = per-sample ops for local samples
+        [s_off, s_off + S_local) whose global index starts at `sample0`."""
+        g, lib, acts = self.graph, self.lib, st["acts"]
+        es = 4 if self.dtype_name == "fp32" else 2
         sum_p, sum_l, sum_pl = self.sums_views(st, B)
         compact, gmode = st["compact"], st["gmode"]
         for op in g.ops:
+            out_t = op.dsts[0] if op.kind == "convg" else (op.dst if op.dst is not None else op.src)
+            is_stoch = True if op.kind == "site" else out_t.stoch
+            if is_stoch != (phase == "stoch"):
+                continue
             if op.kind in ("conv", "convg") and op.src.id in gmode:
                 if S_local == 0:
                     continue
@@ -598,7 +620,7 @@ class Engine:
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset)
                 lo = st["logits"]
                 # per-sample logits: one [S_local][B][C] slab per exit
-                lo_e = lo[e] if lo is not None else None
+                lo_e = lo[e][s_off:] if lo is not None else None
                 hw = op.src.H * op.src.W
                 nbytes = (S_local if op.src.stoch else 1) * B * hw * op.src.C * es + op.d_w.numel() * 4
                 flops = 2 * S_local * B * op.src.C * g.n_classes
@@ -606,7 +628,6 @@ class Engine:
                     _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
                     _ptr(op.d_w), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
                     _ptr(lo_e), int(accumulate), stream))
-        return st
 
     def profile_step(self, x, S_local, seed=0x5EED):
         """Device time of every launch of one step (CUDA events on the launching stream).

@@ -387,12 +387,15 @@ def test_conv_tc_fused_compact_epilogue(lib, Cout, M_img, pair, monkeypatch):
     (128, 68, 64, 1, 1, 16, 2),       # 64-channel tile kernel
     (256, 136, 512, 1, 2, 16, -4),    # B = 4 with the CTA-pair kernels forced: cta_group::2
     (256, 136, 256, 2, 2, 16, -8),
+    (64, 34, 128, 3, 2, 16, -4),      # 128-channel groups paired into 256-column cta_group::2 tiles (+ a dead half-tile)
+    (128, 68, 128, 2, 2, 16, -4),
 ])
 def test_conv_tc_gathered_vs_dense(lib, C, kept, cout_g, groups, stride, H, B, monkeypatch):
     """gathered-K convolution on the compact tensor == the grouped convolution on the dense masked tensor (same
     products; the tensor cores sum them in a different order) and == float64 torch."""
     if B < 0:
         monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+        monkeypatch.setenv("BNN_TC_PAIR_GROUPS", "1")     # experiment flag: 128-channel groups in 256-column tiles
         B = -B
     n, S, s0, cnt0 = 4, 3, 1, 2
     masks, pos, idx, kc = _mask_tables(n, C, kept, C + cout_g)
