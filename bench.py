@@ -169,10 +169,13 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
+NCU_SUMMARY = "profiles/r01_ncu_conv_tc_full_v2.json"
+
+
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 25 launches of one C2 step) from
-    the committed `ncu --set full` summary, or None."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_conv_tc_full.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 19 launches of one C2 step) from
+    the committed `ncu --set full` summary (tools/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, NCU_SUMMARY)
     if not os.path.exists(p):
         return None
     rows = json.load(open(p))
@@ -351,8 +354,12 @@ def main():
                 "flops_per_launch": flops / len(tc), "share_of_step": t_tc * 1e3 / sum(o["ms"] for o in prof),
                 "algorithmic_bytes_per_launch": sum(o["bytes"] for o in tc) / len(tc),
                 "traffic": ncu_traffic() if args.workload == "c2" else None,
-                "traffic_source": "profiles/r01_ncu_conv_tc_full.json (ncu --set full, mean DRAM bytes per launch; "
-                                  "captured before sibling fusion: 25 launches/step)"}
+                "traffic_source": NCU_SUMMARY + " (ncu --set full --clock-control none over the 19 conv launches of one "
+                                  "C2 step: mean dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
+        if roof["frac"] > 1.0:
+            roof["note"] = ("above the SUSTAINED cuBLAS figure (dense random operands at the 1 kW cap): this workload's "
+                            "small maps make most im2col taps zero padding, which draws less power, so the SM clock "
+                            "stays higher; against the burst figure the fraction is %.3f" % (ach / peaks["burst"]))
     else:
         flops = sum(o["flops"] for o in prof)
         t_all = sum(o["ms"] for o in prof) * 1e-3
@@ -389,6 +396,7 @@ def main():
                        "partition": "samples" if shard_samples else ("batch" if world > 1 else "none"),
                        "l2": "per-step activation working set (GiB) >> 126 MB L2; no explicit flush",
                        "cuda_graph": os.environ.get("BNN_CUDA_GRAPH", "1") != "0",
+                       "masksembles_mode": eng.gather_mode if kind == "resnet_mask" else None,
                        "algorithmic_gflop_per_image": 2e-9 * (pre_macs + S * suf_macs)},
             "tflops_whole_step": step_flops * (world if not shard_samples else world) / (ms / args.steps * 1e-3) / 1e12,
             "frac_of_tensor_peak_whole_step": step_flops / (ms / args.steps * 1e-3) / 1e12 / peaks["sustained"],
