@@ -7,6 +7,8 @@
 //                      weights are read once per image and the running sums never leave the SM.
 //   finalize_kernel  : means, cumulative exit ensembles, entropies.
 //   calibration_kernel: top-label confidence / correctness + equal-width bins.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -116,23 +118,132 @@ __device__ __forceinline__ void head_gemm(const float* __restrict__ pooled, floa
   }
 }
 
+
+// ---- tensor-core variant of the head GEMM (wide heads: C > 32, 16-bit feature storage) ---------------------------
+// logits[16 x C] = pooled[16 x F] * W[C x F]^T with mma.sync.m16n8k16 (legacy warp-level MMA: the GEMM is 16 rows per
+// image, far below a tcgen05 tile).  Both operands are split into a 16-bit high part and a 16-bit remainder and three
+// products are accumulated in fp32 (hi*hi + lo*hi + hi*lo), which keeps the result within ~2^-20 of the fp32 FFMA
+// form - the head must not add error on top of the convolution path.  A fragments come from shared memory
+// ([16][F + 8] 16-bit, the +8 padding makes the 32 lanes hit 32 banks), B fragments straight from the nn.Linear weight
+// layout [C][F] in L2.  Warp w owns the 8-class tiles w, w + 8, ...
+template <typename TM>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                                        uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename TM, int MT>
+__device__ __forceinline__ void head_gemm_mma(const TM* __restrict__ a_hi, const TM* __restrict__ a_lo,
+                                              float* __restrict__ logits, const TM* __restrict__ w_hi,
+                                              const TM* __restrict__ w_lo, const float* __restrict__ bias, int F, int C,
+                                              int ns, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int pitch = F + 8;
+  const int n_tiles = (C + 7) >> 3;
+  for (int nt = warp; nt < n_tiles; nt += HEAD_WARPS) {
+    const int n = nt * 8 + g;                               // the class whose weights this lane loads (B fragment)
+    const bool nv = n < C;
+    const TM* wh = w_hi + (size_t)(nv ? n : 0) * F + 2 * t;
+    const TM* wl = w_lo + (size_t)(nv ? n : 0) * F + 2 * t;
+    float acc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+#pragma unroll 2
+    for (int k0 = 0; k0 < F; k0 += 16) {
+      // one weight fragment (hi + lo) feeds all MT 16-sample row tiles
+      const uint32_t bh0 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wh + k0)) : 0u;
+      const uint32_t bh1 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wh + k0 + 8)) : 0u;
+      const uint32_t bl0 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wl + k0)) : 0u;
+      const uint32_t bl1 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wl + k0 + 8)) : 0u;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m * 16 >= ns) break;                            // row tiles past the last sample of this pass
+        const TM* ah0 = a_hi + (size_t)(m * 16 + g) * pitch + 2 * t + k0;
+        const TM* al0 = a_lo + (size_t)(m * 16 + g) * pitch + 2 * t + k0;
+        uint32_t ah[4], al[4];
+        ah[0] = *reinterpret_cast<const uint32_t*>(ah0);
+        ah[1] = *reinterpret_cast<const uint32_t*>(ah0 + 8 * pitch);
+        ah[2] = *reinterpret_cast<const uint32_t*>(ah0 + 8);
+        ah[3] = *reinterpret_cast<const uint32_t*>(ah0 + 8 * pitch + 8);
+        al[0] = *reinterpret_cast<const uint32_t*>(al0);
+        al[1] = *reinterpret_cast<const uint32_t*>(al0 + 8 * pitch);
+        al[2] = *reinterpret_cast<const uint32_t*>(al0 + 8);
+        al[3] = *reinterpret_cast<const uint32_t*>(al0 + 8 * pitch + 8);
+        mma16816<TM>(acc[m], al, bh0, bh1);                 // small terms first
+        mma16816<TM>(acc[m], ah, bl0, bl1);
+        mma16816<TM>(acc[m], ah, bh0, bh1);
+      }
+    }
+    // accumulator fragment: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1)
+    const int c0 = nt * 8 + 2 * t;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sl = m * 16 + g + (i >> 1) * 8, cc = c0 + (i & 1);
+        if (sl < ns && cc < C) logits[sl * C + cc] = acc[m][i] + __ldg(bias + cc);
+      }
+  }
+  __syncthreads();
+}
+
+template <typename TM>
+__device__ __forceinline__ TM to_tm(float v);
+template <>
+__device__ __forceinline__ __half to_tm<__half>(float v) { return from_f32<__half>(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_tm<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ float to_tm<float>(float v) { return v; }
+
+// fp32 weights [C][F] (the nn.Linear layout) -> 16-bit high part and 16-bit remainder
+template <typename TM>
+__global__ void split16_kernel(const float* __restrict__ w, TM* __restrict__ hi, TM* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const TM h = to_tm<TM>(v);
+  hi[i] = h;
+  lo[i] = to_tm<TM>(v - to_f32<TM>(h));
+}
+
 // dynamic shared memory layout (floats):
 //   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1)] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
 //   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
-template <typename T>
+// MMA: the head GEMM runs on mma.sync (head_gemm_mma) - shared memory then holds the pooled features as two 16-bit
+// planes a_hi / a_lo [HEAD_SCHUNK][F + 8] instead of pooled[F][HEAD_SCHUNK] + part[]; w_hi / w_lo are [C][F].
+// SCH = samples per pass (HEAD_SCHUNK; the MMA form can take 64 = four 16-row tiles per weight fragment, see the
+// launcher for why that is not the default).
+template <typename T, bool MMA, int SCH>
 __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
     const float* __restrict__ wt, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
-    float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate) {
+    float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate,
+    const T* __restrict__ w_hi, const T* __restrict__ w_lo) {
   extern __shared__ float sm[];
   float* pooled = sm;
-  float* part = pooled + (size_t)HEAD_SCHUNK * F;
-  float* logits = part + HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1);
-  float* acc_p = logits + (size_t)HEAD_SCHUNK * C;
+  float* part = pooled + (size_t)SCH * F;
+  float* logits = part + HEAD_THREADS * SCH * (C > 32 ? 4 : 1);
+  T* a_hi = reinterpret_cast<T*>(sm);
+  T* a_lo = a_hi + (size_t)SCH * (F + 8);
+  if constexpr (MMA) logits = reinterpret_cast<float*>(a_lo + (size_t)SCH * (F + 8));
+  float* acc_p = logits + (size_t)SCH * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
   float* smax = red + HEAD_WARPS;
-  float* sinv = smax + HEAD_SCHUNK;
+  float* sinv = smax + SCH;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,8 +255,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   }
   float plogp_acc = 0.f;  // meaningful on lane 0 of each warp
 
-  for (int s0 = 0; s0 < S_local; s0 += HEAD_SCHUNK) {
-    const int ns = min(HEAD_SCHUNK, S_local - s0);
+  for (int s0 = 0; s0 < S_local; s0 += SCH) {
+    const int ns = min(SCH, S_local - s0);
     __syncthreads();
     // ---- phase 1: pooled + masked feature vectors for ns samples -----------------------------
     if (F % 8 == 0) {
@@ -170,11 +281,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
                                : philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, ((uint64_t)b * F + f0) >> 3, dp.thr);
           fac *= dp.scale;
         }
+        Vec8h<T> vh, vl;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = ((k8 >> j) & 1u) ? a[j] * fac : 0.f;
           if (dp.kind == BNN_DROP_MASKSEMBLES) v *= drop_factor(dp, (uint32_t)s, 0, 0, f0 + j);
-          pooled[(f0 + j) * HEAD_SCHUNK + sl] = v;
+          if constexpr (MMA) {
+            vh.v[j] = to_tm<T>(v);
+            vl.v[j] = to_tm<T>(v - to_f32<T>(vh.v[j]));
+          } else {
+            pooled[(f0 + j) * SCH + sl] = v;
+          }
+        }
+        if constexpr (MMA) {
+          *reinterpret_cast<Vec8h<T>*>(a_hi + (size_t)sl * (F + 8) + f0) = vh;
+          *reinterpret_cast<Vec8h<T>*>(a_lo + (size_t)sl * (F + 8) + f0) = vl;
         }
       }
     } else {
@@ -187,12 +308,14 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
         a *= inv_hw;
         if (dp.kind != BNN_DROP_NONE)
           a *= drop_factor(dp, (uint32_t)s, (uint64_t)b * F + f, (uint64_t)b * F + f, f);
-        pooled[f * HEAD_SCHUNK + sl] = a;
+        pooled[f * SCH + sl] = a;
       }
     }
     __syncthreads();
     // ---- phase 2: logits[ns x C] = pooled[ns x F] * W^T[F x C] + bias as a register-tiled small GEMM ----
-    if (C > 32)
+    if constexpr (MMA)
+      head_gemm_mma<T, SCH / 16>(a_hi, a_lo, logits, w_hi, w_lo, bias, F, C, ns, tid);
+    else if (C > 32)
       head_gemm<4>(pooled, part, logits, wt, bias, F, C, ns, tid);
     else
       head_gemm<1>(pooled, part, logits, wt, bias, F, C, ns, tid);
@@ -485,11 +608,50 @@ using namespace bnn;
 
 extern "C" {
 
+int bnn_split16(const float* w, void* hi, void* lo, int64_t n, int dtype, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(w && hi && lo && n >= 0, "bnn_split16: bad arguments");
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_split16: dtype must be float16 or bfloat16");
+  if (n == 0) return BNN_OK;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == BNN_F16)
+    split16_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)hi, (__half*)lo, n);
+  else
+    split16_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
+}
+
+static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                         const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                         float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
+                         const void* w_lo);
+
 int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                   const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                   float* sum_plogp, float* logits_out, int accumulate, void* stream) {
+  BNN_REQUIRE(wt, "bnn_exit_head: null pointer");
+  return exit_head_run(feat, dtype, feat_has_samples, B, S_local, HW, F, C, wt, bias, drop, sum_p, sum_logit, sum_plogp,
+                       logits_out, accumulate, stream, nullptr, nullptr);
+}
+
+int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                      const void* w_hi, const void* w_lo, const float* bias, const bnn_drop_desc* drop, float* sum_p,
+                      float* sum_logit, float* sum_plogp, float* logits_out, int accumulate, void* stream) {
+  BNN_REQUIRE(w_hi && w_lo, "bnn_exit_head_mma: null pointer");
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_exit_head_mma: features must be float16 or bfloat16");
+  BNN_REQUIRE(F % 16 == 0, "bnn_exit_head_mma: F=%d must be a multiple of 16", F);
+  return exit_head_run(feat, dtype, feat_has_samples, B, S_local, HW, F, C, nullptr, bias, drop, sum_p, sum_logit,
+                       sum_plogp, logits_out, accumulate, stream, w_hi, w_lo);
+}
+
+static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                         const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                         float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
+                         const void* w_lo) {
   if (int rc = check_device()) return rc;
-  BNN_REQUIRE(feat && wt && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
+  const bool mma = w_hi != nullptr;
+  BNN_REQUIRE(feat && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
   BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && C > 0, "bnn_exit_head: bad geometry");
   if (drop && drop->kind != BNN_DROP_NONE) {
     BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
@@ -498,27 +660,44 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
                 "bnn_exit_head: Masksembles site without a mask table");
   }
   if (B == 0) return BNN_OK;
-  const size_t smem = ((size_t)HEAD_SCHUNK * F + (size_t)HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1) +
-                       (size_t)HEAD_SCHUNK * C +
-                       2 * (size_t)C + HEAD_WARPS + 2 * HEAD_SCHUNK) *
-                      sizeof(float);
+  auto smem_for = [&](int sch) {
+    const size_t tail = ((size_t)sch * C + 2 * (size_t)C + HEAD_WARPS + 2 * (size_t)sch) * sizeof(float);
+    return mma ? 2 * (size_t)sch * (F + 8) * 2 + tail
+               : ((size_t)sch * F + (size_t)HEAD_THREADS * sch * (C > 32 ? 4 : 1)) * sizeof(float) + tail;
+  };
+  // MMA form: 16 samples per pass.  64 per pass (four row tiles per weight fragment, 4x fewer weight re-reads from L2)
+  // is available as an experiment (BNN_HEAD_SCH=64) but measured SLOWER at C4 (1.46 vs 1.22 ms for the five heads):
+  // its 160 KB of shared memory leave one CTA per SM and nothing to hide the feature / weight load latency behind.
+  const char* sch_env = getenv("BNN_HEAD_SCH");
+  const int sch = (mma && sch_env && atoi(sch_env) == 64 && S_local > HEAD_SCHUNK && smem_for(64) <= 160 * 1024)
+                      ? 64 : HEAD_SCHUNK;
+  const size_t smem = smem_for(sch);
   BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);
   DropParams dp = make_drop_params(drop, F);
   dp.batch = B;
   cudaStream_t st = (cudaStream_t)stream;
-#define BNN_HEAD_LAUNCH(T)                                                                                         \
-  do {                                                                                                             \
-    BNN_CUDA_OK(cudaFuncSetAttribute(exit_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    exit_head_kernel<T><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, C, wt, \
-                                                       bias, dp, sum_p, sum_logit, sum_plogp, logits_out,          \
-                                                       accumulate);                                                \
+#define BNN_HEAD_LAUNCH(T, M, SCH)                                                                                  \
+  do {                                                                                                              \
+    BNN_CUDA_OK(cudaFuncSetAttribute(exit_head_kernel<T, M, SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem));                                                                   \
+    exit_head_kernel<T, M, SCH><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, \
+                                                               C, wt, bias, dp, sum_p, sum_logit, sum_plogp,        \
+                                                               logits_out, accumulate, (const T*)w_hi,              \
+                                                               (const T*)w_lo);                                     \
+  } while (0)
+#define BNN_HEAD_LAUNCH16(T)                                            \
+  do {                                                                  \
+    if (!mma) BNN_HEAD_LAUNCH(T, false, HEAD_SCHUNK);                   \
+    else if (sch == 64) BNN_HEAD_LAUNCH(T, true, 64);                   \
+    else BNN_HEAD_LAUNCH(T, true, HEAD_SCHUNK);                         \
   } while (0)
   switch (dtype) {
-    case BNN_F32: BNN_HEAD_LAUNCH(float); break;
-    case BNN_F16: BNN_HEAD_LAUNCH(__half); break;
-    case BNN_BF16: BNN_HEAD_LAUNCH(__nv_bfloat16); break;
+    case BNN_F32: BNN_HEAD_LAUNCH(float, false, HEAD_SCHUNK); break;
+    case BNN_F16: BNN_HEAD_LAUNCH16(__half); break;
+    case BNN_BF16: BNN_HEAD_LAUNCH16(__nv_bfloat16); break;
     default: set_error("unknown dtype code %d", dtype); return BNN_E_ARG;
   }
+#undef BNN_HEAD_LAUNCH16
 #undef BNN_HEAD_LAUNCH
   BNN_LAUNCH_OK();
   return BNN_OK;

@@ -315,6 +315,18 @@ class Engine:
             elif op.kind == "head":
                 op.d_w = op.weight.t().contiguous().to(dev, torch.float32)      # [F][C] for the head kernel
                 op.d_b = op.bias.to(dev, torch.float32)
+                # wide heads on 16-bit features: the Linear runs on mma.sync with hi/lo-split operands
+                C_, F_ = op.weight.shape
+                op.head_mma = (self.dtype_name != "fp32" and C_ > 32 and F_ % 16 == 0 and
+                               os.environ.get("BNN_HEAD_MMA", "1") != "0")
+                if op.head_mma:
+                    w32 = op.weight.contiguous().to(dev, torch.float32)             # [C][F], the nn.Linear layout
+                    op.d_w_hi = torch.empty((C_, F_), dtype=self.tdtype, device=dev)
+                    op.d_w_lo = torch.empty((C_, F_), dtype=self.tdtype, device=dev)
+                    with torch.cuda.device(dev):
+                        _lib.check(self.lib.bnn_split16(_ptr(w32), _ptr(op.d_w_hi), _ptr(op.d_w_lo), C_ * F_, self.dcode,
+                                                        ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                        torch.cuda.current_stream(dev).synchronize()
             if op.site is not None and op.site.kind == "mask":
                 op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()
 
@@ -624,10 +636,17 @@ class Engine:
                 hw = op.src.H * op.src.W
                 nbytes = (S_local if op.src.stoch else 1) * B * hw * op.src.C * es + op.d_w.numel() * 4
                 flops = 2 * S_local * B * op.src.C * g.n_classes
-                self._launch("exit_head", op.name, flops, nbytes, lambda: lib.bnn_exit_head(
-                    _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
-                    _ptr(op.d_w), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
-                    _ptr(lo_e), int(accumulate), stream))
+                if op.head_mma:
+                    call = lambda: lib.bnn_exit_head_mma(
+                        _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
+                        _ptr(op.d_w_hi), _ptr(op.d_w_lo), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]),
+                        _ptr(sum_pl[e]), _ptr(lo_e), int(accumulate), stream)
+                else:
+                    call = lambda: lib.bnn_exit_head(
+                        _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
+                        _ptr(op.d_w), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
+                        _ptr(lo_e), int(accumulate), stream)
+                self._launch("exit_head", op.name, flops, nbytes, call)
 
     def profile_step(self, x, S_local, seed=0x5EED):
         """Device time of every launch of one step (CUDA events on the launching stream).

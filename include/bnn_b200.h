@@ -164,6 +164,17 @@ int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int 
                   const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                   float* sum_plogp, float* logits_out, int accumulate, void* stream);
 
+/* Same exit head with the Linear on the warp-level tensor cores (mma.sync m16n8k16; 16 samples x C classes per image is
+ * far below a tcgen05 tile) for wide heads (C = 100: the FFMA form is 14 % of the C4 step).  w_hi / w_lo: the
+ * nn.Linear weight [C][F] split by bnn_split16 into a 16-bit high part and a 16-bit remainder, in the feature dtype
+ * (float16 / bfloat16); the pooled features are split the same way and three products are accumulated in float32, so
+ * the logits stay within ~2^-20 relative of the float32 form.  F % 16 == 0. */
+int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                      const void* w_hi, const void* w_lo, const float* bias, const bnn_drop_desc* drop, float* sum_p,
+                      float* sum_logit, float* sum_plogp, float* logits_out, int accumulate, void* stream);
+/* hi[i] = round16(w[i]), lo[i] = round16(w[i] - hi[i]) in `dtype` (1 = float16, 2 = bfloat16). */
+int bnn_split16(const float* w, void* hi, void* lo, int64_t n, int dtype, void* stream);
+
 /* ---- statistics finaliser ----
  * From the (all-reduced) sums over S_total samples: predictive mean, mean logits, cumulative exit ensembles
  * (results_analyzer.py:247-248, :260-269), entropy of the mean with the reference's 1e-8 epsilon

@@ -509,3 +509,44 @@ def test_full_analysis_confidence_exiting_flops_and_kde_ece(lib):
     want = stats.kde_triweight_exact(stats.mirror_1d(sel, 0.0, 1.0), bw, grid) * 2
     want[(grid <= 0) | (grid >= 1)] = 0
     assert np.abs(out.cpu().numpy() - want).max() < 1e-9 * max(1.0, want.max())
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("C,F_,HW,kind,S", [(100, 512, 4, 1, 19), (100, 512, 1, 3, 4), (37, 64, 16, 0, 33), (1000, 256, 1, 2, 16)])
+def test_exit_head_mma_matches_ffma_head(lib, dt, C, F_, HW, kind, S):
+    """bnn_exit_head_mma (mma.sync, hi/lo-split operands) == bnn_exit_head (fp32 FFMA) on the same 16-bit features:
+    the split keeps the tensor-core logits within 1e-5 relative of the float32 form."""
+    tdt, code = TORCH_DT[dt]
+    B, s0, p, seed, sid = 5, 3, 0.25, 0x99, 2
+    g = torch.Generator().manual_seed(C + S)
+    feat = (torch.randn(S * B, HW, F_, generator=g).abs() * 3).to(tdt).cuda()
+    w = (torch.randn(C, F_, generator=g) / np.sqrt(F_) * 3).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    masks = (torch.rand(4, F_, generator=g) > 0.5).float().cuda()
+    dd = drop_desc(kind, p, seed, sid, s0, B, masks if kind == 3 else None, cnt0=1)
+    w_hi, w_lo = torch.empty(C, F_, dtype=tdt, device="cuda"), torch.empty(C, F_, dtype=tdt, device="cuda")
+    assert lib.bnn_split16(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C * F_, code, stream()) == 0
+    assert (w_hi.float() + w_lo.float() - w).abs().max().item() <= (2e-6 if dt == "fp16" else 2e-4) * w.abs().max().item()
+    outs = {}
+    for name in ("ffma", "mma"):
+        o = dict(sp=torch.zeros(B, C).cuda(), sl=torch.zeros(B, C).cuda(), spl=torch.zeros(B).cuda(), lo=torch.zeros(S, B, C).cuda())
+        if name == "ffma":
+            wt = w.t().contiguous()
+            rc = lib.bnn_exit_head(feat.data_ptr(), code, 1, B, S, HW, F_, C, wt.data_ptr(), bias.data_ptr(), ctypes.byref(dd),
+                                   o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(), o["lo"].data_ptr(), 0, stream())
+        else:
+            rc = lib.bnn_exit_head_mma(feat.data_ptr(), code, 1, B, S, HW, F_, C, w_hi.data_ptr(), w_lo.data_ptr(),
+                                       bias.data_ptr(), ctypes.byref(dd), o["sp"].data_ptr(), o["sl"].data_ptr(),
+                                       o["spl"].data_ptr(), o["lo"].data_ptr(), 0, stream())
+        assert rc == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        outs[name] = o
+    scale = max(1.0, outs["ffma"]["lo"].abs().max().item())
+    e_lo = (outs["mma"]["lo"] - outs["ffma"]["lo"]).abs().max().item()
+    e_p = (outs["mma"]["sp"] - outs["ffma"]["sp"]).abs().max().item()
+    report(test="exit_head_mma", dtype=dt, C=C, F=F_, err_logits=e_lo, err_sum_p=e_p, scale=scale)
+    tol = 1e-5 if dt == "fp16" else 3e-4          # bf16 hi+lo carries 16 mantissa bits
+    assert e_lo <= tol * scale and e_p <= tol * S
+    assert lib.bnn_exit_head_mma(feat.data_ptr(), code, 1, B, S, HW, 24, C, w_hi.data_ptr(), w_lo.data_ptr(), bias.data_ptr(),
+                                 ctypes.byref(dd), o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(), None, 0,
+                                 stream()) == -1                     # F % 16 != 0
