@@ -75,6 +75,10 @@ struct Params {
   // r = (wsel_cnt0 + s) % wsel_n.  wsel_n == 0: one weight set.
   int last_ksteps;
   int wsel_n, wsel_cnt0, wsel_sample_px;
+  // fused 1x1 stride-2 shortcut (bnn_conv2d_tc_shortcut): `cblocks2` extra k-blocks whose activation tile comes from a
+  // SECOND tensor (tmap_a2: the block input x, centre tap of its stride-2 parity view) and whose weights are the
+  // columns [taps * Cin, taps * Cin + 64 * cblocks2) of the K-concatenated weight matrix
+  int cblocks2;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
   const float* bias;
   const void* res;
@@ -304,7 +308,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // only the kept channels of each sample's mask (DropParams::compact_pos), 2 bytes at a time.
 template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
 __global__ void __launch_bounds__(num_threads(EW), 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_a2, const Params p) {
   constexpr bool MC2 = PAIR == 1;
   constexpr bool CG2 = PAIR == 2;
   constexpr bool PAIRED = PAIR != 0;
@@ -427,6 +432,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+        // fused shortcut: the 1x1 stride-2 convolution of the block input rides in the same accumulator
+        for (int cb = 0; cb < p.cblocks2; ++cb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (CG2) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BK, 0, 0,
+                              oh0[mt], img0[mt]);
+            tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BK,
+                            wrow + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BK, 0, 0, oh0[mt],
+                          img0[mt]);
+            if constexpr (MC2)
+              tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
+                             p.taps * p.Cin + cb * BK, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
+            else
+              tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BK, wrow);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -439,7 +472,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t acc_phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int n_tile_mma = tile % p.n_tiles_n;
-        const int tile_kb = ((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb;
+        const int tile_kb = ((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb + p.cblocks2;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -824,7 +857,7 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
 }
 
 template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st) {
   static bool configured = false;
   constexpr int smem = smem_bytes_pair(BN, MT, PAIR);
   constexpr bool MC2 = PAIR != 0;
@@ -849,11 +882,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, Params p, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, p));
   } else {
     p.num_tiles = m_tiles * p.n_tiles_n;
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, num_threads(EW), smem, st>>>(ta, tb, p);
+    kern<<<grid, num_threads(EW), smem, st>>>(ta, tb, ta2, p);
   }
   BNN_LAUNCH_OK();
   return BNN_OK;
@@ -872,10 +905,15 @@ struct GatherSel {
   int x_has_samples;          // 0: x holds `batch` images shared by all samples
 };
 
+struct Shortcut {
+  const void* x2;   // [N][H2][W2][Cin2]: the input of the residual block, H2 = 2 * OH, W2 = 2 * OW
+  int H2, W2, Cin2;
+};
+
 static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                        int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
-                       const GatherSel* gsel = nullptr) {
+                       const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
@@ -908,6 +946,12 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                 "%s: batch * OH * OW = %lld must be a multiple of %d (one weight set per MMA tile pair)", who,
                 (long long)gsel->batch * OH * OW, 2 * tc::BM);
   }
+  if (sc) {
+    BNN_REQUIRE(sc->x2 != nullptr && groups == 1 && gsel == nullptr, "%s: a fused shortcut needs one dense output", who);
+    BNN_REQUIRE(sc->Cin2 > 0 && sc->Cin2 % 64 == 0 && sc->H2 == 2 * OH && sc->W2 == 2 * OW,
+                "%s: shortcut input %dx%dx%d does not match a 1x1 stride-2 convolution onto %dx%d", who, sc->H2, sc->W2,
+                sc->Cin2, OH, OW);
+  }
   const bool compact_out = drop && drop->kind == BNN_DROP_MASKSEMBLES && drop->compact_pos != nullptr;
   if (compact_out) {
     BNN_REQUIRE(drop->compact_c > 0 && drop->compact_c % 8 == 0 && drop->compact_c <= Cout,
@@ -922,7 +966,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const int th = OH < tc::BM / tw ? OH : tc::BM / tw;
   const int tn = tc::BM / (tw * th);
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2;
   const cuuint64_t eb = 2;
   const int N_in = (gsel && !gsel->x_has_samples) ? gsel->batch : N;     // images held by x
   if (stride == 1) {
@@ -963,8 +1007,18 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const bool cg2_narrow_box = mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
+  if (sc) {
+    const int C2 = sc->Cin2, H2 = sc->H2, W2 = sc->W2;
+    const cuuint64_t dims[5] = {(cuuint64_t)2 * C2, (cuuint64_t)W2 / 2, 2, (cuuint64_t)H2 / 2, (cuuint64_t)N};
+    const cuuint64_t strides[4] = {(cuuint64_t)2 * C2 * eb, (cuuint64_t)W2 * C2 * eb, (cuuint64_t)2 * W2 * C2 * eb,
+                                   (cuuint64_t)H2 * W2 * C2 * eb};
+    const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
+    if (int rc = tc::encode_map(&ta2, dtype, 5, sc->x2, dims, strides, box)) return rc;
+  } else {
+    ta2 = ta;
+  }
   {
-    const int K = ksize * ksize * Cin;
+    const int K = ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
     const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
@@ -986,6 +1040,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     p.wsel_sample_px = gsel->batch * OH * OW;
     p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
   }
+  p.cblocks2 = sc ? sc->Cin2 / tc::BK : 0;
   p.stride = stride;
   p.pad = pad;
   p.OH = OH;
@@ -1004,8 +1059,8 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // row-tiles per CTA tile: two 128-row accumulators share every weight k-block when TMEM allows (BN <= 128)
 #define BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_)                                          \
   case BN_:                                                                                              \
-    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __half>(ta, tb, p, st)   \
-                            : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __nv_bfloat16>(ta, tb, p, st);
+    return dtype == BNN_F16 ? tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __half>(ta, tb, ta2, p, st)   \
+                            : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __nv_bfloat16>(ta, tb, ta2, p, st);
 #define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_) BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, 8)
 #define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_) BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, false)
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
@@ -1079,4 +1134,13 @@ extern "C" int bnn_conv2d_tc_gathered(const void* x, const void* w, const float*
   GatherSel g{n_masks, (int)(((int64_t)cnt0 + (int64_t)sample0) % n_masks), batch, x_has_samples};
   return conv_tc_run("bnn_conv2d_tc_gathered", x, w, bias, nullptr, y, n_groups, relu_mask, center_mask, dtype, N, H, W, Kc,
                      cout_per_group, ksize, stride, nullptr, stream, &g);
+}
+
+extern "C" int bnn_conv2d_tc_shortcut(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype,
+                                      int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
+                                      const bnn_drop_desc* drop, const void* x2, int H2, int W2, int Cin2, void* stream) {
+  void* ys[1] = {y};
+  Shortcut sc{x2, H2, W2, Cin2};
+  return conv_tc_run("bnn_conv2d_tc_shortcut", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
+                     stride, drop, stream, nullptr, &sc);
 }

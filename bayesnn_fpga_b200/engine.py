@@ -177,6 +177,31 @@ class Graph:
             out.append(op)
         self.ops = out
 
+    def fuse_shortcuts(self, eligible):
+        """A residual block's 1x1 stride-2 projection shortcut (BasicBlock.forward resnet18.py:41-46) becomes extra
+        K of the convolution that adds it: conv2(h) + ds(x) is ONE GEMM over [patches(h) | x at the stride-2 centre
+        tap] with the weights concatenated along K.  The shortcut tensor is then never written nor re-read as a
+        residual, and the sibling-group launch in front loses its one-k-block (epilogue-bound) tiles."""
+        producer = {op.dst.id: op for op in self.ops if op.dst is not None}
+        for op in list(self.ops):
+            if op.kind != "conv" or op.res is None:
+                continue
+            d = producer.get(op.res.id)
+            if d is None or d.kind != "conv" or d.ksize != (1, 1) or d.stride != 2 or d.pad != 0 or d.relu or \
+                    d.site is not None or d.res is not None or getattr(d, "sc", None) is not None:
+                continue
+            readers = [o for o in self.ops if o.src is d.dst or o.res is d.dst]
+            src_prod = producer.get(d.src.id)
+            masked_src = src_prod is not None and src_prod.site is not None and src_prod.site.kind == "mask"
+            if readers != [op] or d.src.stoch != op.src.stoch or masked_src or not eligible(op) or not eligible(d) or \
+                    d.src.H != 2 * op.dst.H or d.src.W != 2 * op.dst.W or op.stride != 1:
+                continue
+            op.sc = {"src": d.src, "weight": d.weight[:, :, 0, 0].contiguous(), "name": d.name}
+            op.bias = op.bias + d.bias
+            op.res = None
+            op.name = op.name + "+" + d.name.split(".")[-1]
+            self.ops.remove(d)
+
     def fuse_sibling_convs(self, eligible):
         """Group stride-2 convolutions that read the same tensor (first conv of the next stage, its 1x1 shortcut,
         first conv of the exit branch) into one 'convg' op: the input is fetched from HBM once.  A 1x1 stride-2
@@ -218,6 +243,8 @@ class Graph:
         for op in flat:
             if op.kind == "conv":
                 m = op.dst.H * op.dst.W * op.dst.C * op.src.C * op.ksize[0] * op.ksize[1]
+                if getattr(op, "sc", None) is not None:
+                    m += op.dst.H * op.dst.W * op.dst.C * op.sc["src"].C
             elif op.kind == "head":
                 m = op.weight.shape[0] * op.weight.shape[1]
                 if op.site is not None or op.src.stoch:
@@ -273,6 +300,8 @@ class Engine:
         self.dcode, self.tdtype = DTYPES[dtype]
         # BNN_DISABLE_TC=1 routes the 16-bit path through the CUDA-core kernel too (debugging aid)
         self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
+        if self.use_tc and fuse and os.environ.get("BNN_SHORTCUT_FUSION", "1") != "0":
+            graph.fuse_shortcuts(self._tc_eligible)
         if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
             graph.fuse_sibling_convs(self._tc_eligible)
         self.sample_chunk = int(os.environ.get("BNN_SAMPLE_CHUNK", "0")) if sample_chunk is None else int(sample_chunk)
@@ -310,6 +339,8 @@ class Engine:
             elif op.kind == "conv":
                 w = op.weight.permute(0, 2, 3, 1).contiguous()       # [Cout][KH][KW][Cin]
                 op.use_tc = self._tc_eligible(op)
+                if getattr(op, "sc", None) is not None:              # K-concatenated: 3x3 weights | shortcut weights
+                    w = torch.cat([w.reshape(w.shape[0], -1), op.sc["weight"]], dim=1).contiguous()
                 op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
                 op.d_b = op.bias.to(dev, torch.float32)
             elif op.kind == "head":
@@ -419,6 +450,8 @@ class Engine:
         live = {g.input.id}
         for op in g.ops:
             live.update(t.id for t in (op.src, op.dst, op.res) + tuple(getattr(op, "dsts", ())) if t is not None)
+            if getattr(op, "sc", None) is not None:
+                live.add(op.sc["src"].id)
         for t in g.tensors:
             if t.id not in live or gmode.get(t.id) == "weights":
                 continue                      # e.g. the un-masked output of a conv with a fused site
@@ -596,7 +629,15 @@ class Engine:
                 flops = 2 * out_px * op.dst.C * op.src.C * kh * kw
                 nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * op.dst.C * (2 if res is not None else 1)) * es \
                     + op.d_w.numel() * op.d_w.element_size()
-                if op.use_tc:
+                sc = getattr(op, "sc", None)
+                if sc is not None:
+                    flops += 2 * out_px * op.dst.C * sc["src"].C
+                    nbytes += n_img * sc["src"].H * sc["src"].W * sc["src"].C * es
+                    call = lambda: lib.bnn_conv2d_tc_shortcut(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd),
+                        _ptr(acts[sc["src"].id]), sc["src"].H, sc["src"].W, sc["src"].C, stream)
+                elif op.use_tc:
                     call = lambda: lib.bnn_conv2d_tc(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
                         op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd), stream)

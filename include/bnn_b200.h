@@ -121,6 +121,15 @@ int bnn_conv2d_tc_grouped(const void* x, const void* w, const float* bias, void*
                           uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                           int cout_per_group, int ksize, int stride, void* stream);
 
+/* A residual block's second convolution with its 1x1 stride-2 projection shortcut fused in (BasicBlock.forward,
+ * resnet18.py:41-46: `out = bn2(conv2(out)); out += downsample(x); relu`): the shortcut's input x2 [N][H2][W2][Cin2]
+ * (H2 = 2*OH, W2 = 2*OW) contributes Cin2/64 extra k-blocks to the SAME accumulator, so the shortcut tensor is never
+ * written or re-read as a residual.  w is [Cout][k*k*Cin + Cin2] (the 3x3 weights followed by the folded shortcut
+ * weights), bias the sum of both folded shifts.  Everything else as bnn_conv2d_tc. */
+int bnn_conv2d_tc_shortcut(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype, int N,
+                           int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
+                           const void* x2, int H2, int W2, int Cin2, void* stream);
+
 /* Masksembles "gathered" convolution (north star (3): structured channel masks become smaller GEMMs and dropped
  * channels are never read from HBM).  Same as bnn_conv2d_tc_grouped, but
  *   x  is [N][H][W][Kc]: the compact output of a Masksembles2D site (bnn_drop_desc.compact_pos), Kc % 16 == 0;

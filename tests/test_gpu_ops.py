@@ -550,3 +550,44 @@ def test_exit_head_mma_matches_ffma_head(lib, dt, C, F_, HW, kind, S):
     assert lib.bnn_exit_head_mma(feat.data_ptr(), code, 1, B, S, HW, 24, C, w_hi.data_ptr(), w_lo.data_ptr(), bias.data_ptr(),
                                  ctypes.byref(dd), o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(), None, 0,
                                  stream()) == -1                     # F % 16 != 0
+
+
+@pytest.mark.parametrize("Cin2,C,H,N,pair", [(64, 128, 16, 6, "0"), (128, 256, 8, 20, "0"), (256, 512, 4, 70, "0"),
+                                              (128, 256, 8, 20, "cg2"), (128, 256, 8, 21, "mc2")])
+@pytest.mark.parametrize("drop_kind", [0, 1])
+def test_conv_tc_fused_shortcut(lib, Cin2, C, H, N, pair, drop_kind, monkeypatch):
+    """conv3x3(h) + conv1x1_stride2(x2) + bias -> ReLU [-> dropout] as ONE GEMM with the shortcut as extra K
+    (bnn_conv2d_tc_shortcut) vs float64 torch (BasicBlock.forward resnet18.py:41-46 with the BatchNorms folded)."""
+    if pair != "0":
+        monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+        monkeypatch.setenv("BNN_TC_CG2", "1" if pair == "cg2" else "0")
+    g = torch.Generator().manual_seed(Cin2 + N)
+    h = torch.randn(N, C, H, H, generator=g).half()
+    x2 = torch.randn(N, Cin2, 2 * H, 2 * H, generator=g).half()
+    w = (torch.randn(C, C, 3, 3, generator=g) / np.sqrt(9 * C)).half()
+    wd = (torch.randn(C, Cin2, generator=g) / np.sqrt(Cin2)).half()
+    b = torch.randn(C, generator=g)
+    want = (F.conv2d(h.double(), w.double(), None, 1, 1) + F.conv2d(x2.double(), wd.double()[:, :, None, None], None, 2, 0)
+            + b.double().view(1, -1, 1, 1)).relu()
+    B, S = (N // 2, 2) if N % 2 == 0 else (N, 1)
+    dd = drop_desc(drop_kind, 0.5, 0x77, 4, 5, B)
+    if drop_kind == 1:
+        for s_ in range(S):
+            keep = torch.from_numpy(philox.keep_mask(0x77, 4, 5 + s_, (B, C, H, H), 0.5))
+            want[s_ * B:(s_ + 1) * B] *= keep * 2.0
+    d_h = h.permute(0, 2, 3, 1).contiguous().cuda()
+    d_x2 = x2.permute(0, 2, 3, 1).contiguous().cuda()
+    d_w = torch.cat([w.permute(0, 2, 3, 1).reshape(C, -1), wd], dim=1).contiguous().cuda()
+    d_b = b.cuda()
+    d_y = torch.full((N, H, H, C), float("nan"), dtype=torch.float16, device="cuda")
+    rc = lib.bnn_conv2d_tc_shortcut(d_h.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), None, d_y.data_ptr(), 1, N, H, H, C, C, 3, 1,
+                                    1, ctypes.byref(dd), d_x2.data_ptr(), 2 * H, 2 * H, Cin2, stream())
+    assert rc == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    got = d_y.cpu().float().permute(0, 3, 1, 2)
+    err = (got.double() - want).abs().max().item()
+    report(test="conv_tc_shortcut", Cin2=Cin2, C=C, pair=pair, drop=drop_kind, err=err, scale=want.abs().max().item())
+    assert err <= 2e-3 * max(1.0, want.abs().max().item())
+    # geometry that is not a stride-2 projection is rejected
+    assert lib.bnn_conv2d_tc_shortcut(d_h.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), None, d_y.data_ptr(), 1, N, H, H, C, C, 3,
+                                      1, 1, ctypes.byref(dd), d_x2.data_ptr(), H, H, Cin2, stream()) == -1
