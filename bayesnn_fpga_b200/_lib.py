@@ -66,6 +66,7 @@ _SIGS = {
     "bnn_philox_keep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64,
                                        ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
     "bnn_nchw_to_nhwc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "bnn_nchw_to_nhwc_pitch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "bnn_conv2d_simt": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 11 +
                         [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_conv2d_tc": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +

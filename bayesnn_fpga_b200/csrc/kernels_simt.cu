@@ -82,15 +82,17 @@ __global__ void philox_keep_kernel(uint8_t* out, int64_t count, uint32_t thr, in
 // NCHW fp32 -> NHWC T
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW, int64_t total) {
-  // one thread per output element; reads are strided by HW but the inputs are small (3 x 32 x 32 images)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int C, int HW, int64_t total,
+                                    int pitch) {
+  // one thread per output element; reads are strided by HW but the inputs are small (3 x 32 x 32 images).
+  // pitch >= C: channels per pixel of y (the channels past C are left untouched: the caller zero-fills them once)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
   const int64_t t = i / C;
   const int hw = (int)(t % HW);
   const int64_t n = t / HW;
-  y[i] = from_f32<T>(x[(n * C + c) * HW + hw]);
+  y[t * pitch + c] = from_f32<T>(x[(n * C + c) * HW + hw]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -413,14 +415,18 @@ int bnn_philox_keep(uint8_t* out, int64_t count, float p, uint64_t seed, uint32_
 }
 
 int bnn_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream) {
+  return bnn_nchw_to_nhwc_pitch(x, y, dtype, N, C, H, W, C, stream);
+}
+
+int bnn_nchw_to_nhwc_pitch(const float* x, void* y, int dtype, int N, int C, int H, int W, int pitch, void* stream) {
   if (int rc = check_device()) return rc;
-  BNN_REQUIRE(x && y && N >= 0 && C > 0 && H > 0 && W > 0, "bnn_nchw_to_nhwc: bad arguments");
+  BNN_REQUIRE(x && y && N >= 0 && C > 0 && H > 0 && W > 0 && pitch >= C, "bnn_nchw_to_nhwc: bad arguments");
   const int64_t total = (int64_t)N * C * H * W;
   if (total == 0) return BNN_OK;
   return dispatch_dtype(dtype, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
     nchw_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, C, H * W,
-                                                                                             total);
+                                                                                             total, pitch);
     BNN_LAUNCH_OK();
     return BNN_OK;
   });

@@ -300,6 +300,14 @@ class Engine:
         self.dcode, self.tdtype = DTYPES[dtype]
         # BNN_DISABLE_TC=1 routes the 16-bit path through the CUDA-core kernel too (debugging aid)
         self.use_tc = use_tc and dtype != "fp32" and os.environ.get("BNN_DISABLE_TC") != "1"
+        # stem on the tensor cores: the network input (3 channels) is stored with its channels padded to one 64-channel
+        # k-block (zeros) when every layer that reads it is a 3x3 / 1x1 convolution the tcgen05 kernel accepts otherwise
+        self.in_pad = 0
+        if self.use_tc and graph.input.C < 64 and os.environ.get("BNN_STEM_TC", "1") != "0":
+            readers = [o for o in graph.ops if o.src is graph.input or o.res is graph.input]
+            self.in_pad = 64
+            if not readers or not all(o.kind == "conv" and o.res is None and self._tc_eligible(o) for o in readers):
+                self.in_pad = 0
         if self.use_tc and fuse and os.environ.get("BNN_SHORTCUT_FUSION", "1") != "0":
             graph.fuse_shortcuts(self._tc_eligible)
         if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
@@ -323,8 +331,9 @@ class Engine:
         """Same rule as bnn_conv2d_tc (conv_tc.cu): decided at plan time, never a silent run-time fallback."""
         kh, kw = op.ksize
         pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        cin = self.in_pad if (op.src is self.graph.input and self.in_pad) else op.src.C
         return (self.use_tc and kh == kw and ((kh == 3 and op.pad == 1) or (kh == 1 and op.pad == 0))
-                and op.stride in (1, 2) and op.src.C % 64 == 0 and op.dst.C % 64 == 0
+                and op.stride in (1, 2) and cin % 64 == 0 and op.dst.C % 64 == 0
                 and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0))
                 and pow2(op.dst.H) and pow2(op.dst.W) and op.dst.W <= 128)
 
@@ -339,6 +348,8 @@ class Engine:
             elif op.kind == "conv":
                 w = op.weight.permute(0, 2, 3, 1).contiguous()       # [Cout][KH][KW][Cin]
                 op.use_tc = self._tc_eligible(op)
+                if op.use_tc and op.src is self.graph.input and self.in_pad:
+                    w = torch.nn.functional.pad(w, (0, self.in_pad - w.shape[3]))   # zero weights on the padding channels
                 if getattr(op, "sc", None) is not None:              # K-concatenated: 3x3 weights | shortcut weights
                     w = torch.cat([w.reshape(w.shape[0], -1), op.sc["weight"]], dim=1).contiguous()
                 op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
@@ -456,6 +467,9 @@ class Engine:
             if t.id not in live or gmode.get(t.id) == "weights":
                 continue                      # e.g. the un-masked output of a conv with a fused site
             n = (chunk if t.stoch else 1) * B
+            if t is g.input and self.in_pad:
+                acts[t.id] = torch.zeros((B, t.H, t.W, self.in_pad), dtype=self.tdtype, device=dev)
+                continue
             if t.id in compact:
                 # gathered layout; zero-filled once: the padding slots [kept, kc) are never written
                 acts[t.id] = torch.zeros((n, t.H, t.W, self.gather[t.id]["kc"]), dtype=self.tdtype, device=dev)
@@ -567,8 +581,9 @@ class Engine:
             return st
         es = 4 if self.dtype_name == "fp32" else 2
         n_in = B * g.input.C * g.input.H * g.input.W
-        self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc(
-            _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W, stream))
+        self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc_pitch(
+            _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W,
+            self.in_pad or g.input.C, stream))
         # deterministic prefix once; everything behind the first stochastic site in chunks of `chunk` samples so that
         # the activations handed from one layer to the next stay L2-resident (126 MB) instead of round-tripping HBM
         chunk = st["chunk"]
@@ -630,6 +645,7 @@ class Engine:
                 nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * op.dst.C * (2 if res is not None else 1)) * es \
                     + op.d_w.numel() * op.d_w.element_size()
                 sc = getattr(op, "sc", None)
+                cin = self.in_pad if (op.src is g.input and self.in_pad and op.use_tc) else op.src.C
                 if sc is not None:
                     flops += 2 * out_px * op.dst.C * sc["src"].C
                     nbytes += n_img * sc["src"].H * sc["src"].W * sc["src"].C * es
@@ -640,7 +656,7 @@ class Engine:
                 elif op.use_tc:
                     call = lambda: lib.bnn_conv2d_tc(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
-                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd), stream)
+                        op.src.H, op.src.W, cin, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd), stream)
                 else:
                     call = lambda: lib.bnn_conv2d_simt(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,

@@ -64,6 +64,10 @@ int bnn_philox_keep(uint8_t* out, int64_t count, float p, uint64_t seed, uint32_
  * x[N][C][H][W] float32 (what `model(b_x)` receives, results_analyzer.py:144-146) -> y[N][H][W][C] in
  * `dtype`. */
 int bnn_nchw_to_nhwc(const float* x, void* y, int dtype, int N, int C, int H, int W, void* stream);
+/* Same with `pitch` >= C channels per pixel in y (channels [C, pitch) are not written: zero-fill the buffer once).
+ * Lets the 3-channel stem convolution (resnet18.py:303, vgg19.py make_layers) run on the tensor cores with its input
+ * channels padded to one 64-channel k-block. */
+int bnn_nchw_to_nhwc_pitch(const float* x, void* y, int dtype, int N, int C, int H, int W, int pitch, void* stream);
 
 /* ---- convolution + folded BatchNorm + residual + ReLU (+ fused dropout) ----
  * Replaces conv2d -> BatchNorm2d(eval) [-> += residual] [-> ReLU] [-> MCDropout / Masksembles2D] chains:
