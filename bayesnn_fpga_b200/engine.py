@@ -177,7 +177,7 @@ class Graph:
             out.append(op)
         self.ops = out
 
-    def fuse_shortcuts(self, eligible):
+    def fuse_shortcuts(self, eligible, allow_masked=lambda producer: False):
         """A residual block's 1x1 stride-2 projection shortcut (BasicBlock.forward resnet18.py:41-46) becomes extra
         K of the convolution that adds it: conv2(h) + ds(x) is ONE GEMM over [patches(h) | x at the stride-2 centre
         tap] with the weights concatenated along K.  The shortcut tensor is then never written nor re-read as a
@@ -192,7 +192,8 @@ class Graph:
                 continue
             readers = [o for o in self.ops if o.src is d.dst or o.res is d.dst]
             src_prod = producer.get(d.src.id)
-            masked_src = src_prod is not None and src_prod.site is not None and src_prod.site.kind == "mask"
+            masked_src = (src_prod is not None and src_prod.site is not None and src_prod.site.kind == "mask"
+                          and not allow_masked(src_prod))
             if readers != [op] or d.src.stoch != op.src.stoch or masked_src or not eligible(op) or not eligible(d) or \
                     d.src.H != 2 * op.dst.H or d.src.W != 2 * op.dst.W or op.stride != 1:
                 continue
@@ -308,8 +309,14 @@ class Engine:
             self.in_pad = 64
             if not readers or not all(o.kind == "conv" and o.res is None and self._tc_eligible(o) for o in readers):
                 self.in_pad = 0
+        self.gather_mode = int(os.environ.get("BNN_MASK_GATHER", "1")) if mask_gather is None else int(mask_gather)
         if self.use_tc and fuse and os.environ.get("BNN_SHORTCUT_FUSION", "1") != "0":
-            graph.fuse_shortcuts(self._tc_eligible)
+            # a Masksembles-masked block input may feed a fused shortcut only when it is materialised densely: a site
+            # fused into its producer's epilogue (not the boundary site, which moves into per-mask weight sets, and not
+            # the gathered layout of mode 2)
+            graph.fuse_shortcuts(self._tc_eligible,
+                                 allow_masked=lambda prod: self.gather_mode == 0 or
+                                 (prod.kind == "conv" and self.gather_mode < 2))
         if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
             graph.fuse_sibling_convs(self._tc_eligible)
         self.sample_chunk = int(os.environ.get("BNN_SAMPLE_CHUNK", "0")) if sample_chunk is None else int(sample_chunk)
@@ -322,7 +329,6 @@ class Engine:
         # 1 (default): the site at the prefix boundary moves into per-mask weight sets of its consumers;
         # 2: additionally, sites fused into a producer's epilogue store the gathered (kept-channels-only) layout.
         self.gather = {}
-        self.gather_mode = int(os.environ.get("BNN_MASK_GATHER", "1")) if mask_gather is None else int(mask_gather)
         if self.use_tc and self.gather_mode > 0:
             self._plan_gather()
 
@@ -398,6 +404,8 @@ class Engine:
             if mode is None:
                 continue
             readers = [o for o in g.ops if o.src is t or o.res is t]
+            if any(getattr(o, "sc", None) is not None and o.sc["src"] is t for o in g.ops):
+                continue                      # a fused shortcut reads the dense masked tensor
             if not readers or any(o.kind not in ("conv", "convg") or o.res is not None or o.site is not None
                                   or (o.kind == "conv" and not o.use_tc) for o in readers):
                 continue

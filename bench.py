@@ -169,11 +169,11 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-NCU_SUMMARY = "profiles/r01_ncu_conv_tc_full_v2.json"
+NCU_SUMMARY = "profiles/r01_ncu_conv_tc_full_v3.json"
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 19 launches of one C2 step) from
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 20 launches of one C2 step) from
     the committed `ncu --set full` summary (tools/ncu_summary.py), or None."""
     p = os.path.join(ROOT, NCU_SUMMARY)
     if not os.path.exists(p):
@@ -354,7 +354,7 @@ def main():
                 "flops_per_launch": flops / len(tc), "share_of_step": t_tc * 1e3 / sum(o["ms"] for o in prof),
                 "algorithmic_bytes_per_launch": sum(o["bytes"] for o in tc) / len(tc),
                 "traffic": ncu_traffic() if args.workload == "c2" else None,
-                "traffic_source": NCU_SUMMARY + " (ncu --set full --clock-control none over the 19 conv launches of one "
+                "traffic_source": NCU_SUMMARY + " (ncu --set full --clock-control none over the 20 conv launches of one "
                                   "C2 step: mean dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
         if roof["frac"] > 1.0:
             roof["note"] = ("above the SUSTAINED cuBLAS figure (dense random operands at the 1 kW cap): this workload's "

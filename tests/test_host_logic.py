@@ -213,3 +213,35 @@ def test_lowering_rejects_what_it_cannot_express():
         lowering.lower_module(Odd(), (3, 8, 8))
     with pytest.raises(NotImplementedError, match="kernel == stride"):
         lowering.lower_module(nn.Sequential(nn.Conv2d(3, 4, 3), nn.MaxPool2d(3, 2), nn.Flatten(), nn.Linear(4, 2)), (3, 9, 9))
+
+
+def test_shortcut_fusion_pass_preserves_macs_and_removes_projection_convs():
+    """Graph.fuse_shortcuts: every 1x1 stride-2 projection shortcut of the multi-exit ResNet becomes extra K of the
+    convolution that adds it; MACs (results_analyzer.py:632-637 cost model) are unchanged."""
+    from bayesnn_fpga_b200 import resnet18
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", dropout_p=0.5, out_dim=10)
+    g = m._bnn_graph()
+    g.fuse_sites()
+    before = g.macs()
+    n_ops = len(g.ops)
+    g.fuse_shortcuts(lambda op: True)
+    assert g.macs() == before
+    fused = [o for o in g.ops if getattr(o, "sc", None) is not None]
+    assert [o.name for o in fused] == ["layer2.0.0.conv2+downsample", "layer3.0.0.conv2+downsample",
+                                       "layer4.0.conv2+downsample"]
+    assert len(g.ops) == n_ops - 3 and all(o.res is None for o in fused)
+    assert not any("downsample" == o.name.split(".")[-1] for o in g.ops)
+    for o in fused:
+        assert o.sc["src"].H == 2 * o.dst.H and o.sc["weight"].shape == (o.dst.C, o.sc["src"].C)
+    # siblings: with the projections gone each group holds the exit branch's first conv + the next stage's first conv
+    g.fuse_sibling_convs(lambda op: True)
+    groups = [o for o in g.ops if o.kind == "convg"]
+    assert [len(o.members) for o in groups] == [2, 2, 2]
+    # a Masksembles-masked block input keeps its stand-alone projection (the per-mask weight path owns that tensor)
+    np.random.seed(0)
+    mm = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", out_dim=100, mask_type="mask", num_masks=4,
+                                      mask_scale=2.0)
+    gm = mm._bnn_graph()
+    gm.fuse_sites()
+    gm.fuse_shortcuts(lambda op: True)
+    assert not any(getattr(o, "sc", None) is not None for o in gm.ops)
