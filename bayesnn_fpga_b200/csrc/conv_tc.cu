@@ -1004,6 +1004,17 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const bool cg2 = mc2_any && !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
   // (the compact-store epilogue exists for the single-CTA and the cta_group::2 kernels, not for the multicast one)
   const bool mc2 = BN == 256 && mc2_any && !(compact_out && !cg2);
+  // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
+  // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
+  const bool swap_ok =
+      BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
+      !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0) &&
+      getenv("BNN_TC_NOSWAP") == nullptr;
+  // ... optionally (BNN_TC_SWAP_MC2=1) as CTA pairs with the 128 x 64 weight tile fetched half by each CTA and multicast
+  // into both (L2 -> SM bytes per k-block 48 -> 40 KB).  Bit-identical, measured neutral to 3 % slower per layer at C2
+  // (the cluster hand-shake costs what the saved bytes buy), so it is off by default.
+  const bool swap_mc2 = swap_ok && mc2_any && gsel == nullptr && getenv("BNN_TC_SWAP_MC2") &&
+                        atoi(getenv("BNN_TC_SWAP_MC2")) == 1;
   const bool cg2_narrow_box = mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
@@ -1021,7 +1032,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     const int K = ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box || swap_mc2) ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
   }
 
@@ -1063,11 +1074,6 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                             : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __nv_bfloat16>(ta, tb, ta2, p, st);
 #define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_) BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, 8)
 #define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_) BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, false)
-  // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
-  // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
-  const bool swap_ok =
-      cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
-      !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0);
   const bool cg2_narrow = cg2_narrow_box;   // experiment
   if (compact_out && BN == 256) {
     // compact Masksembles stores: dedicated instantiations so that the other kernels keep their code size
@@ -1086,9 +1092,15 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
       BNN_TC_DISPATCH(64, 2, false, 2)
     }
   }
-  if (swap_ok && getenv("BNN_TC_NOSWAP") == nullptr) {
+  if (swap_ok) {
     const bool wide_epi = drop && drop->kind == BNN_DROP_ELEMENT &&
                           !(getenv("BNN_TC_SWAP_EPI") && atoi(getenv("BNN_TC_SWAP_EPI")) == 8);
+    if (swap_mc2) {
+      if (wide_epi) {
+        switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 1, false, 16) }
+      }
+      switch (BN) { BNN_TC_DISPATCH(128, 2, true, 1) }
+    }
     if (wide_epi) {
       switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 0, false, 16) }
     }

@@ -591,3 +591,21 @@ def test_conv_tc_fused_shortcut(lib, Cin2, C, H, N, pair, drop_kind, monkeypatch
     # geometry that is not a stride-2 projection is rejected
     assert lib.bnn_conv2d_tc_shortcut(d_h.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), None, d_y.data_ptr(), 1, N, H, H, C, C, 3,
                                       1, 1, ctypes.byref(dd), d_x2.data_ptr(), H, H, Cin2, stream()) == -1
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 16, 128, 128, 3, 1, 1, True, True), (9, 16, 16, 128, 128, 3, 1, 1, True, False),
+                                   (4, 32, 32, 64, 128, 3, 2, 1, True, False)])
+@pytest.mark.parametrize("drop_kind", [0, 1])
+def test_conv_tc_swapped_cta_pair_multicast(lib, shape, drop_kind, monkeypatch):
+    """operand-swapped kernel as CTA pairs (weight halves TMA-multicast into both CTAs), incl. an odd number of
+    row-tiles and the 16-warp dropout epilogue: bit-identical to the single-CTA swapped kernel."""
+    monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    monkeypatch.setenv("BNN_TC_SWAP_MC2", "1")
+    N = shape[0]
+    dd = drop_desc(drop_kind, 0.5, 0x77, 4, 5, N) if drop_kind else None
+    got, want = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    if drop_kind == 0:
+        assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+    monkeypatch.setenv("BNN_TC_SWAP_MC2", "0")
+    ref, _ = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    assert torch.equal(got, ref) and not torch.isnan(got).any()
