@@ -609,3 +609,13 @@ def test_conv_tc_swapped_cta_pair_multicast(lib, shape, drop_kind, monkeypatch):
     monkeypatch.setenv("BNN_TC_SWAP_MC2", "0")
     ref, _ = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
     assert torch.equal(got, ref) and not torch.isnan(got).any()
+
+
+def test_conv_tc_tap_skip_on_1x1_maps_is_bit_exact(lib, monkeypatch):
+    """3x3 pad-1 convolutions on 1x1 maps run the centre tap only; identical bits to the nine-tap form."""
+    shape = (300, 1, 1, 512, 512, 3, 1, 1, True, True)
+    got, want = _conv_case(lib, "tc", "fp16", *shape)
+    monkeypatch.setenv("BNN_TC_NO_TAP_SKIP", "1")
+    ref, _ = _conv_case(lib, "tc", "fp16", *shape)
+    assert torch.equal(got, ref)
+    assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
