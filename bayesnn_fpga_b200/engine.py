@@ -211,6 +211,8 @@ class Graph:
         for op in self.ops:
             if op.kind != "conv" or op.res is not None or op.site is not None or op.stride != 2 or not eligible(op):
                 continue
+            if op.src is self.input or getattr(op, "sc", None) is not None:
+                continue                      # the (channel-padded) network input and fused shortcuts stay single launches
             if not ((op.ksize == (3, 3) and op.pad == 1) or (op.ksize == (1, 1) and op.pad == 0)):
                 continue
             groups.setdefault((op.src.id, op.dst.C, op.dst.H, op.dst.W), []).append(op)

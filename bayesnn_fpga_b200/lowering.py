@@ -30,9 +30,22 @@ _ADD_FNS = (operator.add, operator.iadd, torch.add)
 _FLATTEN_FNS = (torch.flatten,)
 
 
+def _is_mc_module(m):
+    """This package's MCDropout, or the reference's own class of that name (an nn.Dropout subclass whose forward is
+    F.dropout(x, p, training=True), resnet18.py:207-210 / vgg19.py:384-387)."""
+    return isinstance(m, MCDropout) or (isinstance(m, nn.Dropout) and type(m).__name__ == "MCDropout")
+
+
+def _is_masksembles(m):
+    """This package's Masksembles modules, or the reference's own (utils.py:115-236): same attributes."""
+    return isinstance(m, _MasksemblesBase) or (
+        type(m).__name__ in ("Masksembles1D", "Masksembles2D") and all(hasattr(m, a) for a in ("masks", "n", "cnt")))
+
+
 class _Tracer(torch.fx.Tracer):
     def is_leaf_module(self, m, qualname):
-        return isinstance(m, (_DropoutBase, MCDropout, _MasksemblesBase)) or super().is_leaf_module(m, qualname)
+        return isinstance(m, _DropoutBase) or _is_mc_module(m) or _is_masksembles(m) or \
+            super().is_leaf_module(m, qualname)
 
 
 class _Lowering:
@@ -48,6 +61,7 @@ class _Lowering:
         self.deferred = {}         # add node -> group waiting for its residual operand
         self.sites = []            # (Site, module) in creation order
         self.exit_of = {}          # fx node -> exit index of the head that produces it
+        self.nonneg = set()        # ids of lowered tensors known to be >= 0 (a ReLU on them is the identity)
 
     # ---- node classification -----------------------------------------------------------------
     def _mod(self, node):
@@ -69,7 +83,7 @@ class _Lowering:
     def _passes_relu(self, node):
         m = self._mod(node)
         inner = m.layer if isinstance(m, _DropoutBase) else m
-        return self._is_maxpool(node) or isinstance(inner, nn.MaxPool2d) or isinstance(m, (MCDropout, _MasksemblesBase))
+        return self._is_maxpool(node) or isinstance(inner, nn.MaxPool2d) or _is_mc_module(m) or _is_masksembles(m)
 
     @staticmethod
     def _sole_user(node):
@@ -83,6 +97,8 @@ class _Lowering:
     def _site(self, t, module, kind, p, name):
         dst = self.g.site(t, kind, p, module=module if kind == "mask" else None, name=name)
         self._bind(self.g.sites[-1], module)
+        if t.id in self.nonneg:
+            self.nonneg.add(dst.id)            # mask multipliers are >= 0
         return dst
 
     def _bind(self, site, module):
@@ -134,6 +150,8 @@ class _Lowering:
         src = self.val[node.args[0]]
         res = self.val[grp["res"]] if grp["res"] is not None else None
         t = self.g.conv(src, conv, grp["bn"], relu=grp["relu"], residual=res, name=node.name)
+        if grp["relu"]:
+            self.nonneg.add(t.id)
         w = grp["wrapper"]
         if w is not None:
             if isinstance(w, BayesianDropout3D) or not isinstance(w, (BayesianDropout, BayesianDropout2D)):
@@ -161,6 +179,8 @@ class _Lowering:
         if nxt is not None and self._is_relu(nxt):
             relu = True
         t = self.g.linear(src, lin, relu=relu, name=node.name)
+        if relu:
+            self.nonneg.add(t.id)
         if wrapper is None and not relu and all(u.op == "output" for u in node.users):
             # `x -> [global pool] -> [site] -> Linear -> output`: a real exit head (pool + site + Linear + softmax +
             # accumulation over the samples in ONE kernel) instead of the generic ops just emitted
@@ -198,7 +218,10 @@ class _Lowering:
             self._fail(node, "square pooling windows only")
         if one(k) != one(s) or one(pad) != 0 or one(dil) != 1 or ceil:
             self._fail(node, "MaxPool2d needs kernel == stride, no padding, no dilation, floor mode")
-        t = self.g.maxpool(self.val[node.args[0]], int(one(k)), name=node.name)
+        src_t = self.val[node.args[0]]
+        t = self.g.maxpool(src_t, int(one(k)), name=node.name)
+        if src_t.id in self.nonneg:
+            self.nonneg.add(t.id)
         if wrapper is not None:
             t = self._site(t, wrapper, "mc", wrapper.p, node.name + ".dropout")
         self.val[node] = t
@@ -212,6 +235,8 @@ class _Lowering:
         w[idx, idx] = 1.0 / (src.H * src.W)
         t = self.g.conv_raw(src, w, torch.zeros(src.C), 1, 0, False, None, node.name)
         self.g.ops[-1].is_gap = True
+        if src.id in self.nonneg:
+            self.nonneg.add(t.id)
         return t
 
     # ---- main walk -----------------------------------------------------------------------------
@@ -221,6 +246,8 @@ class _Lowering:
         for node in self.gm.graph.nodes:
             if node in self.consumed:
                 continue
+            if node.op == "get_attr" and not node.users:
+                continue                      # e.g. a leaf module's parameter that fx materialises but nobody reads
             m = self._mod(node)
             inner = m.layer if isinstance(m, _DropoutBase) else m
             if node.op == "placeholder":
@@ -253,20 +280,34 @@ class _Lowering:
             elif self._is_relu(node):
                 if node in getattr(self, "pool_relu_done", ()):
                     self.val[node] = self.val[node.args[0]]     # already applied in front of the max-pool
+                elif getattr(self.val.get(node.args[0]), "id", None) in self.nonneg:
+                    self.val[node] = self.val[node.args[0]]     # ReLU of a tensor that is already >= 0
                 else:
                     self._fail(node, "a ReLU must follow a convolution, a Linear or a max-pool of a convolution")
-            elif isinstance(m, MCDropout):                       # (a subclass of nn.Dropout: test it first)
+            elif _is_mc_module(m):                               # (a subclass of nn.Dropout: test it first)
                 self.val[node] = self._site(self.val[node.args[0]], m, "mc", m.p, node.name)
+            elif node.op == "call_function" and node.target is F.dropout:
+                a = list(node.args) + [None] * 4
+                p_ = node.kwargs.get("p", a[1] if a[1] is not None else 0.5)
+                training = node.kwargs.get("training", a[2] if a[2] is not None else True)
+                src = self.val[node.args[0]]
+                self.val[node] = self._site(src, None, "mc", float(p_), node.name) if training else src
             elif isinstance(m, (nn.Dropout, nn.Dropout2d, nn.Identity)):
                 self.val[node] = self.val[node.args[0]]          # eval-mode no-ops
-            elif isinstance(m, _MasksemblesBase):
+            elif _is_masksembles(m):
                 self.val[node] = self._site(self.val[node.args[0]], m, "mask", 0.0, node.name)
             elif isinstance(m, nn.Flatten) or (node.op == "call_function" and node.target in _FLATTEN_FNS) or \
                     (node.op == "call_method" and node.target in ("flatten", "view", "reshape")):
                 self.val[node] = self.val[node.args[0]]          # g.linear flattens in NCHW order itself
-            elif isinstance(m, (nn.AdaptiveAvgPool2d, nn.AvgPool2d)):
+            elif isinstance(m, (nn.AdaptiveAvgPool2d, nn.AvgPool2d)) or \
+                    (node.op == "call_function" and node.target in (F.avg_pool2d, F.adaptive_avg_pool2d)):
                 src = self.val[node.args[0]]
-                if isinstance(m, nn.AdaptiveAvgPool2d):
+                if node.op == "call_function":
+                    arg = node.args[1] if len(node.args) > 1 else node.kwargs.get("kernel_size", node.kwargs.get("output_size"))
+                    k = arg if isinstance(arg, (tuple, list)) else (arg,) * 2
+                    ok = tuple(k) == ((1, 1) if node.target is F.adaptive_avg_pool2d else (src.H, src.W)) and \
+                        not node.kwargs.get("padding", 0) and len(node.args) <= 2
+                elif isinstance(m, nn.AdaptiveAvgPool2d):
                     ok = m.output_size in (1, (1, 1))
                 else:
                     k = m.kernel_size if isinstance(m.kernel_size, (tuple, list)) else (m.kernel_size,) * 2

@@ -95,3 +95,68 @@ def reference_mean(model, x, sites, S, sample0=0):
             out = out if isinstance(out, (list, tuple)) else [out]
             acc = [o.clone() for o in out] if acc is None else [a + o for a, o in zip(acc, out)]
     return [a / S for a in acc]
+
+
+class MCDropout(nn.Dropout):
+    """Same shape as the REFERENCE's own class (resnet18.py:207-210): an nn.Dropout subclass, not this package's."""
+
+    def forward(self, x):
+        return F.dropout(x, self.p, True, self.inplace)
+
+
+class RefStyleBlock(nn.Module):
+    """BasicBlock written like the reference's (resnet18.py:32-48): `out += residual`, module ReLU, shortcut last."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        residual = x
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        if self.downsample is not None:
+            residual = self.downsample(x)
+        out += residual
+        return self.relu(out)
+
+
+class RefStyleNet(nn.Module):
+    """Two-exit network in the style of ResNet18MCEarlyExit.forward (resnet18.py:302-346): stem without ReLU, stage =
+    Sequential(blocks, dropout), exit branch on F.relu of an already non-negative tensor, F.avg_pool2d + view heads,
+    a side-effect attribute, list output."""
+
+    def __init__(self, drop, classes=10):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.layer1 = nn.Sequential(nn.Sequential(RefStyleBlock(64, 64, 1)), drop(0.5))
+        self.layer2 = nn.Sequential(RefStyleBlock(64, 128, 2), RefStyleBlock(128, 128, 1))
+        self.ex1conv1 = nn.Conv2d(64, 128, 3, 2, 1, bias=False)
+        self.ex1bn1 = nn.BatchNorm2d(128)
+        self.exit1_dropout = drop(0.25)
+        self.ex1linear = nn.Linear(128, classes)
+        self.exit_dropout = drop(0.25)
+        self.linear = nn.Linear(128, classes)
+
+    def forward(self, x):
+        out = self.bn1(self.conv1(x))
+        out = self.layer1(out)
+        out1 = self.ex1bn1(self.ex1conv1(F.relu(out)))
+        out1 = F.avg_pool2d(F.relu(out1), 8)
+        middle1_fea = out1
+        out1 = out1.view(out1.size(0), -1)
+        out1 = self.ex1linear(self.exit1_dropout(out1))
+        out = self.layer2(out)
+        out = F.avg_pool2d(F.relu(out), 8)
+        out = out.view(out.size(0), -1)
+        out = self.linear(self.exit_dropout(out))
+        self.intermediary_output_list = (out, [out1], None, [middle1_fea])
+        return [out1, out]

@@ -107,3 +107,34 @@ def test_unsupported_network_falls_back_with_warning():
     with pytest.warns(UserWarning, match="stand-alone passes"):
         y = bnn(x)
     assert y.shape == (5, 3) and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("fp16", 2e-3)])
+def test_reference_style_model_object_runs_unmodified(dtype, tol):
+    """A model written like the reference's own classes (its MCDropout = nn.Dropout subclass calling F.dropout,
+    `out += residual`, F.relu on non-negative tensors, F.avg_pool2d + view heads, side-effect attribute) goes through
+    mc_predict as is; sites are numbered in first-use order like the named models."""
+    from tests.nets_generic import MCDropout as RefMCDropout, RefStyleNet
+    torch.manual_seed(4)
+    S, seed, B = 4, 0x5EED, 5
+    model = randomize_bn(RefStyleNet(lambda p: RefMCDropout(p))).cuda().eval()
+    ref_sites = []
+
+    def drop(p):
+        d = InjectedDropout(p, len(ref_sites), seed)
+        ref_sites.append(d)
+        return d
+    ref = RefStyleNet(drop)
+    # module construction order: layer1 dropout (first used), exit1_dropout, exit_dropout == first-use order
+    ref.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    x = torch.randn(B, 3, 16, 16)
+    want = reference_mean(ref, x, ref_sites, S)
+    r = mc_predict(model, x.cuda(), S, seed=seed, dtype=dtype)
+    eng = model.__dict__["_bnn_generic_engines"][((3, 16, 16), dtype, ())]
+    assert [s.stream for s in eng.graph.sites] == [0, 1, 2] and eng.graph.n_exits == 2
+    assert sum(o.kind == "head" for o in eng.graph.ops) == 2 and not any(getattr(o, "is_gap", False) for o in eng.graph.ops)
+    for e, w in enumerate(want):
+        scale = max(1.0, w.abs().max().item())
+        err = (r.mean_logits[e].double().cpu() - w).abs().max().item()
+        report(test="reference_style_model", dtype=dtype, exit=e, err=err, scale=scale)
+        assert err <= tol * scale

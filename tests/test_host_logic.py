@@ -3,6 +3,7 @@ symbol table, and the no-CPU-fallback contract."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -245,3 +246,52 @@ def test_shortcut_fusion_pass_preserves_macs_and_removes_projection_convs():
     gm.fuse_sites()
     gm.fuse_shortcuts(lambda op: True)
     assert not any(getattr(o, "sc", None) is not None for o in gm.ops)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Software_Artifact/software"),
+                    reason="needs the reference checkout (build container only)")
+def test_reference_model_objects_lower_to_the_same_graph_as_the_drop_in_classes():
+    """lowering.lower_module applied to the UNMODIFIED reference model classes (their own MCDropout / Masksembles
+    modules, F.relu / F.avg_pool2d / view forward) yields op for op the graph of this package's classes: same kinds,
+    folded weights, ReLU flags, sites (kind, p, stream) and MACs - so `mc_predict(reference_model, x, S)` is the path
+    the parity tests already cover."""
+    import subprocess
+    code = r'''
+import sys
+sys.path.insert(0, "%s"); sys.path.insert(0, "/root/reference/Software_Artifact/software")
+import numpy as np, torch
+from models.resnet18 import resnet18 as ref
+from models.vgg19 import vgg19 as refv
+from bayesnn_fpga_b200 import lowering, resnet18 as ours, vgg19 as oursv
+def sig(g):
+    return [(o.kind, o.relu, (o.site.kind, o.site.p, o.site.stream) if o.site else None,
+             tuple(o.weight.shape) if o.weight is not None else None, o.stride, o.pad, o.pool_k) for o in g.ops]
+def check(rm, om):
+    om.load_state_dict(rm.state_dict())
+    g1, _ = lowering.lower_module(rm.eval(), (3, 32, 32))
+    g2 = om.eval()._bnn_graph()
+    assert sig(g1) == sig(g2) and g1.macs() == g2.macs() and g1.out_order == list(range(g2.n_exits))
+    for a, b in zip(g1.ops, g2.ops):
+        if a.weight is not None:
+            assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+for kw in (dict(dropout_exit=True, dropout="block", dropout_p=0.5, out_dim=10),
+           dict(dropout_exit=True, dropout=None, dropout_p=0.125, out_dim=100),
+           dict(dropout_exit=True, dropout="block", out_dim=100, mask_type="mask", num_masks=4, mask_scale=2.0),
+           dict(dropout_exit=True, dropout="layer", dropout_p=0.25, out_dim=10)):
+    np.random.seed(0); rm = ref.ResNet18MCEarlyExit(**kw)
+    np.random.seed(0); om = ours.ResNet18MCEarlyExit(**kw)
+    check(rm, om)
+np.random.seed(0)
+check(ref.ResNet18MC(dropout_exit=True, dropout="block", dropout_p=0.375, out_dim=10),
+      ours.ResNet18MC(dropout_exit=True, dropout="block", dropout_p=0.375, out_dim=10))
+kw = dict(dropout_exit=True, dropout=None, dropout_p=0.25, out_dim=10, image_size=32, n_exits=5)
+check(refv.VGG19MCEarlyExit(**kw), oursv.VGG19MCEarlyExit(**kw))
+rm = refv.VGG19MCEarlyExit(**kw)
+for i in (2, 3, 4):
+    rm.blocks[i].append(refv.MCDropout(0.25))
+check(rm, oursv.VGG19MCEarlyExit(**kw).append_block_dropout((2, 3, 4)))
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # a subprocess: the reference's top-level module names (`utils`, `models`) must not leak into this process
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
