@@ -74,6 +74,7 @@ _SIGS = {
     "bnn_conv2d_tc_shortcut": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
                                [ctypes.POINTER(DropDesc), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p]),
+    "bnn_conv2d_tc_pooled": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 + [ctypes.c_void_p]),
     "bnn_conv2d_tc_grouped": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
                               [ctypes.c_int] * 8 + [ctypes.c_void_p]),
     "bnn_conv2d_tc_gathered": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +

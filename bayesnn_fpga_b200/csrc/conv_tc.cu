@@ -79,6 +79,10 @@ struct Params {
   // SECOND tensor (tmap_a2: the block input x, centre tap of its stride-2 parity view) and whose weights are the
   // columns [taps * Cin, taps * Cin + 64 * cblocks2) of the K-concatenated weight matrix
   int cblocks2;
+  // fused global average pool (bnn_conv2d_tc_pooled): the output map of one image (pool_hw = OH * OW pixels, a power of
+  // two <= 32, so one image = pool_hw adjacent lanes of an epilogue warp) is averaged with warp shuffles and only the
+  // pooled row [N][Cout] is written - the exit head's input
+  int pool_hw;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
   const float* bias;
   const void* res;
@@ -719,7 +723,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + (dead ? 0 : c0)) + j);
           tmem_ld_wait();
-          if (valid) {
+          if (valid || (p.pool_hw > 0 && !dead)) {      // pooling: all lanes of the warp take part in the shuffles
             const size_t off = (size_t)m * p.cout_g + (cgrp + ch * 32);
             float f[32];
 #pragma unroll
@@ -785,6 +789,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 f[j + 2] *= m4.z;
                 f[j + 3] *= m4.w;
               }
+            }
+            if (p.pool_hw > 0) {
+              // M is a multiple of pool_hw, so an image is entirely valid or entirely past the end
+#pragma unroll 1
+              for (int o = p.pool_hw >> 1; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += __shfl_xor_sync(0xffffffffu, f[j], o);
+              if (valid && (lane & (p.pool_hw - 1)) == 0) {
+                const float inv = 1.f / (float)p.pool_hw;
+                T* yp = y + (size_t)(m / p.pool_hw) * p.cout_g + (cgrp + ch * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 o;
+                  o.x = pack2<T>(f[j] * inv, f[j + 1] * inv);
+                  o.y = pack2<T>(f[j + 2] * inv, f[j + 3] * inv);
+                  o.z = pack2<T>(f[j + 4] * inv, f[j + 5] * inv);
+                  o.w = pack2<T>(f[j + 6] * inv, f[j + 7] * inv);
+                  *reinterpret_cast<uint4*>(yp + j) = o;
+                }
+              }
+              continue;
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -913,7 +938,7 @@ struct Shortcut {
 static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                        int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
-                       const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr) {
+                       const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr, bool pool = false) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
@@ -951,6 +976,12 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     BNN_REQUIRE(sc->Cin2 > 0 && sc->Cin2 % 64 == 0 && sc->H2 == 2 * OH && sc->W2 == 2 * OW,
                 "%s: shortcut input %dx%dx%d does not match a 1x1 stride-2 convolution onto %dx%d", who, sc->H2, sc->W2,
                 sc->Cin2, OH, OW);
+  }
+  if (pool) {
+    BNN_REQUIRE(groups == 1 && cout_g % 256 == 0 && (drop == nullptr || drop->kind == BNN_DROP_NONE) && gsel == nullptr,
+                "%s: the fused average pool needs one dense output with Cout %% 256 == 0 and no stochastic epilogue", who);
+    BNN_REQUIRE(OH * OW >= 2 && OH * OW <= 32 && tc::pow2(OH * OW), "%s: pooled map %dx%d must have 2..32 pixels (a power of two)",
+                who, OH, OW);
   }
   const bool compact_out = drop && drop->kind == BNN_DROP_MASKSEMBLES && drop->compact_pos != nullptr;
   if (compact_out) {
@@ -1052,6 +1083,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
   }
   p.cblocks2 = sc ? sc->Cin2 / tc::BK : 0;
+  p.pool_hw = pool ? OH * OW : 0;
   p.stride = stride;
   p.pad = pad;
   p.OH = OH;
@@ -1159,4 +1191,12 @@ extern "C" int bnn_conv2d_tc_shortcut(const void* x, const void* w, const float*
   Shortcut sc{x2, H2, W2, Cin2};
   return conv_tc_run("bnn_conv2d_tc_shortcut", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
                      stride, drop, stream, nullptr, &sc);
+}
+
+extern "C" int bnn_conv2d_tc_pooled(const void* x, const void* w, const float* bias, const void* res, void* y_pooled,
+                                    int dtype, int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
+                                    void* stream) {
+  void* ys[1] = {y_pooled};
+  return conv_tc_run("bnn_conv2d_tc_pooled", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
+                     stride, nullptr, stream, nullptr, nullptr, true);
 }

@@ -203,6 +203,27 @@ class Graph:
             op.name = op.name + "+" + d.name.split(".")[-1]
             self.ops.remove(d)
 
+    def fuse_head_pools(self, eligible):
+        """The convolution whose only reader is an exit head writes the head's global average pool instead of the map
+        (`F.avg_pool2d(F.relu(out), k)` -> Linear, resnet18.py:309-314,:339-344): the map never reaches HBM and the head
+        reads one pooled row per image."""
+        for head in [o for o in self.ops if o.kind == "head"]:
+            t = head.src
+            conv = next((o for o in self.ops if o.kind == "conv" and o.dst is t), None)
+            hw = t.H * t.W
+            if conv is None or conv.site is not None or not conv.relu or not eligible(conv) or conv.dst.C % 256 != 0 or \
+                    hw < 2 or hw > 32 or hw & (hw - 1) or getattr(conv, "sc", None) is not None:
+                continue
+            if sum(1 for o in self.ops if o.src is t or o.res is t) != 1:
+                continue
+            if conv.stride == 2 and any(o is not conv and o.kind == "conv" and o.src is conv.src and o.stride == 2
+                                        for o in self.ops):
+                continue                      # stays in its sibling group (the shared input is read once)
+            pooled = self._new(t.C, 1, 1, t.stoch)
+            conv.pool_from = (t.H, t.W)
+            conv.dst = pooled
+            head.src = pooled
+
     def fuse_sibling_convs(self, eligible):
         """Group stride-2 convolutions that read the same tensor (first conv of the next stage, its 1x1 shortcut,
         first conv of the exit branch) into one 'convg' op: the input is fetched from HBM once.  A 1x1 stride-2
@@ -245,9 +266,10 @@ class Graph:
             flat.extend(op.members if op.kind == "convg" else [op])
         for op in flat:
             if op.kind == "conv":
-                m = op.dst.H * op.dst.W * op.dst.C * op.src.C * op.ksize[0] * op.ksize[1]
+                oh, ow = getattr(op, "pool_from", None) or (op.dst.H, op.dst.W)
+                m = oh * ow * op.dst.C * op.src.C * op.ksize[0] * op.ksize[1]
                 if getattr(op, "sc", None) is not None:
-                    m += op.dst.H * op.dst.W * op.dst.C * op.sc["src"].C
+                    m += oh * ow * op.dst.C * op.sc["src"].C
             elif op.kind == "head":
                 m = op.weight.shape[0] * op.weight.shape[1]
                 if op.site is not None or op.src.stoch:
@@ -319,6 +341,8 @@ class Engine:
             graph.fuse_shortcuts(self._tc_eligible,
                                  allow_masked=lambda prod: self.gather_mode == 0 or
                                  (prod.kind == "conv" and self.gather_mode < 2))
+        if self.use_tc and fuse and os.environ.get("BNN_HEAD_POOL_FUSION", "1") != "0":
+            graph.fuse_head_pools(self._tc_eligible)
         if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
             graph.fuse_sibling_convs(self._tc_eligible)
         self.sample_chunk = int(os.environ.get("BNN_SAMPLE_CHUNK", "0")) if sample_chunk is None else int(sample_chunk)
@@ -340,10 +364,11 @@ class Engine:
         kh, kw = op.ksize
         pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
         cin = self.in_pad if (op.src is self.graph.input and self.in_pad) else op.src.C
+        oh, ow = getattr(op, "pool_from", None) or (op.dst.H, op.dst.W)
         return (self.use_tc and kh == kw and ((kh == 3 and op.pad == 1) or (kh == 1 and op.pad == 0))
                 and op.stride in (1, 2) and cin % 64 == 0 and op.dst.C % 64 == 0
                 and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0))
-                and pow2(op.dst.H) and pow2(op.dst.W) and op.dst.W <= 128)
+                and pow2(oh) and pow2(ow) and ow <= 128)
 
     def _prepare_weights(self):
         dev = self.device
@@ -650,11 +675,15 @@ class Engine:
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset,
                                      self.gather[op.dst.id] if op.dst.id in compact else None)
                 kh, kw = op.ksize
-                out_px = n_img * op.dst.H * op.dst.W
+                pool_from = getattr(op, "pool_from", None)
+                out_px = n_img * (pool_from[0] * pool_from[1] if pool_from else op.dst.H * op.dst.W)
                 flops = 2 * out_px * op.dst.C * op.src.C * kh * kw
                 nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * op.dst.C * (2 if res is not None else 1)) * es \
                     + op.d_w.numel() * op.d_w.element_size()
                 sc = getattr(op, "sc", None)
+                if pool_from:
+                    nbytes = (n_img * op.src.H * op.src.W * op.src.C + n_img * op.dst.C + (out_px * op.dst.C if res is not None else 0)) * es \
+                        + op.d_w.numel() * op.d_w.element_size()
                 cin = self.in_pad if (op.src is g.input and self.in_pad and op.use_tc) else op.src.C
                 if sc is not None:
                     flops += 2 * out_px * op.dst.C * sc["src"].C
@@ -663,6 +692,10 @@ class Engine:
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
                         op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd),
                         _ptr(acts[sc["src"].id]), sc["src"].H, sc["src"].W, sc["src"].C, stream)
+                elif pool_from:
+                    call = lambda: lib.bnn_conv2d_tc_pooled(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), stream)
                 elif op.use_tc:
                     call = lambda: lib.bnn_conv2d_tc(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,

@@ -134,6 +134,13 @@ int bnn_conv2d_tc_shortcut(const void* x, const void* w, const float* bias, cons
                            int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
                            const void* x2, int H2, int W2, int Cin2, void* stream);
 
+/* The last convolution in front of an exit head with the head's global average pool fused into its epilogue
+ * (`F.avg_pool2d(F.relu(out), 4)`, resnet18.py:309,:339): the OH x OW map of every image (2..32 pixels, a power of two)
+ * is averaged with warp shuffles and only y_pooled [N][Cout] is written; the map itself never reaches HBM and the head
+ * (bnn_exit_head with HW = 1) reads 1/(OH*OW) of the bytes.  Cout % 256 == 0, no stochastic epilogue. */
+int bnn_conv2d_tc_pooled(const void* x, const void* w, const float* bias, const void* res, void* y_pooled, int dtype,
+                         int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu, void* stream);
+
 /* Masksembles "gathered" convolution (north star (3): structured channel masks become smaller GEMMs and dropped
  * channels are never read from HBM).  Same as bnn_conv2d_tc_grouped, but
  *   x  is [N][H][W][Kc]: the compact output of a Masksembles2D site (bnn_drop_desc.compact_pos), Kc % 16 == 0;

@@ -619,3 +619,34 @@ def test_conv_tc_tap_skip_on_1x1_maps_is_bit_exact(lib, monkeypatch):
     ref, _ = _conv_case(lib, "tc", "fp16", *shape)
     assert torch.equal(got, ref)
     assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("H,N,Cin,C,stride,with_res,pair", [(4, 40, 512, 512, 1, True, "0"), (8, 12, 256, 512, 2, False, "0"),
+                                                           (2, 70, 256, 256, 1, False, "0"), (4, 41, 512, 512, 1, True, "cg2")])
+def test_conv_tc_fused_average_pool(lib, H, N, Cin, C, stride, with_res, pair, monkeypatch):
+    """bnn_conv2d_tc_pooled == mean over the OH x OW map of bnn_conv2d_tc's output (`F.avg_pool2d(F.relu(out), k)`,
+    resnet18.py:309,:339), incl. a last tile that ends inside the warp."""
+    if pair != "0":
+        monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    g = torch.Generator().manual_seed(H + N)
+    x = torch.randn(N, H, H, Cin, generator=g).half().cuda()
+    w = (torch.randn(C, 3, 3, Cin, generator=g) / np.sqrt(9 * Cin)).half().cuda()
+    b = torch.randn(C, generator=g).cuda()
+    OH = H // stride
+    res = torch.randn(N, OH, OH, C, generator=g).half().cuda() if with_res else None
+    full = torch.empty(N, OH, OH, C, dtype=torch.float16, device="cuda")
+    pooled = torch.full((N, C), float("nan"), dtype=torch.float16, device="cuda")
+    dd = drop_desc(batch=N)
+    rp = ctypes.c_void_p(res.data_ptr() if with_res else 0)
+    assert lib.bnn_conv2d_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), rp, full.data_ptr(), 1, N, H, H, Cin, C, 3, stride, 1,
+                             ctypes.byref(dd), stream()) == 0, lib.bnn_last_error()
+    assert lib.bnn_conv2d_tc_pooled(x.data_ptr(), w.data_ptr(), b.data_ptr(), rp, pooled.data_ptr(), 1, N, H, H, Cin, C, 3,
+                                    stride, 1, stream()) == 0, lib.bnn_last_error()
+    torch.cuda.synchronize()
+    want = full.float().mean(dim=(1, 2))
+    err = (pooled.float() - want).abs().max().item()
+    # the fused form averages the fp32 accumulators, the reference form the fp16-rounded map: <= 1 fp16 ulp apart
+    assert not torch.isnan(pooled).any() and err <= 2e-3 * max(1.0, want.abs().max().item())
+    # maps that are not 2..32 pixels (power of two) are rejected
+    assert lib.bnn_conv2d_tc_pooled(x.data_ptr(), w.data_ptr(), b.data_ptr(), rp, pooled.data_ptr(), 1, 1, 16, 16, Cin, C, 3,
+                                    1, 1, stream()) == -1

@@ -295,3 +295,21 @@ print("ok")
     # a subprocess: the reference's top-level module names (`utils`, `models`) must not leak into this process
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_head_pool_fusion_pass():
+    """Graph.fuse_head_pools: the convolutions whose only reader is an exit head write the pooled row; the one that
+    shares its input with the next stage stays in the sibling group; MACs are unchanged."""
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", dropout_p=0.5, out_dim=10)
+    g = m._bnn_graph()
+    g.fuse_sites()
+    before = g.macs()
+    g.fuse_shortcuts(lambda op: True)
+    g.fuse_head_pools(lambda op: True)
+    pooled = [o.name for o in g.ops if getattr(o, "pool_from", None)]
+    assert pooled == ["ex1conv3", "ex2conv2", "layer4.1.conv2"] and g.macs() == before
+    for o in g.ops:
+        if o.kind == "head" and o.name != "ex3linear":
+            assert (o.src.H, o.src.W) == (1, 1)
+    g.fuse_sibling_convs(lambda op: True)
+    assert [len(o.members) for o in g.ops if o.kind == "convg"] == [2, 2, 2]
