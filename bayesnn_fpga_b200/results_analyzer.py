@@ -95,6 +95,49 @@ class FullAnalysis:
                 bad[e] = set(np.flatnonzero(~hit).tolist())
         return self.preds
 
+    def get_validation_predictions(self, val_loader):
+        """-> (preds [E, N, C], ensembled_preds [E, N, C], one-hot labels [N, C]) over `val_loader` like
+        results_analyzer.py:179-215 (the trackers it also fills there are discarded by its only caller)."""
+        preds, labels = [], []
+        for b_x, b_y in val_loader:
+            _, _, sm_np, _, _ = self._get_output(b_x)
+            preds.append(sm_np)
+            labels.append(np.asarray(b_y).reshape(-1))
+        preds = np.concatenate(preds, axis=1)
+        ens = np.stack([np.average(preds[:i], axis=0) for i in range(1, preds.shape[0] + 1)])       # :211-213
+        return preds, ens, np.eye(self.model.out_dim)[np.concatenate(labels)]
+
+    def save_validation(self, experiment_id, loader):
+        """:217-222 - validation_predictions_<id>.npy holding preds, ensemble_preds, labels."""
+        preds, ensemble_preds, labels = self.get_validation_predictions(loader)
+        with open(f"validation_predictions_{experiment_id}.npy", "wb") as file:
+            np.save(file, preds)
+            np.save(file, ensemble_preds)
+            np.save(file, labels)
+
+    def average_results_accuracy(self):
+        """:94-111 - mean over the exits of #correct and of the ECE, for single exits and cumulative ensembles."""
+        n = len(self.layer_correct)
+        acc = sum(len(self.layer_correct[l]) for l in range(n)) / n
+        ens_acc = sum(len(self.ensemble_layer_correct[l]) for l in range(n)) / n
+        ece = sum(self.ece_eval_binary(self.preds[l], self.labels)[0] for l in range(n)) / n
+        ens_ece = sum(self.ece_eval_binary(self.ensemble_preds[l], self.labels)[0] for l in range(n)) / n
+        return acc, ens_acc, ece, ens_ece
+
+    def multipass_experiment(self, passes=range(1, 50)):
+        """:73-92 - accuracy / ECE as a function of the number of MC passes; returns the four lists it prints."""
+        out = ([], [], [], [])
+        keep = self.mc_passes
+        for s in passes:
+            self.mc_passes = s
+            self.sdn_get_detailed_results()
+            for lst, v in zip(out, self.average_results_accuracy()):
+                lst.append(v)
+        self.mc_passes = keep if keep else 10
+        for lst in out:
+            print(",".join(str(v) for v in lst))
+        return out
+
     # ---- calibration statistics ---------------------------------------------------------------
     def _device_bins(self, p, label_index, n_bins):
         lib = _lib.load()

@@ -257,3 +257,38 @@ def test_masksembles_gathered_gemm_vs_oracle(S, cnt0, s0, mode, monkeypatch):
 
 def _launch_names(eng, x, S):
     return [o["name"] for o in eng.profile_step(x.cuda(), S)]
+
+
+def test_full_analysis_over_a_loader(tmp_path, monkeypatch):
+    """FullAnalysis end to end on a small synthetic 'dataset' (LeNet, 2 exits): batch loop, per-exit correct sets,
+    all_experiments, average_results_accuracy, multipass_experiment, validation predictions - consistent with the oracle
+    statistics computed from the same predictions."""
+    from bayesnn_fpga_b200.lenet import LeNetMCEarlyExit
+    from bayesnn_fpga_b200.results_analyzer import FullAnalysis
+    torch.manual_seed(0)
+    model = LeNetMCEarlyExit(dropout_p=0.2, out_dim=10).cuda().eval()
+    N, bs = 96, 32
+    x = seeded.seeded_input((N, 1, 28, 28), seed=3)
+    y = torch.from_numpy(seeded.seeded_labels(N, 10, seed=4))
+    loader = [(x[i:i + bs], y[i:i + bs]) for i in range(0, N, bs)]
+    fa = FullAnalysis(model, loader, mc_dropout=True, mc_passes=4, dtype="fp32")
+    assert fa.preds.shape == (2, N, 10) and fa.ensemble_preds.shape == (2, N, 10) and fa.labels.shape == (N, 10)
+    assert np.allclose(fa.ensemble_preds[1], fa.preds.mean(0), atol=1e-6)
+    for e in range(2):
+        hit = set(np.flatnonzero(fa.preds[e].argmax(1) == y.numpy()).tolist())
+        assert fa.layer_correct[e] == hit and fa.layer_wrong[e] == set(range(N)) - hit
+    fa.all_experiments()
+    for e in range(2):
+        nll, mse, acc = stats.nll_mse_acc(fa.preds[e], fa.labels)
+        assert abs(fa.accu_saver[e] - acc) < 1e-6 and abs(fa.nll_saver[e] - nll) < 1e-5 * max(1.0, nll)
+        assert abs(fa.ece_saver[e] - stats.ece_kde(fa.preds[e], fa.labels)) < 1e-4
+    assert fa.cum_correct_saver[1] == len(fa.layer_correct[0] | fa.layer_correct[1])
+    acc, ens_acc, ece, ens_ece = fa.average_results_accuracy()
+    assert acc == (len(fa.layer_correct[0]) + len(fa.layer_correct[1])) / 2 and 0 <= ece <= 1 and 0 <= ens_ece <= 1
+    lists = fa.multipass_experiment(passes=[1, 3])
+    assert [len(l) for l in lists] == [2, 2, 2, 2] and fa.mc_passes == 4
+    monkeypatch.chdir(tmp_path)
+    fa.save_validation("t", loader)
+    with open(tmp_path / "validation_predictions_t.npy", "rb") as f:
+        p, ep, lab = np.load(f), np.load(f), np.load(f)
+    assert p.shape == (2, N, 10) and np.allclose(ep[1], p.mean(0)) and (lab.argmax(1) == y.numpy()).all()
