@@ -27,6 +27,8 @@ METRIC = "images/sec at S MC samples (multi-exit ResNet-18, 32x32) & % tensor-co
 
 WORKLOADS = {
     # name: (description, model factory name, B, S, classes)
+    "c1": ("multi-exit LeNet-5 MC-dropout (last-layer, p=0.2), S=8, 1x28x28, batch 64 (the reference's CPU-runnable "
+           "case; CUDA-core kernels only: no tensor-core claim)", "lenet", 64, 8, 10),
     "c2": ("multi-exit ResNet-18 MC-dropout (block+exit, p=0.5), S=32, 3x32x32, batch 256", "resnet_mcd", 256, 32, 10),
     "c3": ("multi-exit ResNet-18 Masksembles (4 masks, scale 2.0), S=4, 3x32x32, batch 256, 100 classes",
            "resnet_mask", 256, 4, 100),
@@ -36,13 +38,19 @@ WORKLOADS = {
 }
 
 
+def input_shape(kind):
+    return (1, 28, 28) if kind == "lenet" else (3, 32, 32)
+
+
 def build_model(kind, classes):
     import numpy as np
     import torch
-    from bayesnn_fpga_b200 import resnet18, vgg19
+    from bayesnn_fpga_b200 import lenet, resnet18, vgg19
     torch.manual_seed(0)
     np.random.seed(0)
-    if kind == "resnet_mcd":
+    if kind == "lenet":
+        m = lenet.LeNetMCEarlyExit(dropout_p=0.2, out_dim=classes)
+    elif kind == "resnet_mcd":
         m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", dropout_p=0.5, out_dim=classes)
     elif kind == "resnet_mask":
         m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", out_dim=classes, mask_type="mask",
@@ -65,6 +73,8 @@ def build_model(kind, classes):
 
 def oracle_forward_fn(kind):
     from oracle import nets
+    if kind == "lenet":
+        return lambda sd, x, site: nets.lenet_forward(sd, x, site)
     if kind in ("resnet_mcd", "resnet_mask"):
         return lambda sd, x, site: nets.resnet18_forward(sd, x, site, "block", True)
     return lambda sd, x, site: nets.vgg19_forward(sd, x, site, True, (2, 3, 4))
@@ -80,8 +90,8 @@ def time_cpu_reference(kind, classes, S_nominal, budget_images=256, passes=4):
     model = build_model(kind, classes)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
-    spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.5, tables)
-    x = torch.randn(budget_images, 3, 32, 32)
+    spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.2 if kind == "lenet" else 0.5, tables)
+    x = torch.randn(budget_images, *input_shape(kind))
     fwd = oracle_forward_fn(kind)
 
     def run():
@@ -204,9 +214,9 @@ def reference_arm(args, wl):
     model = build_model(kind, classes)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
-    spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.5, tables)
+    spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.2 if kind == "lenet" else 0.5, tables)
     nb, passes = 64, 2
-    x = torch.randn(nb, 3, 32, 32)
+    x = torch.randn(nb, *input_shape(kind))
     fwd = oracle_forward_fn(kind)
 
     def step():
@@ -270,7 +280,7 @@ def main():
     model = build_model(kind, classes).to(dev)
     eng = model.bnn_engine(args.dtype)
     g = torch.Generator().manual_seed(100 + (0 if shard_samples else rank))
-    x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    x_host = torch.randn(B, *input_shape(kind), generator=g).pin_memory()
     x_dev = x_host.to(dev)
     E = eng.graph.n_exits
     gather_buf = [torch.empty(4 * E * B * classes + 3 * E * B, device=dev) for _ in range(world)] if world > 1 else None
