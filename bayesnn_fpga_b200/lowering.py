@@ -62,6 +62,7 @@ class _Lowering:
         self.sites = []            # (Site, module) in creation order
         self.exit_of = {}          # fx node -> exit index of the head that produces it
         self.nonneg = set()        # ids of lowered tensors known to be >= 0 (a ReLU on them is the identity)
+        self.pool_relu_done = set()   # ReLU nodes already applied in front of the max-pool / site chain they follow
 
     # ---- node classification -----------------------------------------------------------------
     def _mod(self, node):
@@ -164,7 +165,7 @@ class _Lowering:
                 break
             cur = self._sole_user(cur)
         if "relu_after_pool" in grp:
-            self.pool_relu_done = getattr(self, "pool_relu_done", set()) | {grp["relu_after_pool"]}
+            self.pool_relu_done.add(grp["relu_after_pool"])
 
     def _linear(self, node):
         m = self._mod(node)
@@ -278,7 +279,7 @@ class _Lowering:
             elif self._is_maxpool(node) or isinstance(inner, nn.MaxPool2d):
                 self._maxpool(node)
             elif self._is_relu(node):
-                if node in getattr(self, "pool_relu_done", ()):
+                if node in self.pool_relu_done:
                     self.val[node] = self.val[node.args[0]]     # already applied in front of the max-pool
                 elif getattr(self.val.get(node.args[0]), "id", None) in self.nonneg:
                     self.val[node] = self.val[node.args[0]]     # ReLU of a tensor that is already >= 0
