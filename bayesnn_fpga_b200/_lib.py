@@ -26,7 +26,8 @@ class DropDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("p", ctypes.c_float), ("seed", ctypes.c_uint64),
                 ("stream_id", ctypes.c_uint32), ("sample0", ctypes.c_uint32), ("batch", ctypes.c_int),
                 ("masks", ctypes.c_void_p), ("n_masks", ctypes.c_int), ("cnt0", ctypes.c_int),
-                ("compact_pos", ctypes.c_void_p), ("compact_idx", ctypes.c_void_p), ("compact_c", ctypes.c_int)]
+                ("compact_pos", ctypes.c_void_p), ("compact_idx", ctypes.c_void_p), ("compact_c", ctypes.c_int),
+                ("nchw_flat", ctypes.c_int)]
 
 
 def _stale():

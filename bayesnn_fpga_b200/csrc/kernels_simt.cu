@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   if (v0 >= n_per) return;
   // vector path: the 8 elements exist, every sample slab stays 16-byte aligned, and (for the per-channel
   // kinds) the 8 elements sit inside one pixel's channel run
-  const bool vec = (v0 + 8 <= n_per) && (n_per % 8 == 0) && (dp.kind == BNN_DROP_ELEMENT || C % 8 == 0);
+  const bool vec = (v0 + 8 <= n_per) && (n_per % 8 == 0) && (dp.kind == BNN_DROP_ELEMENT || C % 8 == 0) &&
+                   dp.nchw_flat == 0;
   const int c0 = (int)(v0 % C);
   const int64_t b0 = v0 / per_image;
 
@@ -286,7 +287,12 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
         const int64_t i = v0 + j;
         const int c = (int)(i % C);
         const int64_t b = i / per_image;
-        const float f = drop_factor(dp, (uint32_t)s, (uint64_t)i, (uint64_t)(b * C + c), c);
+        uint64_t e = (uint64_t)i;
+        if (dp.nchw_flat) {                       // NHWC buffer position -> NCHW-flattened element index
+          const int64_t pix = (i - b * per_image) / C;
+          e = (uint64_t)(b * per_image + (int64_t)c * (per_image / C) + pix);
+        }
+        const float f = drop_factor(dp, (uint32_t)s, e, (uint64_t)(b * C + c), c);
         ys[i] = from_f32<T>(to_f32<T>(xs[i]) * f);
       }
     }

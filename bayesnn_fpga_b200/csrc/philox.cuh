@@ -73,6 +73,7 @@ struct DropParams {
   const int16_t* compact_pos;
   const int16_t* compact_idx;
   int compact_c;
+  int nchw_flat;    // element indices in NCHW-flattened order (site behind a Flatten of a spatial map)
 };
 
 inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
@@ -93,6 +94,7 @@ inline DropParams make_drop_params(const bnn_drop_desc* d, int channels) {
   q.n_masks = d->n_masks;
   q.cnt0 = d->cnt0;
   q.channels = channels;
+  q.nchw_flat = d->kind == BNN_DROP_ELEMENT ? d->nchw_flat : 0;
   if (d->kind == BNN_DROP_MASKSEMBLES && d->compact_pos != nullptr) {
     q.compact_pos = d->compact_pos;
     q.compact_idx = d->compact_idx;

@@ -54,6 +54,7 @@ class Site:
     stream: int
     name: str
     module: Optional[object] = None      # Masksembles module (owns `masks` and the rotating `cnt`)
+    nchw_flat: bool = False              # element indices in NCHW-flattened order (site behind a Flatten of a map)
 
 
 @dataclass
@@ -169,7 +170,7 @@ class Graph:
             if op.kind == "site":
                 prod = producer.get(op.src.id)
                 if (prod is not None and prod.kind == "conv" and prod.site is None and op.src.stoch
-                        and uses.get(op.src.id, 0) == 1):
+                        and uses.get(op.src.id, 0) == 1 and not op.site.nchw_flat):
                     prod.site = op.site
                     prod.dst = op.dst           # conv now writes the masked tensor
                     producer[op.dst.id] = prod
@@ -536,6 +537,7 @@ class Engine:
             d.batch = B
             return d
         d.kind = KINDS[op_site.kind]
+        d.nchw_flat = int(op_site.nchw_flat)
         d.p = op_site.p
         d.seed = seed & 0xFFFFFFFFFFFFFFFF
         d.stream_id = op_site.stream

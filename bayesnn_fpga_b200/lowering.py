@@ -63,6 +63,7 @@ class _Lowering:
         self.exit_of = {}          # fx node -> exit index of the head that produces it
         self.nonneg = set()        # ids of lowered tensors known to be >= 0 (a ReLU on them is the identity)
         self.pool_relu_done = set()   # ReLU nodes already applied in front of the max-pool / site chain they follow
+        self.flat_nodes = set()       # fx nodes holding a FLATTENED view of a spatial (H*W > 1) map
 
     # ---- node classification -----------------------------------------------------------------
     def _mod(self, node):
@@ -95,8 +96,15 @@ class _Lowering:
         raise NotImplementedError("cannot lower node %r (%s %s): %s" % (node.name, node.op, node.target, why))
 
     # ---- sites ---------------------------------------------------------------------------------
-    def _site(self, t, module, kind, p, name):
+    def _site(self, t, module, kind, p, name, node=None):
+        flat = node is not None and bool(node.all_input_nodes) and node.all_input_nodes[0] in self.flat_nodes
+        if flat and kind != "mc":
+            self._fail(node, "a %s site behind a Flatten of a %dx%d map (only element-wise dropout is supported there)" % (
+                kind, t.H, t.W))
         dst = self.g.site(t, kind, p, module=module if kind == "mask" else None, name=name)
+        self.g.sites[-1].nchw_flat = flat     # masks indexed like a stand-alone call on the flattened tensor would
+        if flat:
+            self.flat_nodes.add(node)
         self._bind(self.g.sites[-1], module)
         if t.id in self.nonneg:
             self.nonneg.add(dst.id)            # mask multipliers are >= 0
@@ -286,20 +294,25 @@ class _Lowering:
                 else:
                     self._fail(node, "a ReLU must follow a convolution, a Linear or a max-pool of a convolution")
             elif _is_mc_module(m):                               # (a subclass of nn.Dropout: test it first)
-                self.val[node] = self._site(self.val[node.args[0]], m, "mc", m.p, node.name)
+                self.val[node] = self._site(self.val[node.args[0]], m, "mc", m.p, node.name, node)
             elif node.op == "call_function" and node.target is F.dropout:
                 a = list(node.args) + [None] * 4
                 p_ = node.kwargs.get("p", a[1] if a[1] is not None else 0.5)
                 training = node.kwargs.get("training", a[2] if a[2] is not None else True)
                 src = self.val[node.args[0]]
-                self.val[node] = self._site(src, None, "mc", float(p_), node.name) if training else src
+                self.val[node] = self._site(src, None, "mc", float(p_), node.name, node) if training else src
             elif isinstance(m, (nn.Dropout, nn.Dropout2d, nn.Identity)):
                 self.val[node] = self.val[node.args[0]]          # eval-mode no-ops
+                if node.args[0] in self.flat_nodes:
+                    self.flat_nodes.add(node)
             elif _is_masksembles(m):
-                self.val[node] = self._site(self.val[node.args[0]], m, "mask", 0.0, node.name)
+                self.val[node] = self._site(self.val[node.args[0]], m, "mask", 0.0, node.name, node)
             elif isinstance(m, nn.Flatten) or (node.op == "call_function" and node.target in _FLATTEN_FNS) or \
                     (node.op == "call_method" and node.target in ("flatten", "view", "reshape")):
                 self.val[node] = self.val[node.args[0]]          # g.linear flattens in NCHW order itself
+                v_ = self.val[node]
+                if v_ is not None and (v_.H * v_.W > 1 or node.args[0] in self.flat_nodes):
+                    self.flat_nodes.add(node)
             elif isinstance(m, (nn.AdaptiveAvgPool2d, nn.AvgPool2d)) or \
                     (node.op == "call_function" and node.target in (F.avg_pool2d, F.adaptive_avg_pool2d)):
                 src = self.val[node.args[0]]

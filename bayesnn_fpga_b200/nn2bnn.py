@@ -35,12 +35,94 @@ def _convert_model(model, p):
     return model
 
 
-class MCDropout(nn.Module):
-    """Monte-Carlo-dropout wrapper: training -> one stochastic pass; eval -> mean of ``nSamples`` passes."""
+# ---- insertion strategies (the Keras converter's, Hardware_Artifact/converter/keras/nn2bnn.py:9-72, for PyTorch) -------
+def _leaves(model):
+    """(parent, attribute name, module) of every leaf module in registration order = `model.layers` of a Keras
+    Sequential / functional model."""
+    out = []
+    for parent in model.modules():
+        for name, child in parent.named_children():
+            if next(child.children(), None) is None:
+                out.append((parent, name, child))
+    return out
 
-    def __init__(self, model, nSamples=10, p=0.5, dtype="fp32", fused=True):
+
+def _is_weight_layer(m):
+    return type(m) is nn.Conv2d or isinstance(m, nn.Linear)        # `type(layer) in conv_list or isinstance(layer, Dense)`
+
+
+def _default_strategy(layers, num=1):
+    """A Bayesian layer in front of each of the LAST `num` dense / conv layers (:9-29)."""
+    pos = [i - 1 for i, m in enumerate(layers) if _is_weight_layer(m)]
+    return pos[max(0, len(pos) - num):]
+
+
+def _last_strategy(layers, num=1):
+    """`num` Bayesian layers going backward from the input of the first dense layer behind the last conv layer (:31-59)."""
+    after_conv, last_conv, count = False, -1, -1
+    for i, m in enumerate(layers):
+        if type(m) is nn.Conv2d:
+            last_conv, after_conv = i, True
+        if isinstance(m, nn.Linear) and after_conv:
+            count, after_conv = i - 1, False
+    if last_conv < 0:
+        return []
+    if count < 0:
+        count = last_conv
+    pos = []
+    while num > 0 and count >= 0:
+        pos.append(count)
+        count -= 1
+        num -= 1
+    return pos
+
+
+def _full_strategy(layers, num=None):
+    """A Bayesian layer in front of every dense / conv layer (:61-72)."""
+    return [i - 1 for i, m in enumerate(layers) if _is_weight_layer(m)]
+
+
+strategy_fn = {"default": _default_strategy, "last": _last_strategy, "full": _full_strategy}
+
+
+def convert_model(model, strategy="default", num=1, type="BayesianDropout", p=0.5, n=4, scale=2.0):
+    """Insert Bayesian layers into `model` (in place) with one of the Keras converter's strategies.  Position k means
+    "behind layer k" exactly as there (`supported_layers[k]`, :120-128), i.e. in front of layer k + 1, which is replaced
+    by ``nn.Sequential(site, layer)``; a position in front of the first layer is ignored like in the reference.
+    type: "BayesianDropout" (element-wise MC dropout, converter/keras/MCDropout.py:37-38) or "Masksembles" (n masks,
+    `scale`; the mask width is the consuming layer's input width)."""
+    from .Dropouts import MCDropout as _Site
+    from .utils import Masksembles1D, Masksembles2D
+    if strategy not in strategy_fn:
+        raise ValueError("unknown strategy %r (expected one of %s)" % (strategy, sorted(strategy_fn)))
+    if type not in ("BayesianDropout", "Masksembles"):
+        raise Exception("The type %s is not supported yet!" % type)
+    leaves = _leaves(model)
+    layers = [m for _, _, m in leaves]
+    for k in sorted(set(strategy_fn[strategy](layers, num))):
+        if k < 0 or k + 1 >= len(leaves):
+            continue
+        parent, name, layer = leaves[k + 1]
+        if type == "BayesianDropout":
+            site = _Site(p)
+        elif isinstance(layer, nn.Conv2d):
+            site = Masksembles2D(layer.in_channels, n, scale)
+        elif isinstance(layer, nn.Linear):
+            site = Masksembles1D(layer.in_features, n, scale)
+        else:
+            raise ValueError("Masksembles in front of %s: the channel count is not known" % layer.__class__.__name__)
+        setattr(parent, name, nn.Sequential(site, layer))
+    return model
+
+
+class MCDropout(nn.Module):
+    """Monte-Carlo-dropout wrapper: training -> one stochastic pass; eval -> mean of ``nSamples`` passes.
+    ``strategy`` (None | "default" | "last" | "full", with ``num``) selects the Keras converter's insertion strategies
+    instead of the PyTorch converter's wrap-every-leaf rule."""
+
+    def __init__(self, model, nSamples=10, p=0.5, dtype="fp32", fused=True, strategy=None, num=1):
         super().__init__()
-        self.model = _convert_model(model, p)
+        self.model = _convert_model(model, p) if strategy is None else convert_model(model, strategy, num, p=p)
         self.nSamples = nSamples
         self.p = p
         self.bnn_dtype = dtype          # "fp32": exact CUDA-core path; "fp16" / "bf16": tensor cores

@@ -105,6 +105,10 @@ typedef struct bnn_drop_desc {
   const int16_t* compact_pos;
   const int16_t* compact_idx;
   int compact_c;
+  /* ELEMENT, bnn_dropout only: the site follows a Flatten of a C x H x W map (`x.view(B, -1)` then dropout): element
+   * indices of the mask stream follow the reference's NCHW-flattened order b*C*HW + c*HW + pixel instead of the
+   * buffer's NHWC order, so the fused run draws the masks a stand-alone call on the flattened tensor would. */
+  int nchw_flat;
 } bnn_drop_desc;
 
 int bnn_conv2d_simt(const void* x, const float* w, const float* bias, const void* res, void* y, int dtype, int N,

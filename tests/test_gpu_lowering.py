@@ -138,3 +138,29 @@ def test_reference_style_model_object_runs_unmodified(dtype, tol):
         err = (r.mean_logits[e].double().cpu() - w).abs().max().item()
         report(test="reference_style_model", dtype=dtype, exit=e, err=err, scale=scale)
         assert err <= tol * scale
+
+
+def test_keras_style_strategy_conversion_runs_fused():
+    """nn2bnn.MCDropout(model, strategy="default", num=2): dropout in front of the last two Linear layers only - the
+    convolutional prefix runs once per image; result == float64 reference with the same injected masks."""
+    torch.manual_seed(7)
+    S, seed, B = 6, 31, 4
+    net = nn.Sequential(nn.Conv2d(3, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(),
+                        nn.Flatten(), nn.Linear(32 * 4 * 4, 64), nn.ReLU(), nn.Linear(64, 10))
+    bnn = nn2bnn.MCDropout(copy.deepcopy(net), nSamples=S, p=0.25, strategy="default", num=2).reseed(seed).cuda().eval()
+    layers, sites = [], []
+    for m in bnn.model:
+        if isinstance(m, nn.Sequential):
+            d = InjectedDropout(m[0].p, m[0].bnn_stream, seed)
+            sites.append(d)
+            layers += [d, copy.deepcopy(m[1]).cpu()]
+        else:
+            layers.append(copy.deepcopy(m).cpu())
+    assert len(sites) == 2
+    x = torch.randn(B, 3, 8, 8)
+    want = reference_mean(nn.Sequential(*layers), x, sites, S)[0]
+    got = bnn(x.cuda())
+    eng, _ = bnn._plan((3, 8, 8), x.cuda().device)
+    pre, suf = eng.graph.macs()
+    assert suf == 512 * 64 + 64 * 10 and pre == 8 * 8 * 16 * 27 + 4 * 4 * 32 * 144   # the convolutions are paid once, not S times
+    assert (got.double().cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())

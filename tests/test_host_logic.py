@@ -313,3 +313,33 @@ def test_head_pool_fusion_pass():
             assert (o.src.H, o.src.W) == (1, 1)
     g.fuse_sibling_convs(lambda op: True)
     assert [len(o.members) for o in g.ops if o.kind == "convg"] == [2, 2, 2]
+
+
+def test_keras_style_insertion_strategies_for_pytorch():
+    """nn2bnn.convert_model mirrors the Keras converter's strategies (converter/keras/nn2bnn.py:9-72): position k =
+    behind layer k; nothing in front of the first layer."""
+    mk = lambda: nn.Sequential(nn.Conv2d(3, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(16, 32, 3, padding=1),
+                               nn.ReLU(), nn.Flatten(), nn.Linear(32 * 4 * 4, 64), nn.ReLU(), nn.Linear(64, 10))
+    layers = list(mk())
+    assert nn2bnn._full_strategy(layers) == [-1, 2, 5, 7]
+    assert nn2bnn._default_strategy(layers, 2) == [5, 7] and nn2bnn._default_strategy(layers, 9) == [-1, 2, 5, 7]
+    assert nn2bnn._last_strategy(layers, 2) == [5, 4] and nn2bnn._last_strategy([nn.ReLU()], 1) == []
+    sited = lambda m: [i for i, l in enumerate(m) if isinstance(l, nn.Sequential)]
+    assert sited(nn2bnn.convert_model(mk(), "full")) == [3, 6, 8]          # never in front of the first layer
+    assert sited(nn2bnn.convert_model(mk(), "default", num=1)) == [8]
+    assert sited(nn2bnn.convert_model(mk(), "last", num=2)) == [5, 6]
+    m = nn2bnn.convert_model(mk(), "default", num=2, p=0.3)
+    assert isinstance(m[6][0], Dropouts.MCDropout) and m[6][0].p == 0.3 and isinstance(m[6][1], nn.Linear)
+    np.random.seed(0)
+    mm = nn2bnn.convert_model(mk(), "full", type="Masksembles", n=4, scale=2.0)
+    assert isinstance(mm[3][0], utils.Masksembles2D) and mm[3][0].channels == 16
+    assert isinstance(mm[6][0], utils.Masksembles1D) and mm[6][0].channels == 512
+    with pytest.raises(ValueError):
+        nn2bnn.convert_model(mk(), "last", num=2, type="Masksembles")      # in front of Flatten: width unknown
+    with pytest.raises(ValueError):
+        nn2bnn.convert_model(mk(), "nope")
+    # the converted network lowers to a prefix / suffix plan: everything in front of the first site is deterministic
+    from bayesnn_fpga_b200 import lowering
+    g, sites = lowering.lower_module(nn2bnn.MCDropout(mk(), nSamples=4, p=0.25, strategy="default", num=2).model, (3, 8, 8))
+    pre, suf = g.macs()
+    assert len(sites) == 2 and suf == 512 * 64 + 64 * 10 and pre == 8 * 8 * 16 * 27 + 4 * 4 * 32 * 144
