@@ -8,7 +8,9 @@ Drop-in for the PyTorch half of os-hxfan/BayesNN_FPGA on this path (see INTEGRAT
     .../models/vgg19/vgg19.py                          bayesnn_fpga_b200.vgg19
     .../train/results_analyzer.py (FullAnalysis)       bayesnn_fpga_b200.results_analyzer
     Hardware_Artifact/converter/pytorch/Dropouts.py    bayesnn_fpga_b200.Dropouts
-    Hardware_Artifact/converter/pytorch/nn2bnn.py      bayesnn_fpga_b200.nn2bnn
+    .../models/model_loader.py (get_network)           bayesnn_fpga_b200.model_loader
+    Hardware_Artifact/converter/pytorch/nn2bnn.py      bayesnn_fpga_b200.nn2bnn  (+ the Keras converter's strategies)
+    any other nn.Module / the reference's own models   bayesnn_fpga_b200.lowering (traced with torch.fx)
     bayes_hw/models/t_qmodels_bayes_me.py (LeNet spec) bayesnn_fpga_b200.lenet
 
 All arithmetic runs in the sm_100a kernels behind include/bnn_b200.h; there is no CPU fallback.

@@ -343,3 +343,25 @@ def test_keras_style_insertion_strategies_for_pytorch():
     g, sites = lowering.lower_module(nn2bnn.MCDropout(mk(), nSamples=4, p=0.25, strategy="default", num=2).model, (3, 8, 8))
     pre, suf = g.macs()
     assert len(sites) == 2 and suf == 512 * 64 + 64 * 10 and pre == 8 * 8 * 16 * 27 + 4 * 4 * 32 * 144
+
+
+def test_get_network_factory(tmp_path):
+    """model_loader.get_network (models/model_loader.py:8-23): factories by `call` / `resnet_type`, pickled models by
+    `load_model`, AttributeError otherwise."""
+    from bayesnn_fpga_b200 import model_loader
+    hp = dict(call="ResNet18", load_model=None, resnet_type="mc_early_exit", dropout_exit=True, dropout="block",
+              dropout_p=0.25, n_exits=4, out_dim=10)
+    m = model_loader.get_network(hp)
+    assert type(m).__name__ == "ResNet18MCEarlyExit" and m.dropout_p == 0.25 and m.out_dim == 10
+    v = model_loader.get_network(dict(call="VGG19", load_model=None, resnet_type="mc_early_exit", dropout_exit=True,
+                                      dropout=None, dropout_p=0.5, n_exits=5, out_dim=100, image_size=32))
+    assert type(v).__name__ == "VGG19MCEarlyExit" and v.out_dim == 100
+    assert type(model_loader.get_network(dict(call="ResNet18", load_model=None, resnet_type=None, out_dim=10))).__name__ \
+        == "ResNet18Base"
+    with pytest.raises(AttributeError):
+        model_loader.get_network(dict(call="LeNet", load_model=None, resnet_type=None))
+    path = str(tmp_path / "m.pt")
+    torch.save(m, path)
+    again = model_loader.get_network(dict(call="ResNet18", load_model=path, resnet_type="mc_early_exit"))
+    assert type(again).__name__ == "ResNet18MCEarlyExit"
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), again.state_dict().values()))
