@@ -365,3 +365,25 @@ def test_get_network_factory(tmp_path):
     again = model_loader.get_network(dict(call="ResNet18", load_model=path, resnet_type="mc_early_exit"))
     assert type(again).__name__ == "ResNet18MCEarlyExit"
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), again.state_dict().values()))
+
+
+def test_drop_desc_struct_layout_matches_the_c_header(tmp_path):
+    """ctypes `DropDesc` == `struct bnn_drop_desc` of include/bnn_b200.h as a C compiler lays it out (size and every
+    field offset); the header itself must compile as plain C."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [f[0] for f in _lib.DropDesc._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "bnn_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(bnn_drop_desc));\n' +
+                   "".join('  printf("%%zu\\n", offsetof(bnn_drop_desc, %s));\n' % f for f in fields) +
+                   "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.DropDesc)
+    assert out[1:] == [getattr(_lib.DropDesc, f).offset for f in fields]
