@@ -244,13 +244,17 @@ class ResNet18MCEarlyExit(ResNet, _ResNet18MCMixin):
         self._install_sites(multi_exit=True)
 
 
+_MC_ONLY_KWARGS = ("dropout", "dropout_exit", "dropout_p", "mask_type", "num_masks", "mask_scale")
+
+
 def get_res_net_18(network_type, hyperparams):
-    """resnet18_loader.py:4-15."""
+    """resnet18_loader.py:4-15.  Like the reference: ``None`` and "early_exit" both build ``ResNet18EarlyExit`` and
+    drop the six MC-only keys of a full hyper-parameter dict; "mc" / "mc_early_exit" keep them."""
     from .utils import dict_drop
     kw = dict_drop(hyperparams, "call", "load_model", "resnet_type")
-    if network_type is None:
-        return ResNet18Base(**kw)
-    table = {"early_exit": ResNet18EarlyExit, "mc": ResNet18MC, "mc_early_exit": ResNet18MCEarlyExit}
+    if network_type is None or network_type == "early_exit":
+        return ResNet18EarlyExit(**dict_drop(kw, *_MC_ONLY_KWARGS))
+    table = {"mc": ResNet18MC, "mc_early_exit": ResNet18MCEarlyExit}
     if network_type not in table:
         raise ValueError("unknown resnet type %r" % (network_type,))
     return table[network_type](**kw)

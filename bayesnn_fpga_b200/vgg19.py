@@ -207,10 +207,16 @@ class VGG19MCEarlyExit(VGG19EarlyExit):
             raise NotImplementedError('VGG dropout=%r is not constructible in the reference either' % (self.dropout,))
 
 
+_MC_ONLY_KWARGS = ("dropout", "dropout_exit", "dropout_p", "mask_type", "num_masks", "mask_scale")
+
+
 def get_vgg_19(network_type, hyperparams):
-    """vgg19.py:16-42."""
+    """vgg19.py:16-42.  The plain and "early_exit" classes are built without the six MC-only keys of a full
+    hyper-parameter dict, like the reference."""
     kw = dict_drop(hyperparams, "call", "load_model", "resnet_type")
     table = {None: VGG19, "early_exit": VGG19EarlyExit, "mc": VGG19MC, "mc_early_exit": VGG19MCEarlyExit}
     if network_type not in table:
         raise ValueError("unknown vgg type %r" % (network_type,))
+    if network_type in (None, "early_exit"):
+        kw = dict_drop(kw, *_MC_ONLY_KWARGS)
     return table[network_type](**kw)

@@ -356,8 +356,23 @@ def test_get_network_factory(tmp_path):
     v = model_loader.get_network(dict(call="VGG19", load_model=None, resnet_type="mc_early_exit", dropout_exit=True,
                                       dropout=None, dropout_p=0.5, n_exits=5, out_dim=100, image_size=32))
     assert type(v).__name__ == "VGG19MCEarlyExit" and v.out_dim == 100
+    # resnet18_loader.py:5-8: None builds the multi-exit class too (4 outputs), not ResNet18Base
     assert type(model_loader.get_network(dict(call="ResNet18", load_model=None, resnet_type=None, out_dim=10))).__name__ \
-        == "ResNet18Base"
+        == "ResNet18EarlyExit"
+    # the reference's drivers always pass the FULL hyper-parameter dict (train/hyperparameters.py:86-109 + main.py's
+    # mask keys): the plain / early-exit classes must be built with the six MC-only keys stripped
+    full = dict(load_model=None, out_dim=100, dropout=None, dropout_exit=False, dropout_p=0.5, n_exits=4,
+                mask_type="mc", num_masks=4, mask_scale=4.0)
+    for call, rtype, want, n_out in (("ResNet18", "early_exit", "ResNet18EarlyExit", 4),
+                                     ("ResNet18", None, "ResNet18EarlyExit", 4),
+                                     ("VGG19", "early_exit", "VGG19EarlyExit", 5), ("VGG19", None, "VGG19", 1)):
+        hp_full = dict(full, call=call, resnet_type=rtype, n_exits=n_out, image_size=32) if call == "VGG19" else \
+            dict(full, call=call, resnet_type=rtype)
+        net = model_loader.get_network(hp_full)
+        assert type(net).__name__ == want and net.out_dim == 100
+        assert net._bnn_graph().n_exits == n_out
+    mc = model_loader.get_network(dict(full, call="ResNet18", resnet_type="mc", dropout_exit=True, n_exits=1))
+    assert type(mc).__name__ == "ResNet18MC" and mc.dropout_exit
     with pytest.raises(AttributeError):
         model_loader.get_network(dict(call="LeNet", load_model=None, resnet_type=None))
     path = str(tmp_path / "m.pt")
