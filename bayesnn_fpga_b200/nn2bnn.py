@@ -9,8 +9,10 @@ the intended semantics - mean over ``nSamples`` stochastic passes of the RAW mod
 Eval mode runs the converted network through the fused plan (``lowering.lower_module`` -> ``engine.Engine``): the
 layers in front of the first wrapped leaf once per image, the rest once per sample, the mean accumulated on the
 device.  The masks are the ones ``nSamples`` successive stand-alone forward calls would draw (every wrapper keeps its
-own Philox stream and call counter), so both forms agree to rounding.  A network the lowering cannot express falls
-back - with a warning - to those stand-alone calls (each leaf through torch, each dropout through ``bnn_dropout``).
+own Philox stream and call counter), so both forms agree to rounding.  A network the lowering cannot express RAISES
+(``NotImplementedError`` naming the construct): there is no silent library path.  ``eager_fallback=True`` opts in to the
+reference's literal loop instead - ``nSamples`` stand-alone calls, each leaf through torch (cuBLAS / cuDNN) and each
+dropout through ``bnn_dropout`` - with a warning.
 """
 import warnings
 
@@ -120,32 +122,35 @@ class MCDropout(nn.Module):
     ``strategy`` (None | "default" | "last" | "full", with ``num``) selects the Keras converter's insertion strategies
     instead of the PyTorch converter's wrap-every-leaf rule."""
 
-    def __init__(self, model, nSamples=10, p=0.5, dtype="fp32", fused=True, strategy=None, num=1):
+    def __init__(self, model, nSamples=10, p=0.5, dtype="fp32", fused=True, strategy=None, num=1,
+                 eager_fallback=False):
         super().__init__()
         self.model = _convert_model(model, p) if strategy is None else convert_model(model, strategy, num, p=p)
         self.nSamples = nSamples
         self.p = p
         self.bnn_dtype = dtype          # "fp32": exact CUDA-core path; "fp16" / "bf16": tensor cores
-        self.bnn_fused = fused
-        self.__dict__["_bnn_plans"] = {}
-
-    def train(self, mode=True):
-        self.__dict__["_bnn_plans"] = {}      # parameters may change while training: re-plan at the next eval
-        return super().train(mode)
+        self.bnn_fused = fused          # False: the stand-alone loop, explicitly requested
+        self.bnn_eager_fallback = eager_fallback
 
     def _site_modules(self):
         return [m for m in self.model.modules() if hasattr(m, "bnn_calls")]
 
     def _plan(self, shape, device):
         """(engine, site modules) for inputs [B, *shape], or None when the network cannot be lowered."""
-        key = (tuple(shape), self.bnn_dtype, str(device))
-        plans = self.__dict__["_bnn_plans"]
+        from . import _plans
+        key = ("nn2bnn", tuple(shape), self.bnn_dtype, str(device))
+        plans = _plans.plans_for(self)       # outside the module (picklable), dropped when the parameters change
         if key not in plans:
             from . import engine, lowering
             try:
                 graph, sites = lowering.lower_module(self.model, shape)
                 plans[key] = (engine.Engine(graph, dtype=self.bnn_dtype, device=device), [m for _, m in sites])
             except NotImplementedError as e:
+                if not self.bnn_eager_fallback:
+                    raise NotImplementedError(
+                        "nn2bnn.MCDropout: this network cannot be lowered to the fused B200 plan (%s). Pass "
+                        "eager_fallback=True to run %d stand-alone passes through torch's own layers instead." % (
+                            e, self.nSamples)) from e
                 warnings.warn("nn2bnn.MCDropout: running %d stand-alone passes instead of the fused plan: %s" % (
                     self.nSamples, e))
                 plans[key] = None

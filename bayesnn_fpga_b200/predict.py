@@ -35,7 +35,7 @@ def allreduce_sums(flat, group=None):
 
 
 def _generic_engine(model, x, dtype, engine_kwargs):
-    """Plan for an arbitrary nn.Module (lowering.lower_module), cached on the module per input shape / dtype."""
+    """Plan for an arbitrary nn.Module (lowering.lower_module), cached per (model, input shape, dtype) in `_plans`."""
     from . import engine, lowering
     flat = x.dim() == 2
     shape = (int(x.shape[1]), 1, 1) if flat else tuple(int(v) for v in x.shape[1:])
@@ -43,8 +43,9 @@ def _generic_engine(model, x, dtype, engine_kwargs):
     if dev.type != "cuda":
         raise RuntimeError("bayesnn_fpga_b200 runs on a CUDA (sm_100) device only; there is no CPU fallback - call "
                            "model.cuda() first")
-    cache = model.__dict__.setdefault("_bnn_generic_engines", {})
-    key = (shape, dtype, tuple(sorted((engine_kwargs or {}).items())))
+    from . import _plans
+    cache = _plans.plans_for(model)          # kept outside the (foreign) module; re-validated against its parameters
+    key = ("generic", shape, dtype, tuple(sorted((engine_kwargs or {}).items())))
     if key not in cache:
         graph, _ = lowering.lower_module(model, shape)
         cache[key] = engine.Engine(graph, dtype=dtype or "fp16", device=dev, **(engine_kwargs or {}))

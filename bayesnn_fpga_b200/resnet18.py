@@ -14,6 +14,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import _plans
 from . import engine as _engine
 from .Dropouts import MCDropout
 from .utils import Masksembles1D, Masksembles2D
@@ -56,21 +57,21 @@ class _BnnModel(nn.Module):
         raise NotImplementedError
 
     def bnn_engine(self, dtype=None, rebuild=False, **kw):
-        """Plan (fold BN, pack weights, fuse sites) for the current parameters; cached per dtype."""
+        """Plan (fold BN, pack weights, fuse sites) for the current parameters; cached per dtype in ``_plans`` (outside
+        the module, so ``torch.save(model)`` / ``copy.deepcopy(model)`` keep working after a run) and rebuilt whenever
+        the parameters, buffers or sub-modules changed since it was made."""
         dtype = dtype or self.bnn_dtype
-        cache = self.__dict__.setdefault("_bnn_engines", {})
+        if rebuild:
+            _plans.drop(self)
+        cache = _plans.plans_for(self)
         key = (dtype, tuple(sorted(kw.items())))
-        if rebuild or key not in cache:
+        if key not in cache:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("bayesnn_fpga_b200 models run on a CUDA (sm_100) device only; there is no "
                                    "CPU fallback - call model.cuda() first")
             cache[key] = _engine.Engine(self._bnn_graph(), dtype=dtype, device=dev, **kw)
         return cache[key]
-
-    def load_state_dict(self, *a, **k):
-        self.__dict__.pop("_bnn_engines", None)      # weights changed: re-plan lazily
-        return super().load_state_dict(*a, **k)
 
     def forward(self, x):
         """One stochastic forward pass -> list of E logits tensors [B, out_dim]."""

@@ -80,8 +80,7 @@ class VGG(_BnnModel):
         ``for i in (2,3,4): m.blocks[i].append(MCDropout(p))`` used for BASELINE config 4."""
         for i in block_indices:
             self.blocks[i].append(module_factory() if module_factory else MCDropout(self.dropout_p))
-        self.__dict__.pop("_bnn_engines", None)
-        return self
+        return self                              # (plans re-validate themselves: _plans.fingerprint sees the new module)
 
     # ---- lowering ---------------------------------------------------------------------------
     def _lower_block(self, g, t, b):

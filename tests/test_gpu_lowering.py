@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn as nn
 
-from bayesnn_fpga_b200 import mc_predict, nn2bnn
+from bayesnn_fpga_b200 import _plans, mc_predict, nn2bnn
 from bayesnn_fpga_b200.Dropouts import BayesianDropout, BayesianDropout2D, MCDropout
 from tests.gpu_util import report
 from tests.nets_generic import InjectedDropout, SmallResNet, plain_cnn, randomize_bn, reference_mean
@@ -88,7 +88,7 @@ def test_residual_network_with_sites_vs_injected_reference(dtype, tol):
     x = torch.randn(B, 3, 16, 16)
     want = reference_mean(ref, x, ref_sites, S)
     r = mc_predict(model, x.cuda(), S, seed=seed, dtype=dtype)
-    eng = model.__dict__["_bnn_generic_engines"][((3, 16, 16), dtype, ())]
+    eng = _plans.plans_for(model)[("generic", (3, 16, 16), dtype, ())]
     pre, suf = eng.graph.macs()
     assert pre > 0 and suf > 0 and eng.graph.out_order == [0, 1]
     for e, w in enumerate(want):
@@ -130,7 +130,7 @@ def test_reference_style_model_object_runs_unmodified(dtype, tol):
     x = torch.randn(B, 3, 16, 16)
     want = reference_mean(ref, x, ref_sites, S)
     r = mc_predict(model, x.cuda(), S, seed=seed, dtype=dtype)
-    eng = model.__dict__["_bnn_generic_engines"][((3, 16, 16), dtype, ())]
+    eng = _plans.plans_for(model)[("generic", (3, 16, 16), dtype, ())]
     assert [s.stream for s in eng.graph.sites] == [0, 1, 2] and eng.graph.n_exits == 2
     assert sum(o.kind == "head" for o in eng.graph.ops) == 2 and not any(getattr(o, "is_gap", False) for o in eng.graph.ops)
     for e, w in enumerate(want):

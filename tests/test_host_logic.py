@@ -402,3 +402,39 @@ def test_drop_desc_struct_layout_matches_the_c_header(tmp_path):
     out = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == ctypes.sizeof(_lib.DropDesc)
     assert out[1:] == [getattr(_lib.DropDesc, f).offset for f in fields]
+
+
+def test_plans_live_outside_the_module_and_follow_the_parameters(tmp_path):
+    """Plans (ctypes handles, CUDA graphs, device buffers) are kept in `_plans`, never in a module's __dict__: a model
+    that has run still pickles (`torch.save(model)` is how the reference stores networks, model_loader.py:9-17) and
+    deep-copies; and a plan is dropped as soon as the model it was built from changes."""
+    import copy
+    from bayesnn_fpga_b200 import _plans, resnet18
+    m = resnet18.ResNet18MCEarlyExit(dropout_exit=True, dropout="block", out_dim=10)
+    plans = _plans.plans_for(m)
+    plans["x"] = ctypes.CDLL(None).printf            # as un-picklable as an Engine (a ctypes function pointer)
+    assert _plans.plans_for(m) is plans and "x" in _plans.plans_for(m)
+    assert not any(k.startswith("_bnn") for k in m.__dict__)
+    torch.save(m, str(tmp_path / "ran.pt"))
+    m2 = copy.deepcopy(m)
+    assert _plans.plans_for(m2) == {}                 # the copy plans for itself
+    # every way the reference's drivers change a model invalidates the plan
+    with torch.no_grad():
+        m.layer1[0][0].conv1.weight.mul_(1.5)         # in-place update (an optimiser step)
+    assert "x" not in _plans.plans_for(m)
+    _plans.plans_for(m)["x"] = 1
+    m.layer2.load_state_dict(m.layer2.state_dict())   # load_state_dict on a SUB-module
+    assert "x" not in _plans.plans_for(m)
+    _plans.plans_for(m)["x"] = 1
+    m.bn1.running_mean.add_(0.1)                      # a buffer
+    assert "x" not in _plans.plans_for(m)
+    _plans.plans_for(m)["x"] = 1
+    m.layer1.append(resnet18.MCDropout(0.1))          # structure: the reference idiom `blocks[i].append(MCDropout(p))`
+    assert "x" not in _plans.plans_for(m)
+    _plans.plans_for(m)["x"] = 1
+    m.double()                                        # .to(dtype / device): new storage
+    assert "x" not in _plans.plans_for(m)
+    _plans.plans_for(m)["x"] = 1
+    assert "x" in _plans.plans_for(m)                 # and an untouched model keeps its plans
+    _plans.drop(m)
+    assert _plans.plans_for(m) == {}
