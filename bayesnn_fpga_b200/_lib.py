@@ -11,14 +11,13 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libbnn_b200.so")
-SOURCES = ["kernels_simt.cu", "kernels_head.cu", "conv_tc.cu"]
+SOURCES = ["kernels_simt.cu", "kernels_head.cu", "kernels_stats.cu", "conv_tc.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "../../include/bnn_b200.h"]
 
 F32, F16, BF16 = 0, 1, 2
 DROP_NONE, DROP_ELEMENT, DROP_CHANNEL, DROP_MASKSEMBLES = 0, 1, 2, 3
+CAL_TOP, CAL_TOP_NORM, CAL_TFP_RESOFTMAX = 0, 1, 2
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 
 class DropDesc(ctypes.Structure):
@@ -30,30 +29,56 @@ class DropDesc(ctypes.Structure):
                 ("nchw_flat", ctypes.c_int)]
 
 
+OBJ_DIR = os.path.join(CSRC, "build")
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _newer(path, t):
+    return os.path.exists(path) and os.path.getmtime(path) > t
+
+
+def _obj_stale(src, obj):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return _newer(src, t) or any(_newer(os.path.join(CSRC, h), t) for h in HEADERS)
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+    return any(_newer(os.path.join(CSRC, f), t) for f in SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into csrc/libbnn_b200.so (nvcc cross-compiles
-    without a GPU).  Returns the library path."""
+    """Compile every CUDA source for sm_100a into csrc/libbnn_b200.so (nvcc cross-compiles without a GPU): one
+    object per source, stale ones recompiled in parallel, then one link.  Returns the library path."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + srcs + ["-o", LIB_PATH]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs, objs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s[:-3] + ".o")
+        if not os.path.exists(src):
+            raise RuntimeError("missing CUDA source %s" % src)
+        objs.append(obj)
+        if force or _obj_stale(src, obj):
+            cmd = [nvcc] + COMPILE_FLAGS + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]
     if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        print(" ".join(link), file=sys.stderr)
+    r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+        raise RuntimeError("nvcc link failed:\n%s\n%s" % (r.stdout, r.stderr))
     return LIB_PATH
 
 
@@ -81,8 +106,8 @@ _SIGS = {
     "bnn_conv2d_tc_gathered": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32] +
                                [ctypes.c_int] * 10 + [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "bnn_confidence_exit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 4),
-    "bnn_top_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4),
+                                           ctypes.c_double, ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "bnn_top_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4),
     "bnn_kde_triweight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
@@ -99,7 +124,7 @@ _SIGS = {
                                    ctypes.c_void_p]),
     "bnn_finalize": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 8),
     "bnn_calibration_bins": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p]),
     "bnn_dataset_metrics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -421,199 +421,6 @@ __global__ void finalize_entropy_kernel(const float* __restrict__ mean_p, const 
   exp_entropy[i] = -sum_plogp[i] * inv_s;
 }
 
-__global__ void calibration_kernel(const float* __restrict__ probs, const int32_t* __restrict__ labels, int N, int C,
-                                   int n_bins, float* __restrict__ conf, int32_t* __restrict__ correct,
-                                   float* __restrict__ bin_stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const float* p = probs + (size_t)i * C;
-  int best = 0;
-  float bp = p[0];
-  for (int c = 1; c < C; ++c)
-    if (p[c] > bp) {   // first maximum wins, like np.argmax
-      bp = p[c];
-      best = c;
-    }
-  const int hit = best == labels[i];
-  conf[i] = bp;
-  correct[i] = hit;
-  int bin = (int)ceilf(bp * (float)n_bins) - 1;
-  bin = max(0, min(n_bins - 1, bin));
-  atomicAdd(&bin_stats[bin * 3 + 0], 1.f);
-  atomicAdd(&bin_stats[bin * 3 + 1], bp);
-  atomicAdd(&bin_stats[bin * 3 + 2], (float)hit);
-}
-
-
-// ---- confidence-threshold early exiting (results_analyzer.py:606-631, :728-735) ----------------------------------
-// Image i leaves at the first exit e in [first_exit, E) whose mean prediction is confident - max p > threshold, or
-// (diff) top1 - top2 > threshold - and at exit E-1 otherwise.  One thread per image.
-__global__ void confidence_exit_kernel(const float* __restrict__ probs, int E, int N, int C, int first_exit,
-                                       float threshold, int diff, int32_t* __restrict__ exit_idx,
-                                       float* __restrict__ best, int32_t* __restrict__ hist) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  int chosen = E - 1;
-  for (int e = first_exit; e < E - 1; ++e) {
-    const float* p = probs + ((size_t)e * N + i) * C;
-    float t1 = -INFINITY, t2 = -INFINITY;
-    for (int c = 0; c < C; ++c) {
-      const float v = p[c];
-      if (v > t1) {
-        t2 = t1;
-        t1 = v;
-      } else if (v > t2) {
-        t2 = v;
-      }
-    }
-    const bool confident = diff ? (fabsf(t1 - t2) > threshold) : (t1 > threshold);
-    if (confident) {
-      chosen = e;
-      break;
-    }
-  }
-  exit_idx[i] = chosen;
-  atomicAdd(&hist[chosen], 1);
-  const float* p = probs + ((size_t)chosen * N + i) * C;
-  for (int c = 0; c < C; ++c) best[(size_t)i * C + c] = p[c];
-}
-
-// ---- KDE-ECE building blocks (results_analyzer.py:351-443) ---------------------------------------------------------
-// Top-label confidence p[argmax] / sum(p), correctness, and the moments of the confidences of the CORRECT images
-// (the bandwidth rule uses their standard deviation, :389-392).  stats: n_correct, sum conf, sum conf^2 (double).
-__global__ void top_label_kernel(const float* __restrict__ probs, const int32_t* __restrict__ labels, int N, int C,
-                                 float* __restrict__ conf, int32_t* __restrict__ correct, double* __restrict__ stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double n1 = 0.0, s1 = 0.0, s2 = 0.0;
-  if (i < N) {
-    const float* p = probs + (size_t)i * C;
-    int best = 0;
-    float bp = p[0];
-    double sum = 0.0;
-    for (int c = 0; c < C; ++c) {
-      const float v = fminf(fmaxf(p[c], 1e-38f), 1.f);    // the reference clips to [1e-256, 1 - 1e-256] in float64
-      sum += (double)v;
-      if (v > bp) {
-        bp = v;
-        best = c;
-      }
-    }
-    const float cf = (float)((double)fminf(fmaxf(bp, 1e-38f), 1.f) / sum);
-    const int hit = best == labels[i];
-    conf[i] = cf;
-    correct[i] = hit;
-    if (hit) {
-      n1 = 1.0;
-      s1 = (double)cf;
-      s2 = (double)cf * (double)cf;
-    }
-  }
-  // warp reduce, one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) {
-    n1 += __shfl_down_sync(0xffffffffu, n1, o);
-    s1 += __shfl_down_sync(0xffffffffu, s1, o);
-    s2 += __shfl_down_sync(0xffffffffu, s2, o);
-  }
-  if ((threadIdx.x & 31) == 0 && n1 > 0.0) {
-    atomicAdd(&stats[0], n1);
-    atomicAdd(&stats[1], s1);
-    atomicAdd(&stats[2], s2);
-  }
-}
-
-// Exact triweight kernel density estimate of the data mirrored about lo and hi (mirror_1d :339-349: points below the
-// midpoint are reflected about lo, the others about hi), evaluated on the grid x0 + j*dx, set to zero outside
-// (lo, hi) and doubled (:403-406) - i.e. (1/n) sum_d [K_h(x - d) + K_h(x - mirror(d))] inside the domain.
-// K_h(u) = (35/32)(1 - (u/h)^2)^3 / h for |u| < h with h = 3*bw (KDEpy: bw is the kernel's standard deviation,
-// triweight variance 1/9).  The reference evaluates the same estimate with KDEpy's FFT approximation.
-// One block per 128 grid points; the data stream through shared memory.
-__global__ void __launch_bounds__(128) kde_triweight_kernel(const float* __restrict__ data,
-                                                            const int32_t* __restrict__ flags, int n, double h,
-                                                            double inv_n, double x0, double dx, int G, double lo,
-                                                            double hi, double* __restrict__ out) {
-  __shared__ float sd[512];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const double x = x0 + (double)j * dx;
-  const bool inside = j < G && x > lo && x < hi;
-  const double inv_h = 1.0 / h, mid = 0.5 * (lo + hi);
-  double acc = 0.0;
-  for (int base = 0; base < n; base += 512) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < 512; t += blockDim.x) {
-      const int i = base + t;
-      // excluded points are parked far outside every kernel support
-      sd[t] = (i < n && (flags == nullptr || flags[i] != 0)) ? data[i] : 1e30f;
-    }
-    __syncthreads();
-    if (inside) {
-      const int m = min(512, n - base);
-      for (int t = 0; t < m; ++t) {
-        const double d = (double)sd[t];
-        if (d > 1e29) continue;
-        const double dm = d < mid ? 2.0 * lo - d : 2.0 * hi - d;
-        double u = (x - d) * inv_h;
-        if (fabs(u) < 1.0) {
-          const double w = 1.0 - u * u;
-          acc += w * w * w;
-        }
-        u = (x - dm) * inv_h;
-        if (fabs(u) < 1.0) {
-          const double w = 1.0 - u * u;
-          acc += w * w * w;
-        }
-      }
-    }
-  }
-  if (j < G) out[j] = inside ? acc * (35.0 / 32.0) * inv_h * inv_n : 0.0;
-}
-
-// per-image NLL / Brier (MSE) / top-1 hit, block-reduced in a fixed order; partial[block][3]
-__global__ void __launch_bounds__(256) dataset_metrics_kernel(const float* __restrict__ probs,
-                                                              const int32_t* __restrict__ labels, int N, int C,
-                                                              float* __restrict__ partial) {
-  __shared__ float sh[3][256];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float nll = 0.f, mse = 0.f, hit = 0.f;
-  if (i < N) {
-    const float* p = probs + (size_t)i * C;
-    const int y = labels[i];
-    int best = 0;
-    float bp = p[0];
-    for (int c = 0; c < C; ++c) {
-      const float v = p[c];
-      const float t = c == y ? 1.f : 0.f;
-      mse += (v - t) * (v - t);
-      if (v > bp) {
-        bp = v;
-        best = c;
-      }
-    }
-    // results_analyzer.py:499-500: clip to [1e-256, 1 - 1e-256] in float64; in float32 the lower clip is the
-    // smallest normal and the upper clip is 1
-    nll = -logf(fmaxf(p[y], 1.17549435e-38f));
-    hit = best == y ? 1.f : 0.f;
-  }
-  sh[0][threadIdx.x] = nll;
-  sh[1][threadIdx.x] = mse;
-  sh[2][threadIdx.x] = hit;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o)
-      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x < 3) partial[blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
-}
-
-__global__ void dataset_metrics_reduce_kernel(const float* __restrict__ partial, int blocks, float inv_n,
-                                              float* __restrict__ out) {
-  const int k = threadIdx.x;
-  if (k >= 3) return;
-  double a = 0.0;
-  for (int b = 0; b < blocks; ++b) a += (double)partial[b * 3 + k];
-  out[k] = (float)(a * inv_n);
-}
-
 }  // namespace bnn
 
 using namespace bnn;
@@ -732,69 +539,6 @@ int bnn_finalize(const float* sum_p, const float* sum_logit, const float* sum_pl
   BNN_LAUNCH_OK();
   finalize_entropy_kernel<<<(E * B + 127) / 128, 128, 0, st>>>(mean_p, ens_p, sum_plogp, E * B, C, inv_s, entropy,
                                                                ens_entropy, exp_entropy);
-  BNN_LAUNCH_OK();
-  return BNN_OK;
-}
-
-int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C, int n_bins, float* conf,
-                         int32_t* correct, float* bin_stats, void* stream) {
-  if (int rc = check_device()) return rc;
-  BNN_REQUIRE(probs && labels && conf && correct && bin_stats && N >= 0 && C > 0 && n_bins > 0,
-              "bnn_calibration_bins: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  BNN_CUDA_OK(cudaMemsetAsync(bin_stats, 0, sizeof(float) * 3 * n_bins, st));
-  if (N == 0) return BNN_OK;
-  calibration_kernel<<<(N + 127) / 128, 128, 0, st>>>(probs, labels, N, C, n_bins, conf, correct, bin_stats);
-  BNN_LAUNCH_OK();
-  return BNN_OK;
-}
-
-int bnn_dataset_metrics(const float* probs, const int32_t* labels, int N, int C, float* workspace, float* out,
-                        void* stream) {
-  if (int rc = check_device()) return rc;
-  BNN_REQUIRE(probs && labels && workspace && out && N > 0 && C > 0, "bnn_dataset_metrics: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = (N + 255) / 256;
-  dataset_metrics_kernel<<<blocks, 256, 0, st>>>(probs, labels, N, C, workspace);
-  BNN_LAUNCH_OK();
-  dataset_metrics_reduce_kernel<<<1, 32, 0, st>>>(workspace, blocks, 1.f / (float)N, out);
-  BNN_LAUNCH_OK();
-  return BNN_OK;
-}
-
-int bnn_confidence_exit(const float* probs, int E, int N, int C, int first_exit, float threshold, int diff,
-                        int32_t* exit_idx, float* best_probs, int32_t* exit_hist, void* stream) {
-  if (int rc = check_device()) return rc;
-  BNN_REQUIRE(probs && exit_idx && best_probs && exit_hist, "bnn_confidence_exit: null pointer");
-  BNN_REQUIRE(E > 0 && N >= 0 && C > 0 && first_exit >= 0 && first_exit < E, "bnn_confidence_exit: bad geometry");
-  cudaStream_t st = (cudaStream_t)stream;
-  BNN_CUDA_OK(cudaMemsetAsync(exit_hist, 0, sizeof(int32_t) * E, st));
-  if (N == 0) return BNN_OK;
-  confidence_exit_kernel<<<(N + 127) / 128, 128, 0, st>>>(probs, E, N, C, first_exit, threshold, diff, exit_idx,
-                                                          best_probs, exit_hist);
-  BNN_LAUNCH_OK();
-  return BNN_OK;
-}
-
-int bnn_top_label(const float* probs, const int32_t* labels, int N, int C, float* conf, int32_t* correct,
-                  double* stats, void* stream) {
-  if (int rc = check_device()) return rc;
-  BNN_REQUIRE(probs && labels && conf && correct && stats && N >= 0 && C > 0, "bnn_top_label: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  BNN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 3, st));
-  if (N == 0) return BNN_OK;
-  top_label_kernel<<<(N + 127) / 128, 128, 0, st>>>(probs, labels, N, C, conf, correct, stats);
-  BNN_LAUNCH_OK();
-  return BNN_OK;
-}
-
-int bnn_kde_triweight(const float* data, const int32_t* flags, int n, double bw, double n_points, double x0,
-                      double dx, int G, double lo, double hi, double* out, void* stream) {
-  if (int rc = check_device()) return rc;
-  BNN_REQUIRE(data && out && n >= 0 && G > 0 && bw > 0.0 && n_points > 0.0 && hi > lo,
-              "bnn_kde_triweight: bad arguments");
-  kde_triweight_kernel<<<(G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(data, flags, n, 3.0 * bw, 1.0 / n_points, x0,
-                                                                          dx, G, lo, hi, out);
   BNN_LAUNCH_OK();
   return BNN_OK;
 }

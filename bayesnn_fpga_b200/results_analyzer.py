@@ -74,25 +74,25 @@ class FullAnalysis:
     def sdn_get_detailed_results(self):
         """Batch loop of :113-177 without the per-sample Python bookkeeping: fills ``preds`` /
         ``ensemble_preds`` [E, N, C], ``labels`` (one-hot [N, C]) and per-exit correct/wrong id sets."""
-        preds, ens, labels = [], [], []
+        preds, ens, labels, top, ens_top = [], [], [], [], []
         for b_x, b_y in self.loader:
-            _, _, sm_np, _, ens_sm = self._get_output(b_x)
+            output, _, sm_np, ens_output, ens_sm = self._get_output(b_x)
             preds.append(sm_np)
             ens.append(np.stack([t.numpy() for t in ens_sm]))
             labels.append(np.asarray(b_y).reshape(-1))
+            # _update_layer_tracker (:273-276) decides correctness from `output[output_id].max(1)`: the argmax of the
+            # MEAN LOGITS over the passes (for ensembles: of the mean over exits of those), not of the mean probabilities
+            top.append(np.stack([t.max(1)[1].numpy() for t in output]))
+            ens_top.append(np.stack([t.max(1)[1].numpy() for t in ens_output]))
         self.preds = np.concatenate(preds, axis=1)
         self.ensemble_preds = np.concatenate(ens, axis=1)
         lab = np.concatenate(labels)
         self.label_index = lab
         self.labels = np.eye(self.model.out_dim)[lab]
-        self.layer_correct, self.layer_wrong = {}, {}
-        self.ensemble_layer_correct, self.ensemble_layer_wrong = {}, {}
-        for e in self.outputs:
-            for src, good, bad in ((self.preds, self.layer_correct, self.layer_wrong),
-                                   (self.ensemble_preds, self.ensemble_layer_correct, self.ensemble_layer_wrong)):
-                hit = src[e].argmax(1) == lab
-                good[e] = set(np.flatnonzero(hit).tolist())
-                bad[e] = set(np.flatnonzero(~hit).tolist())
+        self.layer_predictions = np.concatenate(top, axis=1)                   # [E, N] class index per exit
+        self.ensemble_layer_predictions = np.concatenate(ens_top, axis=1)
+        _, self.layer_correct, self.layer_wrong = layer_hits(self.layer_predictions, lab)
+        _, self.ensemble_layer_correct, self.ensemble_layer_wrong = layer_hits(self.ensemble_layer_predictions, lab)
         return self.preds
 
     def get_validation_predictions(self, val_loader):
@@ -139,65 +139,89 @@ class FullAnalysis:
         return out
 
     # ---- calibration statistics ---------------------------------------------------------------
-    def _device_bins(self, p, label_index, n_bins):
+    def _f64(self, a):
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), dtype=torch.float64,
+                               device=self.device)
+
+    def _device_bins(self, p, label_index, n_bins, mode=_lib.CAL_TOP):
+        """(conf float64 [N], hit int32 [N], bins float64 [n_bins, 3]) of `bnn_calibration_bins` - float64 end to end."""
         lib = _lib.load()
         with torch.cuda.device(self.device):
             _lib.require_device()
-            dp = torch.as_tensor(np.ascontiguousarray(p), dtype=torch.float32, device=self.device)
+            dp = self._f64(p)
             dl = torch.as_tensor(np.ascontiguousarray(label_index), dtype=torch.int32, device=self.device)
             N, C = dp.shape
-            conf = torch.empty(N, dtype=torch.float32, device=self.device)
+            conf = torch.empty(N, dtype=torch.float64, device=self.device)
             hit = torch.empty(N, dtype=torch.int32, device=self.device)
-            bins = torch.zeros((n_bins, 3), dtype=torch.float32, device=self.device)
+            bins = torch.zeros((n_bins, 3), dtype=torch.float64, device=self.device)
             if N == 0:
                 return conf, hit, bins
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(lib.bnn_calibration_bins(dp.data_ptr(), dl.data_ptr(), N, C, n_bins, conf.data_ptr(),
+            _lib.check(lib.bnn_calibration_bins(dp.data_ptr(), dl.data_ptr(), N, C, n_bins, mode, conf.data_ptr(),
                                                 hit.data_ptr(), bins.data_ptr(), stream))
         return conf, hit, bins
 
-    def ece_width(self, p, label_index, n_bins=10):
-        """Top-label ECE over equal-width bins (the statistic of hls4ml_pred.py:90-91), on the device."""
-        _, _, bins = self._device_bins(p, label_index, n_bins)
-        b = bins.double().cpu().numpy()
+    @staticmethod
+    def _binned_ece(bins):
+        b = bins.cpu().numpy()
         n = b[:, 0].sum()
         if n == 0:
             return 0.0
         nz = b[:, 0] > 0
         return float(np.sum(np.abs(b[nz, 1] / b[nz, 0] - b[nz, 2] / b[nz, 0]) * b[nz, 0] / n))
 
+    def ece_width(self, p, label_index, n_bins=10):
+        """Top-label ECE over equal-width bins - what hls4ml_pred.py:90-91 MEANS to compute - on the device."""
+        return self._binned_ece(self._device_bins(p, label_index, n_bins)[2])
+
+    def ece_tfp_as_called(self, y_prob, label_index, n_bins=10):
+        """The number hls4ml_pred.py:90-91,115-116 REALLY prints: ``tfp.stats.expected_calibration_error(num_bins,
+        logits=y_prob, labels_true, labels_predicted=argmax(y_prob))`` receives probabilities as `logits`, so tfp
+        soft-maxes them a second time (float32) and bins that value into [lo, hi) bins.  Restated from
+        tensorflow_probability/python/stats/calibration.py (tfp is not installed: unpinned); :meth:`ece_width` is the
+        statistic the call was meant to compute."""
+        return self._binned_ece(self._device_bins(np.asarray(y_prob, dtype=np.float32), label_index, n_bins,
+                                                  _lib.CAL_TFP_RESOFTMAX)[2])
+
     def ece_hist_binary(self, p, label, n_bins=15, order=1):
-        """Equal-mass top-label ECE, same binning rule as results_analyzer.py:446-495 (multi-class branch)."""
+        """Equal-mass ECE, same binning rule as results_analyzer.py:446-495: top-label confidence p[argmax] / sum(p)
+        (multi-class) or the class-1 probability with the label itself as the outcome (C == 2, :463-465); confidences
+        are float32 like the reference's `torch.zeros(N, 1)` buffer (:455) in the multi-class branch."""
+        p = np.clip(np.asarray(p, dtype=np.float64), 1e-256, 1 - 1e-256)
         label_index = np.argmax(label, axis=1)
-        conf_d, hit_d, _ = self._device_bins(np.clip(p, 1e-256, 1 - 1e-256), label_index, n_bins)
+        binary = p.shape[1] == 2
+        conf_d, hit_d = self._top_label(p, label_index, binary, round_f32=not binary)[:2]
+        if not binary:
+            conf_d = conf_d.float()
         srt = torch.sort(conf_d).values.cpu().numpy()
         conf, hit = conf_d.cpu().numpy(), hit_d.cpu().numpy().astype(np.float64)
         N = conf.shape[0]
         per = int(N / n_bins)
-        edges = np.zeros(n_bins + 1, dtype=np.float32)
+        edges = np.zeros(n_bins + 1, dtype=np.float32)                    # torch.zeros(len(bins)+1, 1) (:477)
         for i in range(n_bins):
             edges[i + 1] = srt[min((i + 1) * per, N - 1)]
         edges[0], edges[-1] = 0.0, 1.0
         total = 0.0
         for lo, hi in zip(edges[:-1], edges[1:]):
-            inside = (conf > lo) & (conf <= hi)
+            inside = (conf > float(lo)) & (conf <= float(hi))
             if inside.any():
-                total += abs(float(conf[inside].mean(dtype=np.float32)) - float(hit[inside].mean())) ** order \
-                    * float(inside.mean())
+                avg = float(conf[inside].mean(dtype=conf.dtype))
+                total += abs(avg - float(np.float32(hit[inside].mean()))) ** order * float(np.float32(inside.mean()))
         return total
 
     def dataset_metrics(self, p, label_index):
-        """(nll, mse, accuracy) of results_analyzer.py:497-503 computed on the device (`bnn_dataset_metrics`)."""
+        """(nll, mse, accuracy) of results_analyzer.py:497-503 computed on the device in float64
+        (`bnn_dataset_metrics`): the NLL clip is the reference's 1e-256, not a float32 stand-in."""
         lib = _lib.load()
         with torch.cuda.device(self.device):
             _lib.require_device()
-            dp = torch.as_tensor(np.ascontiguousarray(p), dtype=torch.float32, device=self.device)
+            dp = self._f64(p)
             dl = torch.as_tensor(np.ascontiguousarray(label_index), dtype=torch.int32, device=self.device)
             N, C = dp.shape
             if N == 0:
                 return 0.0, 0.0, 0.0
-            ws = torch.empty(3 * ((N + 255) // 256), dtype=torch.float32, device=self.device)
-            out = torch.empty(3, dtype=torch.float32, device=self.device)
+            ws = torch.empty(3 * ((N + 255) // 256), dtype=torch.float64, device=self.device)
+            out = torch.empty(3, dtype=torch.float64, device=self.device)
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(lib.bnn_dataset_metrics(dp.data_ptr(), dl.data_ptr(), N, C, ws.data_ptr(), out.data_ptr(), stream))
             nll, mse, acc = out.cpu().tolist()
@@ -209,42 +233,61 @@ class FullAnalysis:
         return float(-np.sum(np.log(probs + 1e-8) * probs) / probs.shape[0])
 
     # ---- KDE-ECE ------------------------------------------------------------------------------------
-    def ece_kde_binary(self, p, label, p_int=None, order=1):
-        """Top-label KDE-ECE like results_analyzer.py:351-443 (multi-class branch, p_int = p): confidences,
-        bandwidth moments and both mirrored triweight density estimates on the device, the 2^14-point carry-forward
-        integration (:426-443) on the host."""
-        if p_int is not None:
-            raise NotImplementedError("ece_kde_binary: a separate integration set p_int is not supported")
-        p = np.asarray(p)
-        if p.shape[1] == 2:
-            raise NotImplementedError("ece_kde_binary: the binary joint-calibration branch is not supported")
+    def _top_label(self, p, label_index, binary, round_f32):
+        """`bnn_top_label` -> (conf float64 [N], flag int32 [N] | None, (n, sum, sum of squares) over the flagged)."""
         lib = _lib.load()
-        G = 2 ** 14
-        x_int = np.linspace(-0.6, 1.6, num=G)
         with torch.cuda.device(self.device):
             _lib.require_device()
-            dp = torch.as_tensor(np.ascontiguousarray(p), dtype=torch.float32, device=self.device)
-            dl = torch.as_tensor(np.ascontiguousarray(np.argmax(label, axis=1)), dtype=torch.int32, device=self.device)
+            dp = self._f64(p)
             N, C = dp.shape
-            conf = torch.empty(N, dtype=torch.float32, device=self.device)
-            hit = torch.empty(N, dtype=torch.int32, device=self.device)
+            conf = torch.empty(N, dtype=torch.float64, device=self.device)
             st = torch.zeros(3, dtype=torch.float64, device=self.device)
+            flag = dl = None
+            if label_index is not None:
+                dl = torch.as_tensor(np.ascontiguousarray(label_index), dtype=torch.int32, device=self.device)
+                flag = torch.empty(N, dtype=torch.int32, device=self.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.bnn_top_label(dp.data_ptr(), dl.data_ptr() if dl is not None else None, N, C, int(binary),
+                                         int(round_f32), conf.data_ptr(), flag.data_ptr() if flag is not None else None,
+                                         st.data_ptr(), stream))
+            return conf, flag, st.cpu().tolist()
+
+    def ece_kde_binary(self, p, label, p_int=None, order=1):
+        """KDE-ECE like results_analyzer.py:351-443, both branches: top-label calibration (C != 2) and the joint
+        calibration of the class-1 probability for binary problems (C == 2, :381-383, :417-419, :422-425), with an
+        optional separate integration set `p_int` (:354-355, :409-419; default: `p` itself).  Confidences, bandwidth
+        moments and both mirrored triweight density estimates are computed on the device in float64, the 2^14-point
+        carry-forward integration (:426-443) on the host."""
+        p = np.asarray(p, dtype=np.float64)
+        p_int = p if p_int is None else np.asarray(p_int, dtype=np.float64)
+        if p_int.shape[1] != p.shape[1]:
+            raise ValueError("ece_kde_binary: p_int has %d classes, p has %d" % (p_int.shape[1], p.shape[1]))
+        lib = _lib.load()
+        binary = p.shape[1] == 2
+        G = 2 ** 14
+        x_int = np.linspace(-0.6, 1.6, num=G)
+        N, N1 = p.shape[0], p_int.shape[0]
+        label_index = np.argmax(label, axis=1)
+        # the multi-class confidences of `p` live in a float32 tensor in the reference (:373); the binary branch and
+        # the integration set stay float64 (:382, :414)
+        conf, flag, (n1, s1, s2) = self._top_label(p, label_index, binary, round_f32=not binary)
+        conf_int, _, _ = self._top_label(p_int, None, binary, round_f32=False)
+        with torch.cuda.device(self.device):
             dens = torch.zeros((2, G), dtype=torch.float64, device=self.device)
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(lib.bnn_top_label(dp.data_ptr(), dl.data_ptr(), N, C, conf.data_ptr(), hit.data_ptr(),
-                                         st.data_ptr(), stream))
-            n1, s1, s2 = st.cpu().tolist()
             var = max(s2 / n1 - (s1 / n1) ** 2, 0.0) if n1 > 0 else 0.0
             std = var ** 0.5
             kbw = (std if std > 1e-12 else 0.0000000000000001) * (N * 2) ** -0.2          # :389-393
             dx = float(x_int[1] - x_int[0])
             if n1 > 0:
-                _lib.check(lib.bnn_kde_triweight(conf.data_ptr(), hit.data_ptr(), N, kbw, float(n1), float(x_int[0]), dx, G,
+                _lib.check(lib.bnn_kde_triweight(conf.data_ptr(), flag.data_ptr(), N, kbw, float(n1), float(x_int[0]), dx, G,
                                                  0.0, 1.0, dens[0].data_ptr(), stream))
-            _lib.check(lib.bnn_kde_triweight(conf.data_ptr(), None, N, kbw, float(N), float(x_int[0]), dx, G, 0.0, 1.0,
-                                             dens[1].data_ptr(), stream))
+            if N1 > 0:
+                _lib.check(lib.bnn_kde_triweight(conf_int.data_ptr(), None, N1, kbw, float(N1), float(x_int[0]), dx, G,
+                                                 0.0, 1.0, dens[1].data_ptr(), stream))
             pp = dens.cpu().numpy()
-        return _kde_ece_integrate(x_int, pp[0], pp[1], n1 / N, order)
+        perc = float(np.mean(label_index)) if binary else n1 / N                          # :422-425
+        return _kde_ece_integrate(x_int, pp[0], pp[1], perc, order)
 
     def ece_eval_binary(self, p, label):
         """(ece, nll, mse, accuracy) like :497-505 - the ECE is the KDE-ECE, everything computed on the device."""
@@ -326,14 +369,14 @@ class FullAnalysis:
         E, N, C = p_evals.shape
         with torch.cuda.device(self.device):
             _lib.require_device()
-            dp = torch.as_tensor(np.ascontiguousarray(p_evals), dtype=torch.float32, device=self.device)
+            dp = self._f64(p_evals)
             idx = torch.empty(N, dtype=torch.int32, device=self.device)
-            best = torch.empty((N, C), dtype=torch.float32, device=self.device)
+            best = torch.empty((N, C), dtype=torch.float64, device=self.device)
             hist = torch.zeros(E, dtype=torch.int32, device=self.device)
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(lib.bnn_confidence_exit(dp.data_ptr(), E, N, C, min(1, E - 1), float(threshold), int(bool(diff)),
                                                idx.data_ptr(), best.data_ptr(), hist.data_ptr(), stream))
-            return idx.cpu().numpy(), best.cpu().numpy().astype(np.float64), hist.cpu().numpy()
+            return idx.cpu().numpy(), best.cpu().numpy(), hist.cpu().numpy()
 
     def confidence_exiting(self, threshold, p_evals, labels, diff=False):
         """-> (accuracy, ece, nll) of the predictions taken at the first confident exit (:606-630)."""
@@ -383,6 +426,24 @@ class FullAnalysis:
                 rows.append(dict(kind=name, threshold=thr, dropout_rate=dropout_rate, accuracy=accu, ece=ece, nll=nll,
                                  flops=fl(thr, pe, self.labels, mc_passes=mc_passes) / (self.baseline_flops * n)))
         return rows
+
+
+def layer_hits(output, labels):
+    """The layer trackers of results_analyzer.py:272-286 for one loader pass.  `output`: per-exit [N, C] mean LOGITS
+    (tensors / arrays; the reference's `output[output_id].max(1)`), or an [E, N] array of already-taken argmaxes.
+    -> (pred [E, N], {exit: set of correct instance ids}, {exit: set of wrong ids})."""
+    if isinstance(output, np.ndarray) and output.ndim == 2:
+        pred = output
+    else:
+        pred = np.stack([o.max(1)[1].cpu().numpy() if isinstance(o, torch.Tensor) else np.asarray(o).argmax(1)
+                         for o in output])
+    lab = np.asarray(labels).reshape(-1)
+    good, bad = {}, {}
+    for e in range(pred.shape[0]):
+        hit = pred[e] == lab
+        good[e] = set(np.flatnonzero(hit).tolist())
+        bad[e] = set(np.flatnonzero(~hit).tolist())
+    return pred, good, bad
 
 
 def _kde_ece_integrate(x_int, pp1, pp2, perc, order=1):

@@ -210,40 +210,52 @@ int bnn_finalize(const float* sum_p, const float* sum_logit, const float* sum_pl
                  int S_total, float* mean_p, float* mean_logit, float* ens_p, float* ens_logit, float* entropy,
                  float* ens_entropy, float* exp_entropy, void* stream);
 
-/* ---- calibration statistics on the device ----
- * Top-label confidence / correctness per image and the equal-width-bin ECE
- * (hls4ml_pred.py:90-91 statistic). probs [N][C] float32, labels int32 [N].
- * bin_stats: float32 [n_bins][3] = (count, sum confidence, sum correct), zeroed by the call. */
-int bnn_calibration_bins(const float* probs, const int32_t* labels, int N, int C, int n_bins, float* conf,
-                         int32_t* correct, float* bin_stats, void* stream);
+/* ---- dataset-level statistics on the device (csrc/kernels_stats.cu) ----
+ * All of them take the FLOAT64 [N][C] mean-probability arrays FullAnalysis keeps on the host
+ * (results_analyzer.py:133-135) and compute in float64 like the reference's NumPy code; labels are int32 [N].
+ *
+ * bnn_calibration_bins: per-image top-label confidence / correctness and equal-width bin statistics.
+ *   mode BNN_CAL_TOP            conf = p[argmax]           bins (lo, hi]    (the corrected 10-bin ECE)
+ *        BNN_CAL_TOP_NORM       conf = p[argmax] / sum(p)  bins (lo, hi]    (confidences of ece_hist_binary :446-460)
+ *        BNN_CAL_TFP_RESOFTMAX  conf = softmax_f32(p)[argmax p], bins [lo, hi) = floor(n * conf): the statistic
+ *                               hls4ml_pred.py:90-91,115-116 REALLY computes - it passes probabilities as `logits=`
+ *                               and tfp.stats.expected_calibration_error soft-maxes them again
+ * bin_stats: float64 [n_bins][3] = (count, sum confidence, sum correct), zeroed by the call. */
+enum { BNN_CAL_TOP = 0, BNN_CAL_TOP_NORM = 1, BNN_CAL_TFP_RESOFTMAX = 2 };
+int bnn_calibration_bins(const double* probs, const int32_t* labels, int N, int C, int n_bins, int mode, double* conf,
+                         int32_t* correct, double* bin_stats, void* stream);
 
-/* Dataset-level scores of ece_eval_binary (results_analyzer.py:497-503) on the device:
- * out[0] = NLL = -mean log p[label], out[1] = MSE = mean sum_c (p_c - onehot_c)^2, out[2] = top-1 accuracy.
- * workspace: float32 [3 * ceil(N / 256)] (fixed-order two-stage reduction: deterministic). */
-int bnn_dataset_metrics(const float* probs, const int32_t* labels, int N, int C, float* workspace, float* out,
+/* Dataset-level scores of ece_eval_binary (results_analyzer.py:497-503):
+ * out[0] = NLL = -mean log clip(p[label], 1e-256, 1 - 1e-256), out[1] = MSE = mean sum_c (p_c - onehot_c)^2,
+ * out[2] = top-1 accuracy.  workspace: float64 [3 * ceil(N / 256)] (fixed-order two-stage reduction: deterministic). */
+int bnn_dataset_metrics(const double* probs, const int32_t* labels, int N, int C, double* workspace, double* out,
                         void* stream);
 
 /* ---- confidence-threshold early exiting (results_analyzer.py:606-631 confidence_exiting, :728-735 is_confident) ----
- * probs [E][N][C] float32 (mean predictions of every exit).  Image i leaves at the first exit e in
- * [first_exit, E-1) with max_c p > threshold (diff == 0) or top1 - top2 > threshold (diff != 0), else at E-1; the
+ * probs [E][N][C] float64 (mean predictions of every exit).  Image i leaves at the first exit e in
+ * [first_exit, E-1) with max_c p > threshold (diff == 0) or |top1 - top2| > threshold (diff != 0), else at E-1; the
  * reference starts its scan at exit 1 (`for layer in range(1, self.n_exits)`), pass first_exit = 1 to mirror it.
- * exit_idx int32 [N]; best_probs float32 [N][C] = the chosen exit's prediction; exit_hist int32 [E] = images per
+ * exit_idx int32 [N]; best_probs float64 [N][C] = the chosen exit's prediction; exit_hist int32 [E] = images per
  * exit (zeroed by the call) - the FLOP accounting of flop_saver / flop_saver_ensembled (:639-726) is a dot product
  * of this histogram with the per-exit cost table. */
-int bnn_confidence_exit(const float* probs, int E, int N, int C, int first_exit, float threshold, int diff,
-                        int32_t* exit_idx, float* best_probs, int32_t* exit_hist, void* stream);
+int bnn_confidence_exit(const double* probs, int E, int N, int C, int first_exit, double threshold, int diff,
+                        int32_t* exit_idx, double* best_probs, int32_t* exit_hist, void* stream);
 
 /* ---- KDE-ECE building blocks (ece_kde_binary, results_analyzer.py:351-443) ----
- * bnn_top_label: conf[i] = p[i][argmax] / sum_c p[i][c] (:374-380, :412-419), correct[i], and
- *   stats (double [3], zeroed by the call) = (#correct, sum conf over correct, sum conf^2 over correct) for the
- *   bandwidth rule std(conf | correct) * (2N)^-0.2 (:389-392).
+ * bnn_top_label: probabilities clipped to [1e-256, 1 - 1e-256] (:357-358), then
+ *     binary == 0 (top-label branch :370-380, :412-416): conf[i] = p[i][argmax] / sum_c p[i][c], flag[i] = argmax == label
+ *     binary != 0 (C == 2, joint-calibration branch :381-383, :417-419): conf[i] = p[i][1] / sum_c p[i][c], flag[i] = label
+ *   round_f32 != 0 rounds conf to float32 (the reference stores the top-label confidences of `p` in a float32 tensor,
+ *   :373; those of the integration set p_int stay float64, :414).  labels may be NULL (integration set: no flags, no
+ *   stats).  stats (double [3], zeroed by the call) = (n, sum conf, sum conf^2) over the flagged images for the
+ *   bandwidth rule std(conf | flag) * (2N)^-0.2 (:389-392).
  * bnn_kde_triweight: density of `data` (only entries with flags[i] != 0 when flags is given) mirrored about lo / hi
  *   (mirror_1d :339-349), triweight kernel of standard deviation `bw`, on the grid x0 + j*dx, j < G; zero outside
  *   (lo, hi) and doubled (:403-406); n_points = number of un-mirrored points used.  The estimate is evaluated
  *   EXACTLY; the reference uses KDEpy's FFTKDE (linear binning + FFT convolution) for the same estimator. */
-int bnn_top_label(const float* probs, const int32_t* labels, int N, int C, float* conf, int32_t* correct,
-                  double* stats, void* stream);
-int bnn_kde_triweight(const float* data, const int32_t* flags, int n, double bw, double n_points, double x0,
+int bnn_top_label(const double* probs, const int32_t* labels, int N, int C, int binary, int round_f32, double* conf,
+                  int32_t* flag, double* stats, void* stream);
+int bnn_kde_triweight(const double* data, const int32_t* flags, int n, double bw, double n_points, double x0,
                       double dx, int G, double lo, double hi, double* out, void* stream);
 
 #ifdef __cplusplus

@@ -34,8 +34,9 @@ class InjectedSites:
     """site(name, x) with masks from the Philox contract; stream id = order of first use
     within one forward pass (the product's plan builder numbers its sites the same way)."""
 
-    def __init__(self, spec, seed, sample):
+    def __init__(self, spec, seed, sample, batch_offset=0):
         self.spec, self.seed, self.sample = spec, int(seed), int(sample)
+        self.batch_offset = int(batch_offset)      # x holds images batch_offset.. of the batch the masks are drawn for
         self.streams = {}
 
     def __call__(self, name, x):
@@ -48,7 +49,7 @@ class InjectedSites:
             row = m[(sp.cnt0 + self.sample) % m.shape[0]].to(x.dtype)
             return x * row.reshape(1, -1, *([1] * (x.dim() - 2)))
         mode = "channel" if sp.kind == "mc2d" else "element"
-        keep = philox.keep_mask(self.seed, stream, self.sample, x.shape, sp.p, mode)
+        keep = philox.keep_mask(self.seed, stream, self.sample, x.shape, sp.p, mode, self.batch_offset)
         if sp.p >= 1.0:
             return torch.zeros_like(x)
         scale = np.float32(1.0) / np.float32(1.0 - sp.p)

@@ -55,20 +55,23 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
             c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def random_words(seed, stream, sample, count):
-    """``count`` uint32 words for element indices 0..count-1 of one (stream, sample)."""
+def random_words(seed, stream, sample, count, first_block=0):
+    """``count`` uint32 words of one (stream, sample), starting at Philox block `first_block` (4 words per block)."""
     nblk = (count + 3) // 4
-    blk = np.arange(nblk, dtype=np.uint64)
+    blk = np.arange(nblk, dtype=np.uint64) + np.uint64(first_block)
     r = philox4x32_10(blk & _MASK32, blk >> np.uint64(32), sample, stream,
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return np.stack(r, axis=1).reshape(-1)[:count]
 
 
-def random_halves(seed, stream, sample, count):
-    """``count`` 16-bit draws for element indices 0..count-1: two per 32-bit word, low half first."""
-    w = random_words(seed, stream, sample, (count + 1) // 2)
+def random_halves(seed, stream, sample, count, first=0):
+    """``count`` 16-bit draws for element indices first..first+count-1: two per 32-bit word, low half first (one
+    Philox block = 8 elements)."""
+    first = int(first)
+    blk0, skip = first // 8, first % 8
+    w = random_words(seed, stream, sample, (skip + count + 1) // 2, first_block=blk0)
     h = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=1).reshape(-1)
-    return h[:count].astype(np.uint32)
+    return h[skip:skip + count].astype(np.uint32)
 
 
 def threshold(p):
@@ -76,29 +79,31 @@ def threshold(p):
     return int(min(np.rint(float(p) * 65536.0), 65535.0))
 
 
-def keep_mask_flat(seed, stream, sample, count, p):
+def keep_mask_flat(seed, stream, sample, count, p, first=0):
     if p >= 1.0:
         return np.zeros(count, dtype=bool)
-    return random_halves(seed, stream, sample, count) >= np.uint32(threshold(p))
+    return random_halves(seed, stream, sample, count, first) >= np.uint32(threshold(p))
 
 
-def keep_mask(seed, stream, sample, shape, p, mode="element"):
+def keep_mask(seed, stream, sample, shape, p, mode="element", batch_offset=0):
     """Boolean keep mask in TORCH (NCHW / [B,F]) layout for one MC sample.
 
     mode "element": the NHWC-ordered contract above, returned permuted to NCHW.
     mode "channel": one draw per (b, c), broadcast over the spatial dims (dropout2d).
+    batch_offset: the tensor holds images batch_offset.. of a larger batch (element indices are per image WITHIN the
+    batch, so rows of a full-size run can be checked without materialising the whole batch on the host).
     """
     shape = tuple(int(v) for v in shape)
     if mode == "channel":
         b, c = shape[0], shape[1]
-        m = keep_mask_flat(seed, stream, sample, b * c, p).reshape(b, c)
+        m = keep_mask_flat(seed, stream, sample, b * c, p, batch_offset * c).reshape(b, c)
         return np.broadcast_to(m.reshape(b, c, *([1] * (len(shape) - 2))), shape).copy()
     if len(shape) == 4:
         b, c, h, w = shape
-        m = keep_mask_flat(seed, stream, sample, b * h * w * c, p).reshape(b, h, w, c)
+        m = keep_mask_flat(seed, stream, sample, b * h * w * c, p, batch_offset * h * w * c).reshape(b, h, w, c)
         return np.ascontiguousarray(m.transpose(0, 3, 1, 2))
     count = int(np.prod(shape))
-    return keep_mask_flat(seed, stream, sample, count, p).reshape(shape)
+    return keep_mask_flat(seed, stream, sample, count, p, batch_offset * (count // max(shape[0], 1))).reshape(shape)
 
 
 def uniform01(seed, stream, sample, count):

@@ -6,7 +6,8 @@ softmax per exit per pass, float64 averages of logits and of probabilities over 
 then the cumulative-exit ensembles.  ``entropy`` follows
 Hardware_Artifact/bayes_hw/metric_utils.py:3-6, ``ece_hist`` follows
 results_analyzer.py:446-495, ``ece_width`` restates the 10-equal-width-bin top-label ECE the
-hardware scripts call (hls4ml_pred.py:90-91), ``nll_mse_acc`` follows results_analyzer.py:497-503.
+hardware scripts mean to call (hls4ml_pred.py:90-91) and ``ece_tfp_as_called`` the number that call really produces,
+``nll_mse_acc`` follows results_analyzer.py:497-503, ``layer_tracker`` :272-286.
 """
 import numpy as np
 import torch
@@ -48,15 +49,19 @@ def entropy_per_image(probs):
 
 
 def ece_hist(p, label_onehot, n_bins=15, order=1):
-    """results_analyzer.py:446-495 for the multi-class (C != 2) branch: top-label confidence,
-    bin edges at every (N // n_bins)-th sorted confidence, first edge 0, last edge 1."""
+    """results_analyzer.py:446-495: top-label confidence (C != 2; float32 like the reference's `torch.zeros(N,1)`
+    buffer :455) or the class-1 probability with the label itself as the outcome (C == 2, :463-465; float64); bin
+    edges at every (N // n_bins)-th sorted confidence, first edge 0, last edge 1."""
     p = np.clip(np.asarray(p, dtype=np.float64), 1e-256, 1 - 1e-256)
     N = p.shape[0]
     label_index = np.argmax(label_onehot, axis=1)
-    pred = np.argmax(p, axis=1)
-    # the reference stores confidences in a float32 torch tensor (torch.zeros(N,1), :455)
-    conf = (p[np.arange(N), pred] / p.sum(axis=1)).astype(np.float32)
-    hit = (pred == label_index).astype(np.float64)
+    if p.shape[1] != 2:
+        pred = np.argmax(p, axis=1)
+        conf = (p[np.arange(N), pred] / p.sum(axis=1)).astype(np.float32)
+        hit = (pred == label_index).astype(np.float64)
+    else:
+        conf = (p / p.sum(axis=1)[:, None])[:, 1]
+        hit = label_index.astype(np.int64)
     srt = np.sort(conf)
     per = int(N / n_bins)
     edges = np.zeros(n_bins + 1, dtype=np.float32)
@@ -90,6 +95,47 @@ def ece_width(p, label_index, n_bins=10):
         if sel.any():
             out += abs(conf[sel].mean() - hit[sel].mean()) * sel.mean()
     return out
+
+
+def ece_tfp_as_called(y_prob, label_index, n_bins=10):
+    """What hls4ml_pred.py:90-91,115-116 really evaluates:
+    ``tfp.stats.expected_calibration_error(num_bins, logits=y_prob, labels_true, labels_predicted=argmax(y_prob))``
+    with PROBABILITIES passed as `logits`.  tensorflow-probability is not installed (and not pinned by the reference:
+    Hardware_Artifact/requirements.txt lists no tfp version), so this restates the published algorithm of
+    tensorflow_probability/python/stats/calibration.py (`_compute_calibration_bin_statistics` +
+    `expected_calibration_error`), float32 like TF:
+        pred   = softmax(logits)                      <- the second soft-max of already-normalised probabilities
+        prob_y = pred[i, labels_predicted[i]]
+        bin    = tf.histogram_fixed_width_bins(prob_y, [0, 1], nbins) = clip(floor(nbins * prob_y), 0, nbins - 1)
+        ece    = sum_b (n_b / N) * |correct_b / (n_b + tiny) - mean prob_y in b|   (empty bins contribute 0)
+    parity unpinned (no tfp here); SURVEY.md A.3 lists the call as a reference defect - `ece_width` is what it meant."""
+    y = np.asarray(y_prob, dtype=np.float32)
+    pred_y = np.argmax(y, axis=1)
+    z = np.exp(y - y.max(axis=1, keepdims=True))
+    sm = (z / z.sum(axis=1, keepdims=True)).astype(np.float32)
+    prob_y = sm[np.arange(y.shape[0]), pred_y]
+    correct = (pred_y == np.asarray(label_index)).astype(np.float32)
+    b = np.clip(np.floor(prob_y * np.float32(n_bins)).astype(np.int64), 0, n_bins - 1)
+    tiny = np.finfo(np.float32).tiny
+    out = 0.0
+    n = float(y.shape[0])
+    for k in range(n_bins):
+        sel = b == k
+        cnt = float(sel.sum())
+        if cnt == 0:
+            continue
+        out += (cnt / n) * abs(float(correct[sel].sum()) / (cnt + tiny) - float(prob_y[sel].sum()) / cnt)
+    return out
+
+
+def layer_tracker(output, b_y):
+    """_update_layer_tracker results_analyzer.py:272-286 without the per-instance dict bookkeeping: the prediction of
+    an exit is ``output[output_id].max(1)[1]`` - the argmax of the MEAN LOGITS over the passes (for the ensemble
+    trackers: of their cumulative mean over exits) - and an instance is correct when it equals the label.
+    -> (pred [E, B] int64, correct [E, B] bool)."""
+    pred = np.stack([np.asarray(o.max(1)[1]) if isinstance(o, torch.Tensor) else np.asarray(o).argmax(1)
+                     for o in output])
+    return pred, pred == np.asarray(b_y).reshape(1, -1)
 
 
 def nll_mse_acc(p, label_onehot):
@@ -197,19 +243,28 @@ def kde_triweight_exact(data, bw, grid):
     return out * (35.0 / 32.0) / (h * data.shape[0])
 
 
-def ece_kde(p, label_onehot, order=1, kde=kde_triweight_exact):
-    """ece_kde_binary :351-443, multi-class (top-label) branch, p_int = p.  `kde(data, bw, grid)` stands in for
-    KDEpy (not installed: parity of this statistic is pinned against the reference's own source with this exact
-    estimator injected as `FFTKDE`, tests/golden/make_golden_analysis.py)."""
-    p = np.clip(np.asarray(p, dtype=np.float64), 1e-256, 1 - 1e-256)
+def ece_kde(p, label_onehot, order=1, kde=kde_triweight_exact, p_int=None):
+    """ece_kde_binary :351-443, both branches (top-label for C != 2, joint calibration of the class-1 probability for
+    C == 2) with an optional integration set p_int (default: p itself).  `kde(data, bw, grid)` stands in for KDEpy
+    (not installed: parity of this statistic is pinned against the reference's own source with this exact estimator
+    injected as `FFTKDE`, tests/golden/make_golden_analysis.py)."""
+    p = np.asarray(p, dtype=np.float64)
+    p_int = np.copy(p) if p_int is None else np.asarray(p_int, dtype=np.float64)
+    p = np.clip(p, 1e-256, 1 - 1e-256)
+    p_int = np.clip(p_int, 1e-256, 1 - 1e-256)
     x_int = np.linspace(-0.6, 1.6, num=2 ** 14)
     N = p.shape[0]
     label_index = np.argmax(label_onehot, axis=1)
-    pred = np.argmax(p, axis=1)
-    label_binary = (pred == label_index).astype(np.float64).reshape(-1, 1)
-    # the reference keeps p_b in a float32 torch tensor (torch.zeros(N,1), :373)
-    p_b = (p[np.arange(N), pred] / p.sum(1)).astype(np.float32).reshape(-1, 1)
-    dconf_1 = p_b[label_binary[:, 0] == 1].reshape(-1, 1)
+    binary = p.shape[1] == 2
+    if not binary:
+        pred = np.argmax(p, axis=1)
+        label_binary = (pred == label_index).astype(np.float64)
+        # the reference keeps p_b in a float32 torch tensor (torch.zeros(N,1), :373)
+        p_b = (p[np.arange(N), pred] / p.sum(1)).astype(np.float32)
+    else:
+        p_b = (p / p.sum(1)[:, None])[:, 1]                      # float64 (:382)
+        label_binary = label_index
+    dconf_1 = p_b[label_binary == 1].reshape(-1, 1)
     if np.std(dconf_1) != 0:
         kbw = np.std(dconf_1) * (N * 2) ** -0.2
     else:
@@ -217,12 +272,16 @@ def ece_kde(p, label_onehot, order=1, kde=kde_triweight_exact):
     pp1 = kde(mirror_1d(dconf_1, 0.0, 1.0), kbw, x_int)
     pp1[(x_int <= 0.0) | (x_int >= 1.0)] = 0
     pp1 = pp1 * 2
-    p_int = p / p.sum(1)[:, None]
-    pred_b_int = p_int[np.arange(N), np.argmax(p_int, axis=1)].reshape(-1, 1)
+    p_int = p_int / p_int.sum(1)[:, None]
+    N1 = p_int.shape[0]
+    if not binary:
+        pred_b_int = p_int[np.arange(N1), np.argmax(p_int, axis=1)].reshape(-1, 1)
+    else:
+        pred_b_int = p_int[:, 1].reshape(-1, 1)
     pp2 = kde(mirror_1d(pred_b_int, 0.0, 1.0), kbw, x_int)
     pp2[(x_int <= 0.0) | (x_int >= 1.0)] = 0
     pp2 = pp2 * 2
-    perc = np.mean(label_binary)
+    perc = np.mean(label_binary) if not binary else np.mean(label_index)
     return kde_ece_integrate(x_int, pp1, pp2, perc, order)
 
 

@@ -3,8 +3,8 @@
     python tests/golden/make_golden_analysis.py     # needs /root/reference, writes tests/golden/analysis.npz
 
 The methods are exec'd from Software_Artifact/software/train/results_analyzer.py inside a stub class (the module
-itself imports KDEpy / matplotlib / sacred, which are not installed): mirror_1d :339-349, ece_kde_binary :351-443,
-ece_eval_binary :497-505, get_flops_per_module :568-580, confidence_exiting :606-630, get_flops_standard_exit
+itself imports KDEpy / matplotlib / sacred, which are not installed): _update_layer_tracker :272-286, mirror_1d
+:339-349, ece_kde_binary :351-443, ece_hist_binary :446-495, ece_eval_binary :497-505, get_flops_per_module :568-580, confidence_exiting :606-630, get_flops_standard_exit
 :632-637, flop_saver :639-672, flop_saver_ensembled :674-726, is_confident :728-735.
 
 KDEpy is absent, so the name `FFTKDE` the reference source looks up is bound to a class that evaluates the SAME
@@ -42,7 +42,7 @@ class ExactKDE:
 
 def load_stub():
     src = open(REF).read().split("\n")
-    spans = [(338, 349), (350, 443), (496, 505), (567, 580), (605, 630), (631, 637), (638, 672), (673, 726), (727, 735)]
+    spans = [(271, 286), (338, 349), (350, 443), (445, 495), (496, 505), (567, 580), (605, 630), (631, 637), (638, 672), (673, 726), (727, 735)]
     body = "\n\n".join("\n".join(src[a:b]) for a, b in spans)
     code = "class Stub:\n" + textwrap.indent(textwrap.dedent(body), "    ")
     if not hasattr(np, "trapz"):
@@ -107,7 +107,78 @@ def main():
             per_exit.append([ece, nll, mse, accu])
         out["per_exit%d" % k] = np.asarray(per_exit)
         print("%s: confidence exiting, FLOP accounting and KDE-ECE - oracle == reference source" % mt)
+    extra_cases(Stub, out)
     np.savez_compressed(os.path.join(HERE, "analysis.npz"), **out)
+
+
+def extra_cases(Stub, out):
+    """Branches the per-exit cases above do not reach: a separate integration set p_int, order 2, the binary (C == 2)
+    joint-calibration branch of both ECEs, float64-only probabilities (NLL clip at 1e-256), and the layer trackers'
+    argmax-of-mean-LOGITS rule on a batch where it disagrees with the argmax of the mean probabilities."""
+    st = Stub()
+    # ---- KDE-ECE with p_int / order / binary ---------------------------------------------------------------
+    p_evals, lab = synthetic_exits(3, 500, 10, seed=40)
+    onehot = np.eye(10)[lab]
+    p, p_int = p_evals[1], p_evals[2][:320]
+    vals = []
+    for kw in (dict(p_int=p_int), dict(p_int=p_int, order=2), dict(order=2)):
+        v = st.ece_kde_binary(p, onehot, **kw)
+        assert abs(v - stats.ece_kde(p, onehot, **kw)) < 1e-12, kw
+        vals.append(v)
+    out["kde_p"], out["kde_p_int"], out["kde_lab"], out["kde_vals"] = p, p_int, lab, np.asarray(vals)
+    pb_evals, labb = synthetic_exits(2, 600, 2, seed=41)
+    onehot_b = np.eye(2)[labb]
+    pb, pb_int = pb_evals[1], pb_evals[0][:450]
+    vb = []
+    for kw in (dict(), dict(p_int=pb_int), dict(order=2)):
+        v = st.ece_kde_binary(pb, onehot_b, **kw)
+        assert abs(v - stats.ece_kde(pb, onehot_b, **kw)) < 1e-12, ("binary", kw)
+        vb.append(v)
+    hb = [float(st.ece_hist_binary(pb, onehot_b)), float(st.ece_hist_binary(pb, onehot_b, n_bins=10, order=2)),
+          float(st.ece_hist_binary(p, onehot)), float(st.ece_hist_binary(p, onehot, n_bins=7))]
+    ho = [stats.ece_hist(pb, onehot_b), stats.ece_hist(pb, onehot_b, n_bins=10, order=2), stats.ece_hist(p, onehot),
+          stats.ece_hist(p, onehot, n_bins=7)]
+    assert np.abs(np.asarray(hb) - np.asarray(ho)).max() < 1e-7, (hb, ho)
+    out["bin_p"], out["bin_p_int"], out["bin_lab"] = pb, pb_int, labb
+    out["bin_kde_vals"], out["hist_vals"] = np.asarray(vb), np.asarray(hb)
+    eb = st.ece_eval_binary(pb, onehot_b)
+    assert abs(eb[1] - stats.nll_mse_acc(pb, onehot_b)[0]) < 1e-12
+    out["bin_eval"] = np.asarray(eb, dtype=np.float64)
+    # ---- probabilities only float64 can hold: the NLL clip is 1e-256, not FLT_MIN ----------------------------
+    pu = p.copy()
+    pu[np.arange(0, 500, 7), lab[::7]] = 1e-300           # the true class got (numerically) zero probability
+    pu[np.arange(3, 500, 11), lab[3::11]] = 1e-60         # below float32's smallest normal, above the clip
+    eu = st.ece_eval_binary(pu, onehot)
+    nll_o, mse_o, acc_o = stats.nll_mse_acc(pu, onehot)
+    assert abs(eu[1] - nll_o) < 1e-9 and abs(eu[2] - mse_o) < 1e-12 and eu[3] == acc_o
+    assert abs(eu[0] - stats.ece_kde(pu, onehot)) < 1e-12
+    out["under_p"], out["under_eval"] = pu, np.asarray(eu, dtype=np.float64)
+    # ---- _update_layer_tracker: argmax of the mean logits ------------------------------------------------------
+    E, B, C, S = 3, 64, 5, 4
+    logits = 3.0 * philox.normal(77, 0, 0, S * E * B * C).reshape(S, E, B, C)
+    logits[:, :, :, 0] += np.linspace(-2, 6, S)[:, None, None]     # a class with a wild logit in one pass
+    probs = np.exp(logits - logits.max(-1, keepdims=True))
+    probs /= probs.sum(-1, keepdims=True)
+    mean_logits, mean_probs = logits.mean(0), probs.mean(0)
+    assert (mean_logits.argmax(-1) != mean_probs.argmax(-1)).sum() >= 5        # the two rules really disagree here
+    b_y = torch.from_numpy(seeded.seeded_labels(B, C, seed=5).astype(np.int64))
+    st.device = torch.device("cpu")
+    st.loader = type("L", (), {"batch_size": B})()
+    trackers = [{e: set() for e in range(E)}, {e: set() for e in range(E)}, {e: {} for e in range(E)},
+                {e: {} for e in range(E)}]
+    output = [torch.from_numpy(mean_logits[e]) for e in range(E)]
+    output_sm = [torch.from_numpy(mean_probs[e]) for e in range(E)]
+    for e in range(E):
+        trackers = list(st._update_layer_tracker(b_y, e, 0, *trackers, output, output_sm))
+    pred_o, hit_o = stats.layer_tracker(output, b_y.numpy())
+    for e in range(E):
+        assert trackers[0][e] == set(np.flatnonzero(hit_o[e]).tolist())
+        assert trackers[1][e] == set(np.flatnonzero(~hit_o[e]).tolist())
+        assert all(int(trackers[2][e][i]) == pred_o[e, i] for i in range(B))
+    out["trk_mean_logits"], out["trk_mean_probs"], out["trk_labels"] = mean_logits, mean_probs, b_y.numpy()
+    out["trk_pred"] = pred_o
+    print("extra cases (p_int, order 2, binary branches, float64-only probabilities, layer trackers) - "
+          "oracle == reference source")
 
 
 if __name__ == "__main__":

@@ -1,7 +1,14 @@
-"""GPU: BASELINE.json's full sizes (the oracle would need minutes here), checked through size-independent
-properties of the path: normalisation, determinism, shard invariance (global Philox sample index), exit-ensemble
-definition, Monte-Carlo consistency of the mask stream, and agreement of the tensor-core path with the exact fp32
-path on the same masks."""
+"""GPU: BASELINE.json's full sizes.
+
+* `test_full_size_rows_vs_oracle`: every BASELINE config (C2 S=32 B=256, C3 Masksembles S=4 B=256 C=100, C4 VGG-19
+  S=64 B=512) runs at its REAL batch size and sample count, and rows from the head, the middle (a tile / cluster-pair
+  boundary) and the tail of the batch are compared with the oracle evaluated on just those images: Philox element
+  indices are per image within the batch, so the oracle injects the masks of batch position `batch_offset + i`
+  (oracle.philox.keep_mask).  This exercises the tile-straddling, grid-stride and `cta_group::2` tail paths at
+  M = 8 192 images against the reference's arithmetic, not only against properties.
+* size-independent properties of the path: normalisation, determinism, shard invariance (global Philox sample index),
+  exit-ensemble definition, Monte-Carlo consistency of the mask stream, and agreement of the tensor-core path with the
+  exact fp32 path on the same masks."""
 import numpy as np
 import pytest
 import torch
@@ -9,6 +16,51 @@ import torch
 from bayesnn_fpga_b200 import mc_predict, resnet18, vgg19
 
 pytestmark = pytest.mark.gpu
+
+# (bench.py workload, oracle case of tests/cases.py, p, rows checked: (first image, count))
+FULL = {
+    "c2": ("resnet18_mcd_block", 0.5, [(0, 6), (125, 6), (250, 6)]),
+    "c3": ("resnet18_mask_block", 0.0, [(0, 6), (125, 6), (250, 6)]),
+    "c4": ("vgg19_mcd_last3", 0.5, [(0, 4), (253, 6), (508, 4)]),
+}
+
+
+@pytest.mark.parametrize("wl", sorted(FULL))
+def test_full_size_rows_vs_oracle(wl):
+    import bench
+    from tests.cases import oracle_run
+    from tests.gpu_util import report
+    tag, p, rows = FULL[wl]
+    _, kind, B, S, classes = bench.WORKLOADS[wl]
+    model = bench.build_model(kind, classes)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.cuda()
+    x = torch.randn(B, *bench.input_shape(kind), generator=torch.Generator().manual_seed(100))
+    seed = 0x5EED
+    want = []
+    for first, n in rows:                      # the oracle sees ONLY these images, with the masks of their batch slots
+        want.append(oracle_run(tag, sd, x[first:first + n], S, seed, p, batch_offset=first))
+    cat = lambda k: np.concatenate([w[k] for w in want], axis=1)
+    idx = np.concatenate([np.arange(f, f + n) for f, n in rows])
+    scale = max(1.0, float(np.abs(cat("mean_logits")).max()))
+    for dt, ptol, ltol in (("fp16", 1e-3, 1e-3), ("fp32", 1e-5, 1e-5)):
+        for m in model.modules():              # Masksembles counters: every run starts from the oracle's cnt0 = 0
+            if hasattr(m, "cnt"):
+                m.cnt = 0
+        r = mc_predict(model, x, S, seed=seed, dtype=dt)
+        got_p = r.mean_probs.double().cpu().numpy()[:, idx]
+        got_l = r.mean_logits.double().cpu().numpy()[:, idx]
+        got_e = r.ens_probs.double().cpu().numpy()[:, idx]
+        perr = float(np.abs(got_p - cat("mean_probs")).max())
+        lerr = float(np.abs(got_l - cat("mean_logits")).max())
+        eerr = float(np.abs(got_e - cat("ens_probs")).max())
+        top2 = np.sort(cat("mean_probs"), axis=-1)[..., -2:]
+        clear = (top2[..., 1] - top2[..., 0]) > 2 * ptol
+        same = bool((got_p.argmax(-1)[clear] == cat("mean_probs").argmax(-1)[clear]).all())
+        report(test="full_size_rows_vs_oracle", workload=wl, dtype=dt, B=B, S=S, rows=rows, prob_err=perr, logit_err=lerr,
+               ens_prob_err=eerr, logit_scale=scale, argmax_same=same)
+        assert perr <= ptol and eerr <= ptol and lerr <= ltol * scale and same
+        model.bnn_engine(dt).release_buffers()
 
 
 def _c2_model(classes=10):

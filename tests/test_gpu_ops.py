@@ -184,8 +184,12 @@ def test_calibration_bins_and_ece(lib):
         p, lab = z["p%d" % k], z["label%d" % k]
         onehot = np.eye(p.shape[1])[lab]
         got = fa.ece_hist_binary(p, onehot)
-        assert abs(got - float(z["ece%d" % k])) < 1e-4            # reference's own ece_hist_binary value
-        assert abs(fa.ece_width(p, lab) - stats.ece_width(p.astype(np.float32), lab)) < 1e-5
+        report(test="ece_hist_binary", case=k, diff=abs(got - float(z["ece%d" % k])))
+        assert abs(got - float(z["ece%d" % k])) < 2e-7            # reference's own ece_hist_binary value (float32 sum)
+        assert abs(fa.ece_width(p, lab) - stats.ece_width(p, lab)) < 1e-12
+        # the statistic hls4ml_pred.py:90-91 really computes (probabilities re-soft-maxed by tfp) vs its restatement
+        assert abs(fa.ece_tfp_as_called(p, lab) - stats.ece_tfp_as_called(p, lab)) < 1e-6
+        assert abs(fa.ece_tfp_as_called(p, lab) - fa.ece_width(p, lab)) > 1e-3      # ... and it is a different number
     assert fa.ece_width(np.zeros((0, 10)), np.zeros(0, dtype=np.int64)) == 0.0        # empty dataset
     # NLL / MSE / accuracy of ece_eval_binary (results_analyzer.py:497-503) on the device vs the float64 restatement
     for k in range(3):
@@ -193,8 +197,42 @@ def test_calibration_bins_and_ece(lib):
         onehot = np.eye(p.shape[1])[lab]
         nll, mse, acc = stats.nll_mse_acc(p, onehot)
         ece, g_nll, g_mse, g_acc = fa.ece_eval_binary(p, onehot)
-        assert abs(g_nll - nll) < 1e-5 * max(1.0, nll) and abs(g_mse - mse) < 1e-6 and abs(g_acc - acc) < 1e-7
-        assert abs(ece - stats.ece_kde(p, onehot)) < 1e-4         # the ECE of ece_eval_binary is the KDE one (:503)
+        assert abs(g_nll - nll) < 1e-12 * max(1.0, nll) and abs(g_mse - mse) < 1e-12 and g_acc == acc
+        assert abs(ece - stats.ece_kde(p, onehot)) < 1e-8         # the ECE of ece_eval_binary is the KDE one (:503)
+
+
+def test_statistics_branches_frozen_from_the_reference_source(lib):
+    """ece_kde_binary with a separate integration set p_int / order 2 / the binary (C == 2) joint-calibration branch,
+    ece_hist_binary's binary branch, and ece_eval_binary on probabilities only float64 can represent (NLL clip 1e-256):
+    device (float64) vs values frozen from the reference's own source (tests/golden/analysis.npz)."""
+    from bayesnn_fpga_b200.results_analyzer import FullAnalysis
+    from tests.cases import GOLDEN
+    z = np.load(GOLDEN + "/analysis.npz")
+
+    class Dummy:
+        n_exits, out_dim = 1, 10
+    fa = FullAnalysis(Dummy(), None, run=False)
+    p, p_int, lab = z["kde_p"], z["kde_p_int"], z["kde_lab"]
+    onehot = np.eye(10)[lab]
+    got = [fa.ece_kde_binary(p, onehot, p_int=p_int), fa.ece_kde_binary(p, onehot, p_int=p_int, order=2),
+           fa.ece_kde_binary(p, onehot, order=2)]
+    pb, pb_int, labb = z["bin_p"], z["bin_p_int"], z["bin_lab"]
+    onehot_b = np.eye(2)[labb]
+    got_b = [fa.ece_kde_binary(pb, onehot_b), fa.ece_kde_binary(pb, onehot_b, p_int=pb_int),
+             fa.ece_kde_binary(pb, onehot_b, order=2)]
+    d1, d2 = np.abs(np.asarray(got) - z["kde_vals"]).max(), np.abs(np.asarray(got_b) - z["bin_kde_vals"]).max()
+    hist = [fa.ece_hist_binary(pb, onehot_b), fa.ece_hist_binary(pb, onehot_b, n_bins=10, order=2),
+            fa.ece_hist_binary(p, onehot), fa.ece_hist_binary(p, onehot, n_bins=7)]
+    d3 = np.abs(np.asarray(hist) - z["hist_vals"]).max()
+    eb = np.asarray(fa.ece_eval_binary(pb, onehot_b))
+    eu = np.asarray(fa.ece_eval_binary(z["under_p"], onehot))
+    d4, d5 = np.abs(eb - z["bin_eval"]).max(), np.abs(eu - z["under_eval"]) / np.maximum(1.0, np.abs(z["under_eval"]))
+    report(test="stats_branches", kde_p_int=float(d1), kde_binary=float(d2), hist=float(d3), eval_binary=float(d4),
+           eval_underflow=float(d5.max()), nll_underflow=float(eu[1]))
+    assert d1 < 1e-8 and d2 < 1e-8 and d3 < 2e-7 and d4 < 1e-8 and d5.max() < 1e-8
+    assert eu[1] > 87.4 / 7                                        # mean NLL carries the 589.5-per-image penalties
+    with pytest.raises(ValueError):
+        fa.ece_kde_binary(p, onehot, p_int=pb_int)
 
 
 TC_SHAPES = [
@@ -480,7 +518,7 @@ def test_full_analysis_confidence_exiting_flops_and_kde_ece(lib):
             accu, ece, nll = fa.confidence_exiting(thr, p_evals, onehot, diff=diff)
             report(test="confidence_exiting", model=mt, thr=thr, diff=diff, d_acc=abs(accu - row[2]), d_ece=abs(ece - row[3]),
                    d_nll=abs(nll - row[4]))
-            assert abs(accu - row[2]) < 1e-6 and abs(ece - row[3]) < 1e-4 and abs(nll - row[4]) < 1e-5 * max(1.0, row[4])
+            assert abs(accu - row[2]) < 1e-12 and abs(ece - row[3]) < 1e-8 and abs(nll - row[4]) < 1e-12 * max(1.0, row[4])
             got = []
             for eo in (True, False):
                 fa.exit_only = eo
@@ -493,11 +531,11 @@ def test_full_analysis_confidence_exiting_flops_and_kde_ece(lib):
             ece, nll, mse, accu = fa.ece_eval_binary(p_evals[e], onehot)
             w = z["per_exit%d" % k][e]
             report(test="kde_ece", model=mt, exit=e, ece=ece, want=float(w[0]))
-            assert abs(ece - w[0]) < 1e-4 and abs(nll - w[1]) < 1e-5 * max(1.0, w[1]) and abs(mse - w[2]) < 1e-6 \
-                and abs(accu - w[3]) < 1e-6
+            assert abs(ece - w[0]) < 1e-8 and abs(nll - w[1]) < 1e-12 * max(1.0, w[1]) and abs(mse - w[2]) < 1e-12 \
+                and abs(accu - w[3]) < 1e-12
     # the KDE kernel alone against the float64 estimator, incl. flags and mirroring
     rng = np.random.RandomState(3)
-    data = rng.beta(5, 2, 700).astype(np.float32)
+    data = rng.beta(5, 2, 700)
     flags = (rng.rand(700) > 0.4).astype(np.int32)
     G, x0, dx, bw = 4096, -0.6, 2.2 / 4095, 0.013
     out = torch.zeros(G, dtype=torch.float64, device="cuda")

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import masksembles as o_masks
-from oracle import philox, seeded, stats
+from oracle import nets, philox, seeded, stats
 from tests.cases import CASES, GOLDEN, build_seeded, load_golden, oracle_run
 
 
@@ -117,7 +117,64 @@ def test_analysis_statistics_oracle_matches_reference_fixture():
         assert idx.min() >= 1                                   # the reference never exits at exit 0 (:612)
         if k == 0:                                              # KDE-ECE: one exit is enough for the CPU suite
             assert abs(stats.ece_kde(p_evals[1], onehot) - z["per_exit%d" % k][1, 0]) < 1e-12
+    # branches frozen by extra_cases(): separate integration set, order 2, binary joint calibration, float64-only inputs
+    onehot = np.eye(10)[z["kde_lab"]]
+    assert abs(stats.ece_kde(z["kde_p"], onehot, p_int=z["kde_p_int"], order=2) - z["kde_vals"][1]) < 1e-12
+    onehot_b = np.eye(2)[z["bin_lab"]]
+    assert abs(stats.ece_kde(z["bin_p"], onehot_b, p_int=z["bin_p_int"]) - z["bin_kde_vals"][1]) < 1e-12
+    assert abs(stats.ece_hist(z["bin_p"], onehot_b) - z["hist_vals"][0]) < 1e-7
+    assert abs(stats.nll_mse_acc(z["under_p"], onehot)[0] - z["under_eval"][1]) < 1e-9
     # the exact estimator integrates to one and reproduces a closed form at a single point
     grid = np.linspace(-1, 1, 4001)
     dens = stats.kde_triweight_exact(np.array([0.0]), 0.1, grid)
     assert abs(np.sum(dens) * (grid[1] - grid[0]) - 1.0) < 1e-6 and abs(dens[2000] - 35.0 / 32.0 / 0.3) < 1e-12
+
+
+def test_layer_trackers_use_the_argmax_of_the_mean_logits():
+    """_update_layer_tracker (results_analyzer.py:272-286) takes `output[output_id].max(1)`: the argmax of the mean
+    LOGITS.  Fixture: a batch where that differs from the argmax of the mean probabilities, predictions frozen from
+    the reference's own source; the oracle restatement and the product's host function must both reproduce them."""
+    from bayesnn_fpga_b200.results_analyzer import layer_hits
+    z = np.load(GOLDEN + "/analysis.npz")
+    ml, mp, lab, want = z["trk_mean_logits"], z["trk_mean_probs"], z["trk_labels"], z["trk_pred"]
+    assert (ml.argmax(-1) != mp.argmax(-1)).sum() >= 5
+    pred_o, hit_o = stats.layer_tracker([torch.from_numpy(m) for m in ml], lab)
+    assert (pred_o == want).all()
+    pred, good, bad = layer_hits([torch.from_numpy(m) for m in ml], lab)
+    assert (pred == want).all()
+    for e in range(ml.shape[0]):
+        assert good[e] == set(np.flatnonzero(want[e] == lab).tolist()) and bad[e] == set(np.flatnonzero(want[e] != lab).tolist())
+
+
+def test_tfp_ece_as_called_restatement():
+    """ece_tfp_as_called: probabilities re-soft-maxed, [lo, hi) bins.  For C classes the re-soft-maxed top probability
+    lies in [1/C, e/(e + C - 1)], so with 10 classes only bins 1-2 can be hit and the value is ~|accuracy - 0.2|."""
+    rng = np.random.RandomState(0)
+    logits = 3 * rng.randn(500, 10)
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    lab = np.where(rng.rand(500) < 0.8, p.argmax(1), rng.randint(0, 10, 500))
+    v = stats.ece_tfp_as_called(p, lab)
+    acc = (p.argmax(1) == lab).mean()
+    assert abs(v - abs(acc - 0.2)) < 0.06 and abs(v - stats.ece_width(p, lab)) > 0.3
+    # two-bin closed form: all predictions [1, 0] -> softmax top = e / (e + 1) = 0.731 -> bin 7, all correct
+    q = np.tile(np.array([[1.0, 0.0]]), (8, 1))
+    assert abs(stats.ece_tfp_as_called(q, np.zeros(8, dtype=np.int64)) - (1 - np.e / (np.e + 1))) < 1e-6
+
+
+def test_mask_contract_rows_of_a_larger_batch():
+    """Element indices are per image WITHIN the batch: the masks of rows [o, o + b) of a B-image batch are a slice of
+    the full mask - what lets the full-size GPU tests check rows of a B = 256 / 512 run against the oracle."""
+    for shape, mode in (((6, 12, 3, 5), "element"), ((9, 7), "element"), ((9, 7, 4, 4), "channel")):
+        full = philox.keep_mask(7, 2, 5, shape, 0.3, mode)
+        for off, n in ((0, 2), (3, 2), (5, 1)):
+            part = philox.keep_mask(7, 2, 5, (n,) + shape[1:], 0.3, mode, batch_offset=off)
+            assert (full[off:off + n] == part).all()
+    x = seeded.seeded_input((5, 1, 28, 28), seed=4)
+    sd = seeded.seeded_state_dict(nets.LENET_SHAPES, seed=3)
+    spec = nets.SiteSpec("mc", 0.2)
+    with torch.no_grad():
+        whole = nets.lenet_forward(sd, x, nets.InjectedSites(spec, 9, 1))
+        tail = nets.lenet_forward(sd, x[3:], nets.InjectedSites(spec, 9, 1, batch_offset=3))
+    for a, b in zip(whole, tail):
+        assert torch.allclose(a[3:], b, atol=1e-6)
