@@ -164,3 +164,36 @@ def test_keras_style_strategy_conversion_runs_fused():
     pre, suf = eng.graph.macs()
     assert suf == 512 * 64 + 64 * 10 and pre == 8 * 8 * 16 * 27 + 4 * 4 * 32 * 144   # the convolutions are paid once, not S times
     assert (got.double().cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("tag", ["mlp", "cnn", "nested"])
+def test_converter_matches_the_reference_converter_fixture(tag):
+    """nn2bnn.MCDropout (fused plan AND stand-alone passes) vs outputs frozen from the reference's OWN converter modules
+    (`Hardware_Artifact/converter/pytorch/{nn2bnn,Dropouts}.py` imported in the build container with the Philox masks
+    injected, tests/golden/make_golden_converter.py): per-pass outputs and the mean over nSamples."""
+    import os
+    from oracle import seeded
+    from tests.cases import GOLDEN
+    from tests.nets_converter import NETS
+    z = np.load(os.path.join(GOLDEN, "converter.npz"))
+    make, in_shape, p, n_samples, seed = NETS[tag]
+    x = torch.from_numpy(z[tag + "/x"]).cuda()
+    want_mean, want_passes = z[tag + "/mean"], z[tag + "/passes"]
+    scale = max(1.0, float(np.abs(want_passes).max()))
+
+    def build(**kw):
+        torch.manual_seed(0)
+        net = make()
+        net.load_state_dict(seeded.seeded_state_dict(net.state_dict(), seed=77))
+        return nn2bnn.MCDropout(net.cuda(), nSamples=n_samples, p=p, **kw).reseed(seed).eval()
+    errs = {}
+    for dtype, tol in (("fp32", 1e-5), ("fp16", 2e-3)):
+        got = build(dtype=dtype)(x)
+        errs[dtype] = float(np.abs(got.double().cpu().numpy() - want_mean).max())
+        assert errs[dtype] <= tol * scale, (tag, dtype, errs)
+    # the reference's literal loop: nSamples stand-alone passes through the wrapped modules
+    loop = build(fused=False)
+    passes = np.stack([loop.model(x).double().cpu().numpy() for _ in range(n_samples)])
+    errs["standalone_passes"] = float(np.abs(passes - want_passes).max())
+    assert errs["standalone_passes"] <= 1e-5 * scale
+    report(test="converter_vs_reference_fixture", net=tag, scale=scale, **errs)

@@ -438,3 +438,22 @@ def test_plans_live_outside_the_module_and_follow_the_parameters(tmp_path):
     assert "x" in _plans.plans_for(m)                 # and an untouched model keeps its plans
     _plans.drop(m)
     assert _plans.plans_for(m) == {}
+
+
+def test_converter_structure_matches_the_reference_converter():
+    """`_convert_model` wraps exactly the leaves the reference's converter wraps, with the same wrapper class and p, in
+    the same places (fixture frozen from the reference's own nn2bnn.py / Dropouts.py, make_golden_converter.py);
+    `extra_repr` and the constructor's ValueError read the same."""
+    from bayesnn_fpga_b200 import Dropouts, nn2bnn
+    from tests.golden.make_golden_converter import structure
+    from tests.nets_converter import NETS
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "converter.npz"))
+    for tag, (make, in_shape, p, n_samples, seed) in NETS.items():
+        w = nn2bnn.MCDropout(make(), nSamples=n_samples, p=p)
+        assert structure(w.model) == [str(s) for s in z[tag + "/structure"]], tag
+        assert w.extra_repr() == str(z[tag + "/repr"][0])
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ValueError) as e:
+            Dropouts.BayesianDropout(nn.Linear(2, 2), bad)
+        assert str(e.value) == str(z["err/%g" % bad][0])
+    assert Dropouts.BayesianDropout2D(nn.Conv2d(1, 1, 1), 0.25).extra_repr() == str(z["extra_repr"][0])
