@@ -347,6 +347,23 @@ __global__ void __launch_bounds__(256) maxpool_vec8_kernel(const T* __restrict__
   *reinterpret_cast<Vec8<T>*>(y + i * 8) = o;
 }
 
+// ------------------------------------------------------------------------------------------
+// per-channel affine [+ ReLU], NHWC: y = relu?(x * scale[c] + bias[c]) - an eval-mode BatchNorm2d that cannot be folded
+// into the convolution in front of it because a stochastic site sits in between (the converter's
+// BayesianDropout2D(conv) -> BatchNorm2d -> ReLU chains, Hardware_Artifact/converter/pytorch/nn2bnn.py:32-45)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) channel_affine_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ bias, int C, int relu,
+                                                             int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  float v = to_f32<T>(x[i]) * __ldg(scale + c) + __ldg(bias + c);
+  if (relu) v = fmaxf(v, 0.f);
+  y[i] = from_f32<T>(v);
+}
 
 // Masksembles "gathered" layout: y[s][b][px][j] = x[s or 0][b][px][idx[row(s)][j]] for the kept channels of sample
 // s's mask row (utils.py:165-168 rotation), zeros in the padding slots.  One thread = 8 consecutive output slots of
@@ -502,6 +519,21 @@ int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int
     using T = std::remove_pointer_t<decltype(tag)>;
     dropout_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)x, (T*)y, n_per, per_image, C, S_local, x_has_samples, dp);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  });
+}
+
+int bnn_channel_affine(const void* x, void* y, const float* scale, const float* bias, int dtype, int64_t pixels, int C,
+                       int relu, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && y && scale && bias && pixels >= 0 && C > 0, "bnn_channel_affine: bad arguments");
+  const int64_t total = pixels * C;
+  if (total == 0) return BNN_OK;
+  return dispatch_dtype(dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    channel_affine_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x, (T*)y, scale, bias, C, relu, total);
     BNN_LAUNCH_OK();
     return BNN_OK;
   });

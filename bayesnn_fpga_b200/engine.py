@@ -59,7 +59,7 @@ class Site:
 
 @dataclass
 class Op:
-    kind: str                            # conv | site | maxpool | head
+    kind: str                            # conv | site | maxpool | affine | head
     src: Optional[TensorRef] = None
     dst: Optional[TensorRef] = None
     res: Optional[TensorRef] = None
@@ -142,6 +142,17 @@ class Graph:
     def maxpool(self, src, k, name=""):
         dst = self._new(src.C, src.H // k, src.W // k, src.stoch)
         self.ops.append(Op("maxpool", src, dst, pool_k=k, name=name))
+        return dst
+
+    def affine(self, src, bn, relu=False, name=""):
+        """Eval-mode BatchNorm2d [+ ReLU] as a stand-alone per-channel affine (a BN that cannot be folded into the
+        convolution in front of it: a stochastic site sits in between)."""
+        f64 = lambda t: t.detach().cpu().double()
+        g = f64(bn.weight) / torch.sqrt(f64(bn.running_var) + bn.eps)
+        b = f64(bn.bias) - f64(bn.running_mean) * g
+        dst = self._new(src.C, src.H, src.W, src.stoch)
+        self.ops.append(Op("affine", src, dst, weight=g.float().contiguous(), bias=b.float().contiguous(), relu=relu,
+                           name=name))
         return dst
 
     def head(self, src, lin, site=None, name=""):
@@ -388,6 +399,9 @@ class Engine:
                     w = torch.cat([w.reshape(w.shape[0], -1), op.sc["weight"]], dim=1).contiguous()
                 op.d_w = w.to(dev, self.tdtype if op.use_tc else torch.float32)
                 op.d_b = op.bias.to(dev, torch.float32)
+            elif op.kind == "affine":
+                op.d_w = op.weight.to(dev, torch.float32)
+                op.d_b = op.bias.to(dev, torch.float32)
             elif op.kind == "head":
                 op.d_w = op.weight.t().contiguous().to(dev, torch.float32)      # [F][C] for the head kernel
                 op.d_b = op.bias.to(dev, torch.float32)
@@ -588,8 +602,10 @@ class Engine:
         s = st["sums"]
         return s[:n].view(E, B, C), s[n:2 * n].view(E, B, C), s[2 * n:].view(E, B)
 
-    def _launch(self, kernel, name, flops, nbytes, call):
-        """One C-ABI launch; with profiling on, bracket it with CUDA events on the launching stream."""
+    def _launch(self, kernel, name, flops, nbytes, call, flops_exec=None):
+        """One C-ABI launch; with profiling on, bracket it with CUDA events on the launching stream.
+        flops = ALGORITHMIC work of the reference's layer (the hook-derived MAC count); flops_exec = what
+        the kernel really multiplies when that is LESS (3x3 windows on 1x1 maps run their centre tap only)."""
         if self._prof is None:
             _lib.check(call())
         else:
@@ -597,7 +613,7 @@ class Engine:
             e0.record()
             _lib.check(call())
             e1.record()
-            self._prof.append((kernel, name, flops, nbytes, e0, e1))
+            self._prof.append((kernel, name, flops, nbytes, e0, e1, flops if flops_exec is None else flops_exec))
         self.launches += 1
 
     def enqueue(self, x, S_local, sample0=0, seed=0x5EED, accumulate=False, want_logits=False, mask_offset=None):
@@ -707,7 +723,12 @@ class Engine:
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
                         op.src.H, op.src.W, op.src.C, op.dst.C, kh, kw, op.stride, op.pad, int(op.relu),
                         ctypes.byref(dd), stream)
-                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name, flops, nbytes, call)
+                # bnn_conv2d_tc runs only the centre tap of a 3x3 window on a 1x1 map (conv_tc.cu, bit-exact): the other
+                # eight taps are zero padding and must not count as executed work
+                tap_skip = (op.use_tc and kh == 3 and op.src.H == 1 and op.src.W == 1 and op.stride == 1 and
+                            os.environ.get("BNN_TC_NO_TAP_SKIP") is None)
+                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name, flops, nbytes, call,
+                             flops_exec=flops / 9 if tap_skip else None)
             elif op.kind == "site":
                 if S_local == 0:
                     continue
@@ -721,6 +742,14 @@ class Engine:
                 self._launch("dropout", op.name, 0, nbytes, lambda: lib.bnn_dropout(
                     _ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), self.dcode, per_image, op.src.C, S_local,
                     int(op.src.stoch), ctypes.byref(dd), stream))
+            elif op.kind == "affine":
+                n_img = (S_local if op.dst.stoch else 1) * B
+                if n_img == 0:
+                    continue
+                px = n_img * op.src.H * op.src.W
+                self._launch("affine", op.name, 0, 2 * px * op.src.C * es, lambda: lib.bnn_channel_affine(
+                    _ptr(acts[op.src.id]), _ptr(acts[op.dst.id]), _ptr(op.d_w), _ptr(op.d_b), self.dcode, px, op.src.C,
+                    int(op.relu), stream))
             elif op.kind == "maxpool":
                 n_img = (S_local if op.dst.stoch else 1) * B
                 if n_img == 0:
@@ -752,7 +781,8 @@ class Engine:
 
     def profile_step(self, x, S_local, seed=0x5EED):
         """Device time of every launch of one step (CUDA events on the launching stream).
-        -> list of {kernel, name, ms, flops (algorithmic), bytes (algorithmic)} in launch order."""
+        -> list of {kernel, name, ms, flops (algorithmic), flops_exec (executed <= algorithmic), bytes (algorithmic)}
+        in launch order."""
         x = x.to(self.device, torch.float32)
         with torch.cuda.device(self.device):
             self._prof = []
@@ -763,7 +793,8 @@ class Engine:
                 rec = self._prof
             finally:
                 self._prof = None
-        return [{"kernel": k, "name": n, "flops": f, "bytes": b, "ms": e0.elapsed_time(e1)} for k, n, f, b, e0, e1 in rec]
+        return [{"kernel": k, "name": n, "flops": f, "flops_exec": fx, "bytes": b, "ms": e0.elapsed_time(e1)}
+                for k, n, f, b, e0, e1, fx in rec]
 
     def finalize(self, st, B, S_total):
         g = self.graph

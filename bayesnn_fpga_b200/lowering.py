@@ -10,6 +10,7 @@ samples is accumulated on the device.
 
 Supported vocabulary (anything else raises ``NotImplementedError`` naming the node - there is no silent fallback):
   Conv2d (square kernel, dilation 1, groups 1) [-> BatchNorm2d] [-> + residual] [-> ReLU], Linear [-> ReLU],
+  BatchNorm2d [-> ReLU] behind a stochastic layer (eval mode; a stand-alone per-channel affine),
   MaxPool2d (kernel == stride, no padding) in either order with ReLU, Flatten / flatten / view(B, -1),
   AdaptiveAvgPool2d(1) / full-map AvgPool2d, Dropout / Identity (eval: no-ops), MCDropout, Masksembles1D/2D,
   BayesianDropout(Linear | MaxPool2d), BayesianDropout2D(Conv2d), one or several (list / tuple) outputs.
@@ -278,6 +279,19 @@ class _Lowering:
                     if grp["add"] is not None:
                         self.consumed.add(grp["add"])
                     self._emit_conv_group(grp)
+            elif isinstance(m, nn.BatchNorm2d):
+                # a BatchNorm the convolution in front could not absorb (a stochastic site sits in between, e.g. the
+                # converter's BayesianDropout2D(conv) -> BN -> ReLU): per-channel affine [+ the ReLU behind it]
+                if m.training or not m.track_running_stats:
+                    self._fail(node, "BatchNorm2d must be in eval mode with running statistics")
+                nxt = self._sole_user(node)
+                relu = nxt is not None and self._is_relu(nxt)
+                t = g.affine(self.val[node.args[0]], m, relu=relu, name=node.name)
+                self.val[node] = t
+                if relu:
+                    self.nonneg.add(t.id)
+                    self.val[nxt] = t
+                    self.consumed.add(nxt)
             elif self._is_add(node):
                 if node not in self.deferred:
                     self._fail(node, "an add is only supported as the residual of a convolution (conv [-> BN] -> +)")

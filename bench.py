@@ -2,15 +2,19 @@
 """Benchmark of the S-sample multi-exit inference path (BASELINE.json metric: images/sec at S MC samples,
 multi-exit ResNet-18, 32x32, and % of tensor-core peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--dtype fp16|bf16|fp32]
-    python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--dtype fp16|bf16|fp32]
+    python bench.py --impl reference ...        # the reference's own CPU implementation (oracle/_ref) on the host cores
 
 A "step" is one pass of the hot path over one batch: B images x S stochastic samples -> per-exit predictive
-mean / entropy statistics.  N = 1 runs BASELINE.json configs[1] (ResNet-18 ME, MC dropout after every stage +
-at every exit, S = 32, B = 256, 3x32x32).  N > 1 (torchrun, one rank per GPU): every rank owns its own batch of
-B images (weak scaling, global batch N*B) and the per-exit statistics are all-gathered over NCCL inside the
-timed region; `--workload c5` instead shards the S = 128 samples of ONE batch over the ranks (strong scaling)
-with a single all-reduce of the per-exit sums.
+mean / entropy statistics.  The HEADLINE (`value`, `e2e`, `roofline`) is BASELINE.json configs[1] (C2: ResNet-18 ME,
+MC dropout after every stage + at every exit, S = 32, B = 256, 3x32x32).  The same JSON line carries, each measured in
+its own short timed region with its own clock sample:
+  * N = 1:  `configs` = {c1, c3, c4, c5} (LeNet S=8; Masksembles S=4 C=100; VGG-19 S=64 B=512; ResNet S=128 on one GPU)
+  * N > 1:  the headline is C2 weak-scaled (every rank its own B images; one `all_gather_into_tensor` of the
+            statistics inside the timed region) and `c5_strong` = BASELINE configs[4]: the S = 128 samples of ONE batch
+            sharded over the ranks with a single all-reduce of the per-exit sums (strong scaling), with the unsharded
+            single-GPU time measured in the same process for `efficiency_vs_n1`.
+`--workload cX` makes cX the headline instead (debugging / profiling).
 """
 import argparse
 import json
@@ -71,6 +75,10 @@ def build_model(kind, classes):
     return m.eval()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref, staged by oracle/make_ref.py) - or, where no PyTorch
+# reference exists (LeNet) or the staged tree is missing, the oracle port
+# ---------------------------------------------------------------------------------------------------------------
 def oracle_forward_fn(kind):
     from oracle import nets
     if kind == "lenet":
@@ -80,21 +88,23 @@ def oracle_forward_fn(kind):
     return lambda sd, x, site: nets.vgg19_forward(sd, x, site, True, (2, 3, 4))
 
 
-def time_cpu_reference(kind, classes, S_nominal, budget_images=256, passes=4):
-    """The reference's algorithm (results_analyzer.py:236-270: S sequential full forward passes, softmax per exit
-    per pass, fp64 host means) through the oracle port, torch's own dropout RNG, all host threads.
-    Bounded sample: `budget_images` images x `passes` passes, scaled linearly to S_nominal passes."""
+def cpu_step_fn(kind, classes, S):
+    """-> (step(x) running the FULL S passes of the reference's `_get_output` on the host for the images in x, kind)
+    kind "reference": the unmodified reference modules from oracle/_ref; "port": the oracle restatement."""
     import torch
-    from oracle import nets, stats
     torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import ref_arm
+    if kind != "lenet" and ref_arm.available():
+        runner = ref_arm.ReferenceRunner(kind, classes, S)
+        return runner.step, "reference"
+    from oracle import nets, stats
     model = build_model(kind, classes)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
     spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.2 if kind == "lenet" else 0.5, tables)
-    x = torch.randn(budget_images, *input_shape(kind))
     fwd = oracle_forward_fn(kind)
 
-    def run():
+    def step(x):
         sites = nets.TorchRngSites(spec)
 
         def one(i):
@@ -102,36 +112,88 @@ def time_cpu_reference(kind, classes, S_nominal, budget_images=256, passes=4):
             sites.next_pass()
             return out
         with torch.no_grad():
-            stats.mc_get_output(one, passes)
-    run()                                   # warm-up
+            return stats.mc_get_output(one, S)
+    return step, "port"
+
+
+def calibrate_images(step, kind, B, budget_s):
+    """How many images of the batch one CPU step may take to stay inside `budget_s` (full S passes each; images are
+    independent, so images/s does not depend on the slice).  -> (n_images, seconds of the calibration step)"""
+    import torch
+    n0 = min(B, 8)
+    x = torch.randn(n0, *input_shape(kind))
+    step(x)                                         # first call: allocator / thread-pool warm-up
+    t = time.perf_counter()
+    step(x)
+    dt = time.perf_counter() - t
+    n = int(budget_s / max(dt / n0, 1e-9))
+    n = max(8, min(B, n - n % 8 if n >= 8 else 8))
+    return n, dt
+
+
+def time_cpu_reference(kind, classes, S, B, budget_s=6.0):
+    """cpu_baseline: median of 3 steps of the reference's S-pass loop over a bounded slice of the batch."""
+    import torch
+    step, impl = cpu_step_fn(kind, classes, S)
+    n, _ = calibrate_images(step, kind, B, budget_s)
+    x = torch.randn(n, *input_shape(kind))
     reps = []
     for _ in range(3):
         t = time.perf_counter()
-        run()
+        step(x)
         reps.append(time.perf_counter() - t)
     t_med = sorted(reps)[1]
-    img_per_s = budget_images / (t_med * S_nominal / passes)
-    return {"value": img_per_s, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "%d images x %d of %d passes (full recompute per pass, like the reference), median of 3, "
-                      "scaled linearly to S=%d; %.2f s per repetition" % (budget_images, passes, S_nominal, S_nominal,
-                                                                         t_med)}
+    return {"value": n / t_med, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": impl,
+            "sample": "%d of the batch's %d images x ALL %d passes (FullAnalysis._get_output of %s, full recompute per "
+                      "pass, torch's own dropout RNG, fp64 host means), median of 3 steps of %.2f s" % (
+                          n, B, S, "the unmodified reference modules in oracle/_ref" if impl == "reference"
+                          else "the oracle port", t_med)}
 
 
+def reference_arm(args, wl_name):
+    desc, kind, B, S, classes = WORKLOADS[wl_name]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    warm, reps = max(args.warmup, 1), max(args.steps, 1)
+    step, impl = cpu_step_fn(kind, classes, S)
+    # bounded so that the whole run ends within a few minutes: every step = n images of the batch x ALL S passes
+    n, _ = calibrate_images(step, kind, B, 150.0 / (warm + reps))
+    x = torch.randn(n, *input_shape(kind))
+    for _ in range(warm):
+        step(x)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step(x)
+    dt = (time.perf_counter() - t0) / reps
+    val = n / dt
+    cores = os.cpu_count() or 1
+    sample = "each step = %d of the batch's %d images x ALL %d passes through %s on %d host threads" % (
+        n, B, S, "the unmodified reference (oracle/_ref: models.model_loader.get_network + FullAnalysis._get_output "
+        "source)" if impl == "reference" else "the oracle port (no PyTorch reference exists for this network)", cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch": B, "S": S, "images_per_step": n, "same_S": True, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": impl, "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe): one sampler process,
+    any number of [t0, t1] windows read from it afterwards."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
         self.idx, self.proc, self.lines = device_index, None, []
-        self.t0 = self.t1 = None
-
-    def mark_start(self):
-        self.t0 = time.time()
-
-    def mark_end(self):
-        self.t1 = time.time()
 
     def start(self):
         try:
@@ -149,18 +211,23 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
-        window = "timed region"
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1]
+        where = "timed region"
         if not inside:                       # region shorter than one sampling period: nearest samples
-            inside, window = [ln for (_, ln) in self.lines[-3:]], "nearest samples (timed region < sampling period)"
+            near = sorted(self.lines, key=lambda e: abs(e[0] - 0.5 * (t0 + t1)))[:3]
+            inside, where = [ln for (_, ln) in near], "nearest samples (timed region < sampling period)"
         for ln in inside:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 9:
@@ -176,20 +243,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "sm_mhz_min": sm[0], "power_w_max": max(pw),
-                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
+                "samples": len(sm), "window": where, "seconds": t1 - t0, "reasons": sorted(reasons)}
 
 
-NCU_SUMMARY = "profiles/r01_ncu_conv_tc_full_v3.json"
+NCU_SUMMARY = "profiles/r02_ncu_conv_tc_full.json"
+NCU_SUMMARY_FALLBACK = "profiles/r01_ncu_conv_tc_full_v3.json"
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the 20 launches of one C2 step) from
-    the committed `ncu --set full` summary (tools/ncu_summary.py), or None."""
-    p = os.path.join(ROOT, NCU_SUMMARY)
-    if not os.path.exists(p):
-        return None
-    rows = json.load(open(p))
-    return sum((r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows) / max(len(rows), 1)
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (mean over the conv launches of one C2 step) from
+    the committed `ncu --set full` summary (tools/ncu_summary.py), or (None, None)."""
+    for rel in (NCU_SUMMARY, NCU_SUMMARY_FALLBACK):
+        p = os.path.join(ROOT, rel)
+        if os.path.exists(p):
+            rows = json.load(open(p))
+            return sum((r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows) / max(len(rows), 1), rel
+    return None, None
 
 
 def load_peaks():
@@ -197,50 +266,64 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"burst": d["bf16_tflops"], "sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                "hbm": d["hbm_gbs"], "src": "measured"}
-    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+                "hbm": d["hbm_gbs"], "src": "MEASURED_PEAKS.json"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "src": "B200_PROFILING.md fallback"}
 
 
-def reference_arm(args, wl):
-    desc, kind, B, S, classes = wl
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    warm, reps = max(args.warmup, 1), max(args.steps, 1)
-    # bounded so that the whole run ends within a few minutes: each step = 64 images x 2 passes, scaled to S
-    import torch
-    from oracle import nets, stats
-    torch.set_num_threads(os.cpu_count() or 1)
-    model = build_model(kind, classes)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
-    spec = nets.SiteSpec("mask" if kind == "resnet_mask" else "mc", 0.2 if kind == "lenet" else 0.5, tables)
-    nb, passes = 64, 2
-    x = torch.randn(nb, *input_shape(kind))
-    fwd = oracle_forward_fn(kind)
-
-    def step():
-        sites = nets.TorchRngSites(spec)
-        with torch.no_grad():
-            stats.mc_get_output(lambda i: fwd(sd, x, sites), passes)
-    for _ in range(warm):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        step()
-    dt = (time.perf_counter() - t0) / reps
-    val = nb / (dt * S / passes)
-    sample = "each step = %d images x %d of %d passes on %d host threads, scaled linearly to S=%d" % (
-        nb, passes, S, os.cpu_count() or 1, S)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "S": S, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+def summarize_profile(prof, peaks, clocks, region_s, with_traffic):
+    """Per-launch CUDA-event times of one step -> (roofline of the dominant tensor kernel, per-kernel table with HBM
+    sub-rooflines).  The denominator is chosen from how the TIMED REGION ran: a region of a few tenths of a second at
+    (near) maximum SM clock is the burst regime -> burst peak; seconds-long, power-capped regions -> sustained peak.
+    Both fractions are always printed."""
+    kernels = {}
+    for o in prof:
+        k = kernels.setdefault(o["kernel"], {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0, "flops_exec": 0})
+        k["ms"] += o["ms"]; k["launches"] += 1; k["bytes"] += o["bytes"]; k["flops"] += o["flops"]
+        k["flops_exec"] += o["flops_exec"]
+    total_ms = sum(o["ms"] for o in prof)
+    for name, k in kernels.items():
+        k["share_of_step"] = k["ms"] / total_ms if total_ms else None
+        k["GBps"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
+        k["TFLOPs_exec"] = k["flops_exec"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else None
+        if name in ("dropout", "exit_head", "maxpool", "layout") and k["GBps"] is not None:
+            # HBM-bound kernels: algorithmic bytes (read once + write once) / CUDA-event time vs the measured copy peak
+            k["roofline"] = {"bound": "hbm", "achieved": k["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": k["GBps"] / peaks["hbm"]}
+    sm = (clocks or {}).get("sm_mhz")
+    mx = (clocks or {}).get("sm_max_mhz")
+    burst_regime = region_s < 2.0 and (sm is None or mx is None or sm >= 0.9 * mx)
+    kind = "burst" if burst_regime else "sustained"
+    tc = [o for o in prof if o["kernel"] == "conv_tc"]
+    if tc:
+        fx = sum(o["flops_exec"] for o in tc)
+        fa = sum(o["flops"] for o in tc)
+        t_tc = sum(o["ms"] for o in tc) * 1e-3
+        ach = fx / t_tc / 1e12
+        traffic, src = ncu_traffic() if with_traffic else (None, None)
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
+                "peak": peaks[kind], "unit": "TFLOP/s", "frac": ach / peaks[kind], "peak_kind": kind,
+                "frac_of_burst_peak": ach / peaks["burst"], "frac_of_sustained_peak": ach / peaks["sustained"],
+                "peak_source": "%s: bf16 cuBLAS %s %.1f TFLOP/s chosen because the timed region ran %.2f s at a median "
+                               "%s MHz of %s MHz (burst %.1f / sustained %.1f)" % (
+                                   peaks["src"], kind, peaks[kind], region_s, sm, mx, peaks["burst"],
+                                   peaks["sustained"]),
+                "flops_counted": "EXECUTED multiply-adds (3x3 windows on 1x1 maps run their centre tap only; zero-padded "
+                                 "stem channels and Masksembles-dropped channels are not counted)",
+                "achieved_algorithmic": fa / t_tc / 1e12,
+                "launches_per_step": len(tc), "avg_launch_ms": t_tc * 1e3 / len(tc),
+                "flops_per_launch": fx / len(tc), "share_of_step": t_tc * 1e3 / total_ms,
+                "algorithmic_bytes_per_launch": sum(o["bytes"] for o in tc) / len(tc),
+                "traffic": traffic,
+                "traffic_source": (src + " (ncu --set full --clock-control none over the conv launches of one C2 step: "
+                                   "mean dram__bytes_read.sum + dram__bytes_write.sum per launch)") if src else None}
+    else:
+        flops = sum(o["flops_exec"] for o in prof)
+        t_all = total_ms * 1e-3
+        roof = {"bound": "tensor", "kernel": "conv2d_simt (CUDA cores: fp32 parity path / LeNet)",
+                "achieved": flops / t_all / 1e12, "peak": peaks[kind], "unit": "TFLOP/s",
+                "frac": flops / t_all / 1e12 / peaks[kind], "peak_kind": kind, "peak_source": peaks["src"], "traffic": None,
+                "note": "CUDA-core kernels: no tensor-core claim for this workload"}
+    return roof, kernels
 
 
 def main():
@@ -254,19 +337,16 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch (debugging)")
     ap.add_argument("--samples", type=int, default=0, help="override the workload's S (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="headline only (profiling runs)")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device times of one step")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        return reference_arm(args, wl)
+        return reference_arm(args, args.workload)
 
     import torch
     import torch.distributed as dist
     from bayesnn_fpga_b200 import mc_predict, predict
 
-    desc, kind, B, S, classes = wl
-    B = args.batch or B
-    S = args.samples or S
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,39 +354,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    shard_samples = args.workload == "c5" and world > 1
     W = max(args.warmup, 3)
-
-    model = build_model(kind, classes).to(dev)
-    eng = model.bnn_engine(args.dtype)
-    g = torch.Generator().manual_seed(100 + (0 if shard_samples else rank))
-    x_host = torch.randn(B, *input_shape(kind), generator=g).pin_memory()
-    x_dev = x_host.to(dev)
-    E = eng.graph.n_exits
-    gather_buf = [torch.empty(4 * E * B * classes + 3 * E * B, device=dev) for _ in range(world)] if world > 1 else None
-
-    def step_device():
-        """inputs already resident in HBM"""
-        if shard_samples:
-            s0, sl = predict.shard_samples(S, world, rank)
-            r = eng.run(x_dev, sl, sample0=s0, S_total=S, reduce_fn=predict.allreduce_sums)
-        else:
-            r = eng.run(x_dev, S)
-            if world > 1:      # weak scaling: every rank's statistics are gathered (one small NCCL collective)
-                dist.all_gather(gather_buf, eng._bufs[(B, S, False)]["out"])
-        return r
-
-    out_host = torch.empty((4, E, B, classes), dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        """the public API with HOST buffers: pinned H2D of the batch, D2H of the statistics, every step"""
-        r = mc_predict(model, x_host, S, dtype=args.dtype, distributed=shard_samples)
-        out_host[0].copy_(r.mean_probs, non_blocking=True)
-        out_host[1].copy_(r.mean_logits, non_blocking=True)
-        out_host[2].copy_(r.ens_probs, non_blocking=True)
-        out_host[3].copy_(r.ens_logits, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return r
+    peaks = load_peaks()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~1 s to start: launch it before the first warm-up
 
     def barrier():
         if world > 1:
@@ -314,110 +366,178 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """-> (ms max over ranks, per-rank ms list, wall-clock window).  CUDA events on the launching stream,
+        barrier + synchronize on both sides."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        t1 = time.time()
         ms = e0.elapsed_time(e1)
+        per_rank = [ms]
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            allt = torch.empty(world, device=dev)
+            dist.all_gather_into_tensor(allt, t)
+            per_rank = [float(v) for v in allt.tolist()]
+            ms = max(per_rank)
+        return ms, per_rank, (t0, t1)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                      # nvidia-smi needs ~1 s to start: launch it before the warm-up
-    for _ in range(W):
-        step_device()
-    launches0 = eng.launches
-    sampler.mark_start()
-    ms = timed(step_device, args.steps)
-    sampler.mark_end()
-    launches = eng.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    def measure(wl_name, steps, headline, shard, B_over=0, S_over=0):
+        """One workload on this rank set.  shard: None (N=1) | "batch" (weak: every rank its own batch, statistics
+        all-gathered) | "samples" (strong: the S samples of one batch over the ranks, sums all-reduced)."""
+        desc, kind, B, S, classes = WORKLOADS[wl_name]
+        B, S = B_over or B, S_over or S
+        model = build_model(kind, classes).to(dev)
+        eng = model.bnn_engine(args.dtype)
+        g = torch.Generator().manual_seed(100 + (rank if shard == "batch" else 0))
+        x_host = torch.randn(B, *input_shape(kind), generator=g).pin_memory()
+        x_dev = x_host.to(dev)
+        E = eng.graph.n_exits
+        n_stats = 4 * E * B * classes + 3 * E * B
+        gathered = torch.empty(world * n_stats, device=dev) if shard == "batch" else None
+        s0, sl = predict.shard_samples(S, world, rank) if shard == "samples" else (0, S)
 
-    images_per_step = B * (1 if shard_samples else world)
-    value = images_per_step * args.steps / (ms * 1e-3)
-    e2e_value = images_per_step * args.steps / (ms_e2e * 1e-3)
+        def step_device():
+            """inputs already resident in HBM"""
+            if shard == "samples":
+                return eng.run(x_dev, sl, sample0=s0, S_total=S, reduce_fn=predict.allreduce_sums)
+            r = eng.run(x_dev, S)
+            if shard == "batch":   # ONE NCCL collective on the compute stream right behind the finaliser
+                dist.all_gather_into_tensor(gathered, eng._bufs[(B, S, False)]["out"])
+            return r
 
-    # ---- per-op device times of one step (CUDA events on the launching stream) -> roofline of the dominant kernel
-    prof = eng.profile_step(x_dev, S if not shard_samples else predict.shard_samples(S, world, rank)[1])
-    peaks = load_peaks()
-    tc = [o for o in prof if o["kernel"] == "conv_tc"]
-    pre_macs, suf_macs = eng.graph.macs()
-    if tc:
-        flops = sum(o["flops"] for o in tc)
-        t_tc = sum(o["ms"] for o in tc) * 1e-3
-        ach = flops / t_tc / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": ach,
-                "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"],
-                "peak_source": "%s bf16 cuBLAS sustained (kernel timed inside a long step); burst %.1f" % (
-                    peaks["src"], peaks["burst"]),
-                "launches_per_step": len(tc), "avg_launch_ms": t_tc * 1e3 / len(tc),
-                "flops_per_launch": flops / len(tc), "share_of_step": t_tc * 1e3 / sum(o["ms"] for o in prof),
-                "algorithmic_bytes_per_launch": sum(o["bytes"] for o in tc) / len(tc),
-                "traffic": ncu_traffic() if args.workload == "c2" else None,
-                "traffic_source": NCU_SUMMARY + " (ncu --set full --clock-control none over the 20 conv launches of one "
-                                  "C2 step: mean dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
-        if roof["frac"] > 1.0:
-            roof["note"] = ("above the SUSTAINED cuBLAS figure (dense random operands at the 1 kW cap): this workload's "
-                            "small maps make most im2col taps zero padding, which draws less power, so the SM clock "
-                            "stays higher; against the burst figure the fraction is %.3f" % (ach / peaks["burst"]))
+        out_host = torch.empty((4, E, B, classes), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            """the public API with HOST buffers: pinned H2D of the batch, D2H of the statistics, every step"""
+            r = mc_predict(model, x_host, S, dtype=args.dtype, distributed=(shard == "samples"))
+            out_host[0].copy_(r.mean_probs, non_blocking=True)
+            out_host[1].copy_(r.mean_logits, non_blocking=True)
+            out_host[2].copy_(r.ens_probs, non_blocking=True)
+            out_host[3].copy_(r.ens_logits, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return r
+
+        for _ in range(W):
+            step_device()
+        launches0 = eng.launches
+        ms, per_rank, win = timed(step_device, steps)
+        launches = eng.launches - launches0
+        clocks = sampler.window(*win) if rank == 0 else None
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _, _ = timed(step_e2e, steps)
+        images = B * (world if shard == "batch" else 1)
+        rec = {"workload": desc, "value": images * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps,
+               "steps": steps, "batch_per_gpu": B, "global_batch": images, "S": S, "exits": E, "classes": classes,
+               "partition": shard or "none", "per_rank_ms_per_step": [v / steps for v in per_rank],
+               "e2e": {"value": images * steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / steps,
+                       "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+               "gpu_launches": launches, "clocks": clocks}
+        prof = eng.profile_step(x_dev, sl)
+        roof, kernels = summarize_profile(prof, peaks, clocks, ms * 1e-3, with_traffic=(wl_name == "c2"))
+        pre_macs, suf_macs = eng.graph.macs()
+        rec["algorithmic_gflop_per_image"] = 2e-9 * (pre_macs + S * suf_macs)
+        step_flops = 2.0 * B * (pre_macs + sl * suf_macs) * world        # all ranks (each replicates the prefix)
+        rec["tflops_whole_step"] = step_flops / (ms / steps * 1e-3) / 1e12
+        rec["frac_of_tensor_peak_whole_step"] = {
+            "burst": rec["tflops_whole_step"] / world / peaks["burst"],
+            "sustained": rec["tflops_whole_step"] / world / peaks["sustained"]}
+        rec["roofline"] = roof
+        rec["kernels"] = kernels
+        if kind == "resnet_mask":
+            rec["masksembles_mode"] = eng.gather_mode
+        if args.profile_ops and rank == 0 and headline:
+            for o in prof:
+                print("  %-10s %-44s %8.3f ms  %8.1f TFLOP/s %8.1f GB/s" % (
+                    o["kernel"], o["name"], o["ms"], o["flops_exec"] / (o["ms"] * 1e-3) / 1e12 if o["ms"] else 0,
+                    o["bytes"] / (o["ms"] * 1e-3) / 1e9 if o["ms"] else 0), file=sys.stderr)
+        extra = None
+        if shard == "samples":
+            # the unsharded run on ONE GPU in the same process (every rank does it, no collective) and the collective
+            # alone: strong-scaling efficiency without a second launch of the benchmark
+            n1 = max(3, min(steps, 5))
+            for _ in range(2):
+                eng.run(x_dev, S)
+            ms1, _, _ = timed(lambda: eng.run(x_dev, S), n1)
+            flat = eng._bufs[(B, sl, False)]["sums"]
+            for _ in range(5):
+                predict.allreduce_sums(flat.clone())
+            buf = flat.clone()
+            ms_c, _, _ = timed(lambda: predict.allreduce_sums(buf), 50)
+            t_n1 = ms1 / n1
+            extra = {"n1_ms_per_step": t_n1, "speedup_vs_n1": t_n1 / (ms / steps),
+                     "efficiency_vs_n1": t_n1 / (ms / steps) / world, "collective_us": ms_c / 50 * 1e3,
+                     "collective": "all_reduce(sum) of %d fp32 statistics" % flat.numel(),
+                     "ideal_efficiency_with_replicated_prefix":
+                         (pre_macs + S * suf_macs) / (world * (pre_macs + (S / world) * suf_macs))}
+            rec.update(extra)
+        eng.release_buffers()
+        del eng, model
+        torch.cuda.empty_cache()
+        return rec
+
+    head_wl = args.workload
+    if world > 1 and head_wl == "c5":
+        head = measure("c5", args.steps, True, "samples", args.batch, args.samples)
     else:
-        flops = sum(o["flops"] for o in prof)
-        t_all = sum(o["ms"] for o in prof) * 1e-3
-        roof = {"bound": "tensor", "kernel": "conv2d_simt (CUDA cores, fp32 parity path)", "achieved": flops / t_all / 1e12,
-                "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": flops / t_all / 1e12 / peaks["sustained"],
-                "peak_source": peaks["src"], "traffic": None}
-    step_flops = 2.0 * B * (pre_macs + (S if not shard_samples else S / world) * suf_macs)
-    kernels = {}
-    for o in prof:
-        k = kernels.setdefault(o["kernel"], {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0})
-        k["ms"] += o["ms"]; k["launches"] += 1; k["bytes"] += o["bytes"]; k["flops"] += o["flops"]
-    for k in kernels.values():
-        k["GBps"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
-        k["TFLOPs"] = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else None
-    if args.profile_ops and rank == 0:
-        for o in prof:
-            print("  %-10s %-28s %8.3f ms  %8.1f TFLOP/s %8.1f GB/s" % (
-                o["kernel"], o["name"], o["ms"], o["flops"] / (o["ms"] * 1e-3) / 1e12 if o["ms"] else 0,
-                o["bytes"] / (o["ms"] * 1e-3) / 1e9 if o["ms"] else 0), file=sys.stderr)
+        head = measure(head_wl, args.steps, True, "batch" if world > 1 else None, args.batch, args.samples)
+
+    extras, c5_strong = {}, None
+    if not args.no_extra_configs and not (args.batch or args.samples) and head_wl == "c2":
+        sub_steps = max(5, min(args.steps, 20))
+        if world == 1:
+            for name in ("c1", "c3", "c4", "c5"):
+                extras[name] = measure(name, sub_steps if name != "c5" else max(3, min(args.steps, 8)), False, None)
+        else:
+            c5_strong = measure("c5", sub_steps, False, "samples")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_reference(kind, classes, S)
-
+        desc, kind, B, S, classes = WORKLOADS[head_wl]
+        cpu = time_cpu_reference(kind, classes, args.samples or S, args.batch or B)
     if rank == 0:
+        sampler.stop()
+        desc, kind, B, S, classes = WORKLOADS[head_wl]
+        shard_samples = head["partition"] == "samples"
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if shard_samples else "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " operands, f32 accumulate",
             "data": "synthetic",
-            "config": {"workload": desc if not (args.batch or args.samples) else desc + " [overridden B=%d S=%d]" % (B, S),
-                       "batch_per_gpu": B, "global_batch": images_per_step, "S": S, "exits": E, "classes": classes,
-                       "partition": "samples" if shard_samples else ("batch" if world > 1 else "none"),
+            "config": {"workload": head["workload"] if not (args.batch or args.samples) else
+                       head["workload"] + " [overridden B=%d S=%d]" % (head["batch_per_gpu"], head["S"]),
+                       "batch_per_gpu": head["batch_per_gpu"], "global_batch": head["global_batch"], "S": head["S"],
+                       "exits": head["exits"], "classes": head["classes"], "partition": head["partition"],
                        "l2": "per-step activation working set (GiB) >> 126 MB L2; no explicit flush",
                        "cuda_graph": os.environ.get("BNN_CUDA_GRAPH", "1") != "0",
-                       "masksembles_mode": eng.gather_mode if kind == "resnet_mask" else None,
-                       "algorithmic_gflop_per_image": 2e-9 * (pre_macs + S * suf_macs)},
-            "tflops_whole_step": step_flops * (world if not shard_samples else world) / (ms / args.steps * 1e-3) / 1e12,
-            "frac_of_tensor_peak_whole_step": step_flops / (ms / args.steps * 1e-3) / 1e12 / peaks["sustained"],
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
-            "gpu_launches": launches,
-            "roofline": roof,
-            "kernels": kernels,
+                       "collective": (None if world == 1 else
+                                      "all_reduce(sum) of the per-exit sums before the finaliser" if shard_samples else
+                                      "all_gather_into_tensor of the finished statistics, on the compute stream"),
+                       "algorithmic_gflop_per_image": head["algorithmic_gflop_per_image"]},
+            "tflops_whole_step": head["tflops_whole_step"],
+            "frac_of_tensor_peak_whole_step": head["frac_of_tensor_peak_whole_step"],
+            "per_rank_ms_per_step": head["per_rank_ms_per_step"],
+            "clocks": head["clocks"],
+            "e2e": head["e2e"],
+            "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"],
+            "kernels": head["kernels"],
             "cpu_baseline": cpu,
         }
+        for k in ("n1_ms_per_step", "speedup_vs_n1", "efficiency_vs_n1", "collective_us"):
+            if k in head:
+                line[k] = head[k]
+        if extras:
+            line["configs"] = extras
+        if c5_strong is not None:
+            line["c5_strong"] = c5_strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

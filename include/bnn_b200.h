@@ -170,6 +170,13 @@ int bnn_conv2d_tc_gathered(const void* x, const void* w, const float* bias, void
 int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int S_local, int x_has_samples,
                 const bnn_drop_desc* drop, void* stream);
 
+/* ---- per-channel affine [+ ReLU] on an NHWC tensor of `pixels` pixels: y = relu?(x * scale[c] + bias[c]) ----
+ * An eval-mode BatchNorm2d (scale = gamma / sqrt(var + eps), bias = beta - mean * scale) that cannot be folded into
+ * the convolution in front of it because a stochastic layer sits in between: the reference's converter wraps every
+ * Conv2d leaf (nn2bnn.py:32-45), which turns conv -> BN -> ReLU into BayesianDropout2D(conv) -> BN -> ReLU. */
+int bnn_channel_affine(const void* x, void* y, const float* scale, const float* bias, int dtype, int64_t pixels, int C,
+                       int relu, void* stream);
+
 /* ---- max-pool k x k, stride k (vgg19.py:128, LeNet t_qmodels_bayes_me.py:54,:104) ---- */
 int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C, int k, void* stream);
 

@@ -100,10 +100,14 @@ def test_residual_network_with_sites_vs_injected_reference(dtype, tol):
     assert torch.allclose(r.mean_probs.sum(-1), torch.ones_like(r.mean_probs.sum(-1)), atol=1e-4)
 
 
-def test_unsupported_network_falls_back_with_warning():
-    net = nn.Sequential(nn.Linear(6, 8), nn.Sigmoid(), nn.Linear(8, 3)).cuda()
-    bnn = nn2bnn.MCDropout(net, nSamples=3, p=0.5).reseed(4).eval()
+def test_unsupported_network_raises_unless_the_eager_loop_is_requested():
+    """No silent library path: a network the lowering cannot express raises; `eager_fallback=True` opts in to the
+    reference's literal loop (stand-alone passes through torch's own layers) with a warning."""
+    mk = lambda: nn.Sequential(nn.Linear(6, 8), nn.Sigmoid(), nn.Linear(8, 3)).cuda()
     x = torch.randn(5, 6, device="cuda")
+    with pytest.raises(NotImplementedError, match="eager_fallback=True"):
+        nn2bnn.MCDropout(mk(), nSamples=3, p=0.5).reseed(4).eval()(x)
+    bnn = nn2bnn.MCDropout(mk(), nSamples=3, p=0.5, eager_fallback=True).reseed(4).eval()
     with pytest.warns(UserWarning, match="stand-alone passes"):
         y = bnn(x)
     assert y.shape == (5, 3) and torch.isfinite(y).all()
@@ -193,7 +197,12 @@ def test_converter_matches_the_reference_converter_fixture(tag):
         assert errs[dtype] <= tol * scale, (tag, dtype, errs)
     # the reference's literal loop: nSamples stand-alone passes through the wrapped modules
     loop = build(fused=False)
-    passes = np.stack([loop.model(x).double().cpu().numpy() for _ in range(n_samples)])
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # the leaves run in torch here
+    try:
+        passes = np.stack([loop.model(x).double().cpu().numpy() for _ in range(n_samples)])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     errs["standalone_passes"] = float(np.abs(passes - want_passes).max())
     assert errs["standalone_passes"] <= 1e-5 * scale
     report(test="converter_vs_reference_fixture", net=tag, scale=scale, **errs)

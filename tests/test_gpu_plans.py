@@ -56,13 +56,3 @@ def test_generic_module_and_converter_replan_when_weights_change(tmp_path):
         g[0].weight.mul_(-1.0)
     r2 = mc_predict(g, x, 4, seed=1, dtype="fp32").mean_logits
     assert (r1 - r2).abs().max().item() > 1e-3
-
-
-def test_unlowerable_network_raises_instead_of_falling_back():
-    net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1), nn.Tanh(), nn.Flatten(), nn.Linear(4 * 8 * 8, 5)).cuda().eval()
-    x = torch.randn(2, 3, 8, 8).cuda()
-    with pytest.raises(NotImplementedError, match="eager_fallback"):
-        nn2bnn.MCDropout(copy.deepcopy(net), nSamples=3).eval()(x)
-    with pytest.warns(UserWarning):
-        y = nn2bnn.MCDropout(copy.deepcopy(net), nSamples=3, eager_fallback=True).eval()(x)
-    assert y.shape == (2, 5)
