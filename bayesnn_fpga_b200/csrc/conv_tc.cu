@@ -84,6 +84,8 @@ struct Params {
   // pooled row [N][Cout] is written - the exit head's input
   int pool_hw;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
+  int exp_flags;   // MEASUREMENT ONLY (BNN_TC_EXP, results are garbage): bit 0 = do not load activation tiles, bit 1 = do
+                   // not load weight tiles - isolates what operand delivery costs a launch
   const float* bias;
   const void* res;
   void* yg[4];
@@ -415,6 +417,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK,
                               wrow + (int)cta_rank * (BN / 2));
             } else {
+              if (p.exp_flags != 0 && !MC2) {
+                // measurement mode: part of the operands is never fetched
+                const uint32_t bytes = ((p.exp_flags & 1) ? 0 : A_STAGE) + ((p.exp_flags & 2) ? 0 : B_TILE);
+                if (bytes == 0) mbar_arrive(&full_bar[stage]); else mbar_expect_tx(&full_bar[stage], bytes);
+                if (!(p.exp_flags & 1)) {
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
+                    if (p.stride == 1)
+                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                    else
+                      tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
+                  }
+                }
+                if (!(p.exp_flags & 2))
+                  tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK, wrow);
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+                continue;
+              }
               mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
@@ -1082,6 +1106,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     p.wsel_sample_px = gsel->batch * OH * OW;
     p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
   }
+  p.exp_flags = getenv("BNN_TC_EXP") ? atoi(getenv("BNN_TC_EXP")) : 0;
   p.cblocks2 = sc ? sc->Cin2 / tc::BK : 0;
   p.pool_hw = pool ? OH * OW : 0;
   p.stride = stride;
