@@ -84,6 +84,7 @@ struct Params {
   // pooled row [N][Cout] is written - the exit head's input
   int pool_hw;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
+  int vh_a, vh_w;  // vertical-halo form: slots of the haloed-activation ring and of the weight ring
   int exp_flags;   // MEASUREMENT ONLY (BNN_TC_EXP, results are garbage): bit 0 = do not load activation tiles, bit 1 = do
                    // not load weight tiles - isolates what operand delivery costs a launch
   const float* bias;
@@ -151,6 +152,22 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       "%7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// One elected lane of a fully converged warp (the MMA-issuer warp runs its loop with all 32 lanes so that the loop
+// state - stage indices, shared-memory descriptors, TMEM addresses - is warp-uniform and lives in uniform registers;
+// with the whole loop under `if (lane == 0)` every tcgen05.mma cost an ELECT + five R2UR.BROADCAST + predicate shuffling,
+// ~140 cycles of dependent issue per 128-cycle MMA: ncu showed the issuing thread busy 80 % of the time).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -312,16 +329,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 // accumulator-full barriers of both CTAs; both epilogues arrive on the leader's accumulator-empty barrier.
 // COMPACT (non-swapped epilogue only; the swapped one decides at run time): a fused Masksembles site may store
 // only the kept channels of each sample's mask (DropParams::compact_pos), 2 bytes at a time.
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
-__global__ void __launch_bounds__(num_threads(EW), 1)
+// VH ("vertical halo", operand-swapped kernel, 3x3 stride-1 convolutions whose 256-pixel tile is ONE whole image of 16
+// rows x 16 columns): the three vertical taps (kh = 0, 1, 2) of a (kw, channel block) read the SAME pixels shifted by
+// one image row = 16 operand rows = 2048 bytes = two 128-byte-swizzle atoms.  The producer therefore loads ONE haloed
+// tile (image rows -1..16, 18 x 16 pixels x 64 channels = 36 KB; rows -1 and 16 are zero-filled by the TMA unit) and
+// the MMA issuer runs the three taps from it by offsetting the B-operand descriptor by kh * 2048 bytes.  Measured reason
+// (profiles/r02_exp_operand_delivery.txt): this kernel is paced by the delivery of ACTIVATION tiles into the SM - 32 KB
+// per 512-cycle k-block; with the activation loads switched off it runs at the MMA floor (1 430 vs 1 140 TFLOP/s), with
+// the weight loads switched off nothing changes - so the activation bytes per k-block drop from 32 KB to 12 KB.
+// Two rings instead of one: VH_A_SLOTS haloed activation tiles and VH_W_SLOTS weight tiles.
+constexpr int VH_A_BYTES = 18 * 16 * BK * 2;      // 36 864
+constexpr int VH_RING_BYTES = 220 * 1024;         // both rings together; the split is a launch parameter (vh_a / vh_w)
+constexpr int VH_MAX_SLOTS = 12;
+__host__ __device__ constexpr int smem_bytes_vh() { return VH_RING_BYTES + 1024 + 256; }
+
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false>
+__global__ void __launch_bounds__(num_threads(EW) + (VH ? 32 : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_a2, const Params p) {
+               const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_ah, const Params p) {
   constexpr bool MC2 = PAIR == 1;
   constexpr bool CG2 = PAIR == 2;
   constexpr bool PAIRED = PAIR != 0;
+  static_assert(!VH || (SWAP && PAIR == 0 && BN == 128 && MT == 2), "VH is a variant of the operand-swapped kernel");
   constexpr int A_STAGE = MT * A_TILE_BYTES;
   constexpr int B_TILE = CG2 ? b_tile_bytes(BN) / 2 : b_tile_bytes(BN);   // bytes of weights in THIS CTA's stage
-  constexpr int STAGES = stages_for_bytes(A_STAGE + B_TILE);
+  constexpr int STAGES = VH ? VH_MAX_SLOTS : stages_for_bytes(A_STAGE + B_TILE);   // VH: number of slot barriers
   constexpr int STAGE_BYTES = A_STAGE + B_TILE;
   constexpr int ACC_COLS = MT * BN;                 // one accumulator set: MT row-tiles of BN columns
   constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered (power of two, <= 512)
@@ -330,8 +362,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const int VH_A_SLOTS = p.vh_a, VH_W_SLOTS = p.vh_w;      // ring depths (vertical-halo form only)
+  uint8_t* smem_b = smem + (VH ? VH_A_SLOTS * VH_A_BYTES : STAGES * A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (VH ? VH_RING_BYTES : STAGES * STAGE_BYTES));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -368,7 +401,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (VH && warp == 0) {
+    // ===================== TMA producer, vertical-halo form =====================
+    // barriers: full/empty[0 .. VH_A_SLOTS) belong to the activation ring, [VH_A_SLOTS .. STAGES) to the weight ring
+    // Two producer threads, one per ring, each issuing in consumption order: warp 0 feeds the haloed activation tiles,
+    // the extra warp behind the epilogue warps (index 2 + EW) feeds the weight tiles.  (One thread feeding both rings
+    // in order lets the shallower ring throttle the other to a look-ahead of a single group - measured: 1 249 vs
+    // 1 167 TFLOP/s for the per-tap kernel, against a 1 480 floor.)
+    if (lane == 0) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+        for (int kw = 0; kw < 3; ++kw)
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&empty_bar[as], aph ^ 1);
+            if (p.exp_flags & 1) {
+              mbar_arrive(&full_bar[as]);                   // measurement mode: activations never fetched
+            } else {
+              mbar_expect_tx(&full_bar[as], VH_A_BYTES);
+              tma_load_4d(smem_a + as * VH_A_BYTES, &tmap_ah, &full_bar[as], cb * BK, kw - 1, -1, tile);
+            }
+            if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
+          }
+        // fused 1x1 stride-2 shortcut: plain 2 x 128-pixel tiles of the block input's parity view
+        for (int cb = 0; cb < p.cblocks2; ++cb) {
+          mbar_wait(&empty_bar[as], aph ^ 1);
+          mbar_expect_tx(&full_bar[as], A_STAGE);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_5d(smem_a + as * VH_A_BYTES + mt * A_TILE_BYTES, &tmap_a2, &full_bar[as], cb * BK, 0, 0,
+                        mt * (BM / p.OW), tile);
+          if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (VH && warp == 2 + EW) {
+    // ===================== TMA producer of the weight ring (vertical-halo form) =====================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      auto load_w = [&](int kcol) {
+        mbar_wait(&empty_bar[VH_A_SLOTS + ws], wph ^ 1);
+        if (p.exp_flags & 2) {
+          mbar_arrive(&full_bar[VH_A_SLOTS + ws]);          // measurement mode: weights never fetched
+        } else {
+          mbar_expect_tx(&full_bar[VH_A_SLOTS + ws], B_TILE);
+          tma_load_2d(smem_b + ws * B_TILE, &tmap_b, &full_bar[VH_A_SLOTS + ws], kcol, 0);
+        }
+        if (++ws == VH_W_SLOTS) { ws = 0; wph ^= 1; }
+      };
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+        for (int kw = 0; kw < 3; ++kw)
+          for (int cb = 0; cb < p.cblocks; ++cb)
+            for (int kh = 0; kh < 3; ++kh) load_w((kh * 3 + kw) * p.Cin + cb * BK);
+        for (int cb = 0; cb < p.cblocks2; ++cb) load_w(p.taps * p.Cin + cb * BK);
+      }
+    }
+  } else if (VH && warp == 1) {
+    // ===================== MMA issuer, vertical-halo form =====================
+    {
+      constexpr uint32_t idesc = make_idesc<T>(MT * BM);
+      const bool leader = elect_one();                      // the same lane issues every MMA and every commit
+      int as = 0, ws = 0, acc = 0;
+      uint32_t aph = 0, wph = 0, acc_phase = 0;
+      for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        uint32_t accum = 0;
+        const int groups = 3 * p.cblocks + p.cblocks2;      // (kw, channel block) groups, then the shortcut k-blocks
+        for (int g = 0; g < groups; ++g) {
+          const int ntap = g < 3 * p.cblocks ? 3 : 1;
+          mbar_wait(&full_bar[as], aph);
+          tc_fence_after();
+          for (int kh = 0; kh < ntap; ++kh) {
+            mbar_wait(&full_bar[VH_A_SLOTS + ws], wph);
+            tc_fence_after();
+            const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + ws * B_TILE));
+            // tap kh reads image rows kh-1 .. kh+14 of the haloed tile: 16 pixels x 128 bytes further per kh
+            const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + as * VH_A_BYTES + kh * (16 * BK * 2)));
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (k | accum) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[VH_A_SLOTS + ws]);
+            }
+            accum = 1;
+            __syncwarp();
+            if (++ws == VH_W_SLOTS) { ws = 0; wph ^= 1; }
+          }
+          if (leader) umma_commit(&empty_bar[as]);
+          __syncwarp();
+          if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
+        }
+        if (leader) umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -492,8 +624,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && !(CG2 && cta_rank != 0)) {         // CG2: only the leader CTA issues MMAs
+    if (!(CG2 && cta_rank != 0)) {                      // CG2: only the leader CTA issues MMAs
       constexpr uint32_t idesc = CG2 ? make_idesc_m<T>(2 * BM, BN) : make_idesc<T>(SWAP ? MT * BM : BN);
+      const bool leader = elect_one();                  // all 32 lanes run the loop (uniform state), one lane issues
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -512,51 +645,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
-          if (CG2) {
+          if (leader) {
+            if (CG2) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  if (k < ksteps)
+                    umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k),
+                                 idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            } else if (SWAP) {
+              // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
+              const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
                 if (k < ksteps)
-                  umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k),
-                               idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-          } else if (SWAP) {
-            // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
-            const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
+                  umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              if (k < ksteps)
-                umma_f16(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          } else {
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                if (k < ksteps)
-                  umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                  if (k < ksteps)
+                    umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+                }
               }
             }
+            if constexpr (CG2)
+              umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
+            else if constexpr (MC2)
+              umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs (the peer writes into it)
+            else
+              umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
           }
-          if constexpr (CG2)
-            umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);   // both CTAs' producers may refill their halves
-          else if constexpr (MC2)
-            umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs (the peer writes into it)
-          else
-            umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if constexpr (CG2)
-          umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)3);   // accumulators complete in both CTAs -> both epilogues
-        else
-          umma_commit(&tmem_full[acc]);                   // accumulators complete -> epilogue
+        if (leader) {
+          if constexpr (CG2)
+            umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)3);   // accumulators complete in both CTAs -> both epilogues
+          else
+            umma_commit(&tmem_full[acc]);                   // accumulators complete -> epilogue
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -905,12 +1044,14 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st) {
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st,
+                  const CUtensorMap* tah = nullptr) {
   static bool configured = false;
-  constexpr int smem = smem_bytes_pair(BN, MT, PAIR);
+  constexpr int smem = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR);
   constexpr bool MC2 = PAIR != 0;
-  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T>;
+  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T, VH>;
+  const CUtensorMap& th = tah ? *tah : ta;
   if (!configured) {
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -921,7 +1062,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     int grid = 2 * p.num_tiles < (sm_count() & ~1) ? 2 * p.num_tiles : (sm_count() & ~1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(num_threads(EW));
+    cfg.blockDim = dim3(num_threads(EW) + (VH ? 32 : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -931,11 +1072,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, p));
+    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, th, p));
   } else {
     p.num_tiles = m_tiles * p.n_tiles_n;
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, num_threads(EW), smem, st>>>(ta, tb, ta2, p);
+    kern<<<grid, num_threads(EW) + (VH ? 32 : 0), smem, st>>>(ta, tb, ta2, th, p);
   }
   BNN_LAUNCH_OK();
   return BNN_OK;
@@ -1156,6 +1297,32 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   if (swap_ok) {
     const bool wide_epi = drop && drop->kind == BNN_DROP_ELEMENT &&
                           !(getenv("BNN_TC_SWAP_EPI") && atoi(getenv("BNN_TC_SWAP_EPI")) == 8);
+    // vertical-halo form: 3x3 stride-1 convolutions on 16 x 16 maps (one image per 256-pixel tile) - layer2 of the
+    // ResNet, block 1 of the VGG.  BNN_TC_NO_VH=1 keeps the one-box-per-tap kernel (A/B measurements, unit tests).
+    const bool vh = ksize == 3 && stride == 1 && OH == 16 && OW == 16 && groups == 1 && gsel == nullptr && !swap_mc2 &&
+                    !compact_out && getenv("BNN_TC_NO_VH") == nullptr;
+    if (vh) {
+      p.vh_a = 3;
+      p.vh_w = 7;
+      if (const char* e = getenv("BNN_TC_VH_SLOTS")) {      // "a,w" (tuning aid)
+        int a = 0, w_ = 0;
+        if (sscanf(e, "%d,%d", &a, &w_) == 2 && a >= 1 && w_ >= 1 && a + w_ <= tc::VH_MAX_SLOTS &&
+            a * tc::VH_A_BYTES + w_ * tc::b_tile_bytes(128) <= tc::VH_RING_BYTES) {
+          p.vh_a = a;
+          p.vh_w = w_;
+        }
+      }
+      CUtensorMap tah;
+      const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N_in};
+      const cuuint64_t strides[3] = {(cuuint64_t)Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)H * W * Cin * eb};
+      const cuuint32_t box[4] = {(cuuint32_t)tc::BK, 16u, 18u, 1u};
+      if (int rc = tc::encode_map(&tah, dtype, 4, x, dims, strides, box)) return rc;
+      if (wide_epi)
+        return dtype == BNN_F16 ? tc::launch<128, 2, true, 0, false, 16, __half, true>(ta, tb, ta2, p, st, &tah)
+                                : tc::launch<128, 2, true, 0, false, 16, __nv_bfloat16, true>(ta, tb, ta2, p, st, &tah);
+      return dtype == BNN_F16 ? tc::launch<128, 2, true, 0, false, 8, __half, true>(ta, tb, ta2, p, st, &tah)
+                              : tc::launch<128, 2, true, 0, false, 8, __nv_bfloat16, true>(ta, tb, ta2, p, st, &tah);
+    }
     if (swap_mc2) {
       if (wide_epi) {
         switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 1, false, 16) }

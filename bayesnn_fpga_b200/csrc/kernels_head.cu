@@ -142,48 +142,59 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uin
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// K permutation: inside every 32-wide K chunk lane t of a quad owns the PHYSICAL features k0 + 8t .. k0 + 8t + 7 and
+// feeds them to two consecutive MMAs (slots 2t, 2t+1, 2t+8, 2t+9 <- physical 8t + {0,1,2,3}, then 8t + {4,5,6,7}).  A
+// and B use the same assignment, so the products are unchanged, but every fragment becomes ONE 16-byte access: the B
+// fragments of a class row are two full 32-byte sectors per quad instead of eight half-used ones (ncu on the C4 heads:
+// the kernel sat at 72 % of the L1TEX pipe with 8 sectors per 4-byte LDG request, 30.5 M sectors per launch), and the A
+// fragments are LDS.128 instead of four LDS.32.  HEAD_APAD keeps the 16-byte A accesses of a quarter-warp (rows g, g+1)
+// on disjoint banks: (F + 32) * 2 bytes = 64 (mod 128).
+constexpr int HEAD_APAD = 32;
+
 template <typename TM, int MT>
 __device__ __forceinline__ void head_gemm_mma(const TM* __restrict__ a_hi, const TM* __restrict__ a_lo,
                                               float* __restrict__ logits, const TM* __restrict__ w_hi,
                                               const TM* __restrict__ w_lo, const float* __restrict__ bias, int F, int C,
                                               int ns, int tid) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int pitch = F + 8;
+  const int pitch = F + HEAD_APAD;
   const int n_tiles = (C + 7) >> 3;
   for (int nt = warp; nt < n_tiles; nt += HEAD_WARPS) {
     const int n = nt * 8 + g;                               // the class whose weights this lane loads (B fragment)
     const bool nv = n < C;
-    const TM* wh = w_hi + (size_t)(nv ? n : 0) * F + 2 * t;
-    const TM* wl = w_lo + (size_t)(nv ? n : 0) * F + 2 * t;
+    const TM* wh = w_hi + (size_t)(nv ? n : 0) * F + 8 * t;
+    const TM* wl = w_lo + (size_t)(nv ? n : 0) * F + 8 * t;
     float acc[MT][4];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
 #pragma unroll 2
-    for (int k0 = 0; k0 < F; k0 += 16) {
-      // one weight fragment (hi + lo) feeds all MT 16-sample row tiles
-      const uint32_t bh0 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wh + k0)) : 0u;
-      const uint32_t bh1 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wh + k0 + 8)) : 0u;
-      const uint32_t bl0 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wl + k0)) : 0u;
-      const uint32_t bl1 = nv ? __ldg(reinterpret_cast<const uint32_t*>(wl + k0 + 8)) : 0u;
+    for (int k0 = 0; k0 < F; k0 += 32) {
+      // one 16-byte weight fragment pair (hi + lo) feeds two MMA k-steps of all MT 16-sample row tiles
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 bh = nv ? __ldg(reinterpret_cast<const uint4*>(wh + k0)) : z4;
+      const uint4 bl = nv ? __ldg(reinterpret_cast<const uint4*>(wl + k0)) : z4;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         if (m * 16 >= ns) break;                            // row tiles past the last sample of this pass
-        const TM* ah0 = a_hi + (size_t)(m * 16 + g) * pitch + 2 * t + k0;
-        const TM* al0 = a_lo + (size_t)(m * 16 + g) * pitch + 2 * t + k0;
-        uint32_t ah[4], al[4];
-        ah[0] = *reinterpret_cast<const uint32_t*>(ah0);
-        ah[1] = *reinterpret_cast<const uint32_t*>(ah0 + 8 * pitch);
-        ah[2] = *reinterpret_cast<const uint32_t*>(ah0 + 8);
-        ah[3] = *reinterpret_cast<const uint32_t*>(ah0 + 8 * pitch + 8);
-        al[0] = *reinterpret_cast<const uint32_t*>(al0);
-        al[1] = *reinterpret_cast<const uint32_t*>(al0 + 8 * pitch);
-        al[2] = *reinterpret_cast<const uint32_t*>(al0 + 8);
-        al[3] = *reinterpret_cast<const uint32_t*>(al0 + 8 * pitch + 8);
-        mma16816<TM>(acc[m], al, bh0, bh1);                 // small terms first
-        mma16816<TM>(acc[m], ah, bl0, bl1);
-        mma16816<TM>(acc[m], ah, bh0, bh1);
+        const size_t r0 = (size_t)(m * 16 + g) * pitch + 8 * t + k0;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(a_hi + r0);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(a_hi + r0 + 8 * pitch);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(a_lo + r0);
+        const uint4 l1 = *reinterpret_cast<const uint4*>(a_lo + r0 + 8 * pitch);
+        {
+          const uint32_t ah[4] = {h0.x, h1.x, h0.y, h1.y}, al[4] = {l0.x, l1.x, l0.y, l1.y};
+          mma16816<TM>(acc[m], al, bh.x, bh.y);             // small terms first
+          mma16816<TM>(acc[m], ah, bl.x, bl.y);
+          mma16816<TM>(acc[m], ah, bh.x, bh.y);
+        }
+        {
+          const uint32_t ah[4] = {h0.z, h1.z, h0.w, h1.w}, al[4] = {l0.z, l1.z, l0.w, l1.w};
+          mma16816<TM>(acc[m], al, bh.z, bh.w);
+          mma16816<TM>(acc[m], ah, bl.z, bl.w);
+          mma16816<TM>(acc[m], ah, bh.z, bh.w);
+        }
       }
     }
     // accumulator fragment: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1)
@@ -223,7 +234,7 @@ __global__ void split16_kernel(const float* __restrict__ w, TM* __restrict__ hi,
 //   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1)] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
 //   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
 // MMA: the head GEMM runs on mma.sync (head_gemm_mma) - shared memory then holds the pooled features as two 16-bit
-// planes a_hi / a_lo [HEAD_SCHUNK][F + 8] instead of pooled[F][HEAD_SCHUNK] + part[]; w_hi / w_lo are [C][F].
+// planes a_hi / a_lo [SCH][F + HEAD_APAD] instead of pooled[F][HEAD_SCHUNK] + part[]; w_hi / w_lo are [C][F].
 // SCH = samples per pass (HEAD_SCHUNK; the MMA form can take 64 = four 16-row tiles per weight fragment, see the
 // launcher for why that is not the default).
 template <typename T, bool MMA, int SCH>
@@ -237,8 +248,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   float* part = pooled + (size_t)SCH * F;
   float* logits = part + HEAD_THREADS * SCH * (C > 32 ? 4 : 1);
   T* a_hi = reinterpret_cast<T*>(sm);
-  T* a_lo = a_hi + (size_t)SCH * (F + 8);
-  if constexpr (MMA) logits = reinterpret_cast<float*>(a_lo + (size_t)SCH * (F + 8));
+  T* a_lo = a_hi + (size_t)SCH * (F + HEAD_APAD);
+  if constexpr (MMA) logits = reinterpret_cast<float*>(a_lo + (size_t)SCH * (F + HEAD_APAD));
   float* acc_p = logits + (size_t)SCH * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
@@ -306,8 +317,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
           }
         }
         if constexpr (MMA) {
-          *reinterpret_cast<Vec8h<T>*>(a_hi + (size_t)sl * (F + 8) + f0) = vh;
-          *reinterpret_cast<Vec8h<T>*>(a_lo + (size_t)sl * (F + 8) + f0) = vl;
+          *reinterpret_cast<Vec8h<T>*>(a_hi + (size_t)sl * (F + HEAD_APAD) + f0) = vh;
+          *reinterpret_cast<Vec8h<T>*>(a_lo + (size_t)sl * (F + HEAD_APAD) + f0) = vl;
         }
       }
     } else {
@@ -459,7 +470,7 @@ int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, 
                       float* sum_logit, float* sum_plogp, float* logits_out, int accumulate, void* stream) {
   BNN_REQUIRE(w_hi && w_lo, "bnn_exit_head_mma: null pointer");
   BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_exit_head_mma: features must be float16 or bfloat16");
-  BNN_REQUIRE(F % 16 == 0, "bnn_exit_head_mma: F=%d must be a multiple of 16", F);
+  BNN_REQUIRE(F % 32 == 0, "bnn_exit_head_mma: F=%d must be a multiple of 32", F);
   return exit_head_run(feat, dtype, feat_has_samples, B, S_local, HW, F, C, nullptr, bias, drop, sum_p, sum_logit,
                        sum_plogp, logits_out, accumulate, stream, w_hi, w_lo);
 }
@@ -481,15 +492,21 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
   if (B == 0) return BNN_OK;
   auto smem_for = [&](int sch) {
     const size_t tail = ((size_t)sch * C + 2 * (size_t)C + HEAD_WARPS + 2 * (size_t)sch) * sizeof(float);
-    return mma ? 2 * (size_t)sch * (F + 8) * 2 + tail
+    return mma ? 2 * (size_t)sch * (F + HEAD_APAD) * 2 + tail
                : ((size_t)sch * F + (size_t)HEAD_THREADS * sch * (C > 32 ? 4 : 1)) * sizeof(float) + tail;
   };
   // MMA form: 16 samples per pass.  64 per pass (four row tiles per weight fragment, 4x fewer weight re-reads from L2)
   // is available as an experiment (BNN_HEAD_SCH=64) but measured SLOWER at C4 (1.46 vs 1.22 ms for the five heads):
   // its 160 KB of shared memory leave one CTA per SM and nothing to hide the feature / weight load latency behind.
+  // 32 samples per pass (two row tiles per weight fragment: half the weight re-reads) when the image has that many and
+  // three CTAs still fit an SM; BNN_HEAD_SCH overrides (16 | 32 | 64).
   const char* sch_env = getenv("BNN_HEAD_SCH");
-  const int sch = (mma && sch_env && atoi(sch_env) == 64 && S_local > HEAD_SCHUNK && smem_for(64) <= 160 * 1024)
-                      ? 64 : HEAD_SCHUNK;
+  int sch = HEAD_SCHUNK;
+  if (mma) {
+    const int want = sch_env ? atoi(sch_env) : (S_local >= 32 ? 32 : 16);
+    if (want == 64 && S_local > HEAD_SCHUNK && smem_for(64) <= 160 * 1024) sch = 64;
+    else if (want >= 32 && S_local > HEAD_SCHUNK && smem_for(32) <= 72 * 1024) sch = 32;
+  }
   const size_t smem = smem_for(sch);
   BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head: F=%d, C=%d need %zu bytes of shared memory", F, C, smem);
   DropParams dp = make_drop_params(drop, F);
@@ -508,6 +525,7 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
   do {                                                                  \
     if (!mma) BNN_HEAD_LAUNCH(T, false, HEAD_SCHUNK);                   \
     else if (sch == 64) BNN_HEAD_LAUNCH(T, true, 64);                   \
+    else if (sch == 32) BNN_HEAD_LAUNCH(T, true, 32);                   \
     else BNN_HEAD_LAUNCH(T, true, HEAD_SCHUNK);                         \
   } while (0)
   switch (dtype) {

@@ -407,7 +407,7 @@ class Engine:
                 op.d_b = op.bias.to(dev, torch.float32)
                 # wide heads on 16-bit features: the Linear runs on mma.sync with hi/lo-split operands
                 C_, F_ = op.weight.shape
-                op.head_mma = (self.dtype_name != "fp32" and C_ > 32 and F_ % 16 == 0 and
+                op.head_mma = (self.dtype_name != "fp32" and C_ > 32 and F_ % 32 == 0 and
                                os.environ.get("BNN_HEAD_MMA", "1") != "0")
                 if op.head_mma:
                     w32 = op.weight.contiguous().to(dev, torch.float32)             # [C][F], the nn.Linear layout

@@ -639,6 +639,7 @@ def test_conv_tc_swapped_cta_pair_multicast(lib, shape, drop_kind, monkeypatch):
     row-tiles and the 16-warp dropout epilogue: bit-identical to the single-CTA swapped kernel."""
     monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
     monkeypatch.setenv("BNN_TC_SWAP_MC2", "1")
+    monkeypatch.setenv("BNN_TC_NO_VH", "1")        # the vertical-halo form accumulates the taps in another order
     N = shape[0]
     dd = drop_desc(drop_kind, 0.5, 0x77, 4, 5, N) if drop_kind else None
     got, want = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
@@ -688,3 +689,28 @@ def test_conv_tc_fused_average_pool(lib, H, N, Cin, C, stride, with_res, pair, m
     # maps that are not 2..32 pixels (power of two) are rejected
     assert lib.bnn_conv2d_tc_pooled(x.data_ptr(), w.data_ptr(), b.data_ptr(), rp, pooled.data_ptr(), 1, 1, 16, 16, Cin, C, 3,
                                     1, 1, stream()) == -1
+
+
+@pytest.mark.parametrize("N,Cin,res,drop_kind", [(5, 128, True, 0), (200, 128, False, 0), (181, 128, True, 1), (150, 64, False, 3),
+                                                 (2, 256, False, 0)])
+def test_conv_tc_vertical_halo_form(lib, N, Cin, res, drop_kind, monkeypatch):
+    """Operand-swapped kernel, vertical-halo form (3x3 stride-1, 16 x 16 maps, Cout = 128): one haloed 18-row tile per
+    (kw, channel block) serves the three vertical taps through descriptor offsets.  vs float64 torch on the rounded
+    operands, incl. more tiles than SMs (ring wrap-around, persistent loop), residual, fused element dropout /
+    Masksembles epilogues - and vs the one-box-per-tap kernel (same values up to fp32 summation order)."""
+    masks = (torch.rand(4, 128, generator=torch.Generator().manual_seed(1)) > 0.5).float().cuda()
+    B = N
+    dd = drop_desc(drop_kind, 0.5, 0x99, 3, 2, B, masks if drop_kind == 3 else None, cnt0=1) if drop_kind else None
+    shape = (N, 16, 16, Cin, 128, 3, 1, 1, True, res)
+    got, want = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    if drop_kind == 1:
+        want = want * torch.from_numpy(philox.keep_mask(0x99, 3, 2, (B, 128, 16, 16), 0.5)).double() * 2.0
+    elif drop_kind == 3:
+        want = want * masks[(1 + 2) % 4].cpu().view(1, 128, 1, 1).double()
+    err = (got.double() - want).abs().max().item()
+    scale = max(1.0, want.abs().max().item())
+    monkeypatch.setenv("BNN_TC_NO_VH", "1")
+    ref, _ = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    d_old = (got.double() - ref.double()).abs().max().item()
+    report(test="conv_tc_vertical_halo", N=N, Cin=Cin, res=res, drop=drop_kind, err=err, vs_per_tap_kernel=d_old, scale=scale)
+    assert err <= 1e-3 * scale and d_old <= 2e-3 * scale and not torch.isnan(got).any()
