@@ -52,8 +52,10 @@ __host__ __device__ constexpr int stages_for(int bn, int mt) {
 __host__ __device__ constexpr int stages_for_bytes(int stage_bytes) {
   return (200 * 1024) / stage_bytes > 8 ? 8 : (200 * 1024) / stage_bytes;
 }
-__host__ __device__ constexpr int smem_bytes_pair(int bn, int mt, int pair) {
-  const int stage = mt * A_TILE_BYTES + (pair == 2 ? b_tile_bytes(bn) / 2 : b_tile_bytes(bn));
+__host__ __device__ constexpr int smem_bytes_pair(int bn, int mt, int pair, bool swap = false) {
+  // operand-swapped cta_group::2 ("sibling pair"): per CTA one 128-pixel tile + its own group's full weight tile
+  const int stage = (swap && pair == 2) ? A_TILE_BYTES + b_tile_bytes(bn)
+                                        : mt * A_TILE_BYTES + (pair == 2 ? b_tile_bytes(bn) / 2 : b_tile_bytes(bn));
   return stages_for_bytes(stage) * stage + 1024 + 256;
 }
 __host__ __device__ constexpr int smem_bytes(int bn, int mt) {
@@ -351,8 +353,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool CG2 = PAIR == 2;
   constexpr bool PAIRED = PAIR != 0;
   static_assert(!VH || (SWAP && PAIR == 0 && BN == 128 && MT == 2), "VH is a variant of the operand-swapped kernel");
-  constexpr int A_STAGE = MT * A_TILE_BYTES;
-  constexpr int B_TILE = CG2 ? b_tile_bytes(BN) / 2 : b_tile_bytes(BN);   // bytes of weights in THIS CTA's stage
+  static_assert(!(SWAP && PAIR == 1), "the multicast pairing of the operand-swapped kernel was retired");
+  // SCG2 (SWAP && CG2, "sibling pair"): the CTA pair works on the SAME 256 output pixels; CTA r owns output group
+  // 2 * pair + r (its 128 weight rows are the pair-MMA's M rows r*128..) and loads only ITS half of the pixel tile (the
+  // MMA's N = 256 columns are split over the pair), so a CTA ingests 16 KB of activations per k-block instead of 32 KB
+  // - the operand whose delivery paces the operand-swapped kernel (profiles/r02_exp_operand_delivery.txt).
+  constexpr bool SCG2 = SWAP && CG2;
+  constexpr int A_STAGE = SCG2 ? A_TILE_BYTES : MT * A_TILE_BYTES;
+  constexpr int B_TILE = (CG2 && !SWAP) ? b_tile_bytes(BN) / 2 : b_tile_bytes(BN);   // weights in THIS CTA's stage
   constexpr int STAGES = VH ? VH_MAX_SLOTS : stages_for_bytes(A_STAGE + B_TILE);   // VH: number of slot barriers
   constexpr int STAGE_BYTES = A_STAGE + B_TILE;
   constexpr int ACC_COLS = MT * BN;                 // one accumulator set: MT row-tiles of BN columns
@@ -507,20 +515,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
-        const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
+        const int m_tile = (PAIRED && !SCG2) ? 2 * m_unit + (int)cta_rank : m_unit;
+        constexpr int NLOAD = SCG2 ? 1 : MT;          // 128-pixel tiles THIS CTA loads per k-block
         int img0[MT], oh0[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          int m0 = (m_tile * MT + mt) * BM;
+        for (int mt = 0; mt < NLOAD; ++mt) {
+          int m0 = SCG2 ? (m_unit * MT + (int)cta_rank) * BM : (m_tile * MT + mt) * BM;
           if (m0 >= p.M) m0 = 0;                      // row-tile past the end: load something valid, never stored
           img0[mt] = m0 / p.OHW;
           oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
           if (p.a_img_mod > 0) img0[mt] %= p.a_img_mod;
         }
-        const bool center = (p.center_mask >> ((n_tile * BN) / p.cout_g)) & 1u;
+        // SCG2: n_tile counts group PAIRS; this CTA's output group (and weight rows) is 2 * n_tile + rank
+        const int grp_w = SCG2 ? 2 * n_tile + (int)cta_rank : n_tile;
+        const bool center = (p.center_mask >> ((grp_w * BN) / p.cout_g)) & 1u;
         const int tap_lo = center ? 4 : 0, tap_hi = center ? 5 : p.taps;
         // weight set of this tile's MC sample (host guarantees that a tile / tile pair never straddles two samples)
-        int wrow = n_tile * BN;
+        int wrow = grp_w * BN;
         if (p.wsel_n > 0) {
           int m0 = m_tile * MT * BM;
           if (m0 >= p.M) m0 = 0;
@@ -538,7 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               // both CTAs' loads complete on the leader's barrier: it expects the bytes of the pair
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
+              for (int mt = 0; mt < NLOAD; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
                   tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
@@ -547,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                   img0[mt]);
               }
               tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK,
-                              wrow + (int)cta_rank * (BN / 2));
+                              SCG2 ? wrow : wrow + (int)cta_rank * (BN / 2));
             } else {
               if (p.exp_flags != 0 && !MC2) {
                 // measurement mode: part of the operands is never fetched
@@ -625,14 +636,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (!(CG2 && cta_rank != 0)) {                      // CG2: only the leader CTA issues MMAs
-      constexpr uint32_t idesc = CG2 ? make_idesc_m<T>(2 * BM, BN) : make_idesc<T>(SWAP ? MT * BM : BN);
+      constexpr uint32_t idesc = SCG2 ? make_idesc_m<T>(2 * BM, MT * BM)
+                                      : (CG2 ? make_idesc_m<T>(2 * BM, BN) : make_idesc<T>(SWAP ? MT * BM : BN));
       const bool leader = elect_one();                  // all 32 lanes run the loop (uniform state), one lane issues
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
-        const int n_tile_mma = tile % p.n_tiles_n;
+        const int n_tile_mma = (tile % p.n_tiles_n) * (SCG2 ? 2 : 1);      // SCG2: first group of the pair
         const int tile_kb = (((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb) + p.cblocks2;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
@@ -646,7 +658,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
           if (leader) {
-            if (CG2) {
+            if (SCG2) {
+              // D^T[256 ch of the group pair, 256 px] += W[256 ch, 64] * P[256 px, 64]^T over the CTA pair: each CTA holds
+              // its 128 weight rows (A) and its 128 pixels (half of B)
+              const uint64_t p_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                if (k < ksteps)
+                  umma_f16_2sm(d_tmem, w_desc + (uint64_t)(2 * k), p_desc + (uint64_t)(2 * k), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            } else if (CG2) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE + mt * A_TILE_BYTES));
@@ -722,8 +743,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int c = q * 32 + lane;                                    // channel inside the group (cout_g == BN)
       const bool has_res = res16 != nullptr;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
-        const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;   // n_tile == output group
-        const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
+        const int m_unit = tile / p.n_tiles_n;
+        // output group: the channel tile itself, or (sibling pair) this CTA's member of the group pair
+        const int n_tile = SCG2 ? 2 * (tile - m_unit * p.n_tiles_n) + (int)cta_rank : tile - m_unit * p.n_tiles_n;
+        const int m_tile = (PAIRED && !SCG2) ? 2 * m_unit + (int)cta_rank : m_unit;
         uint16_t* __restrict__ y16 = reinterpret_cast<uint16_t*>(p.yg[n_tile]);
         const float bias_c = __ldg(p.bias + n_tile * BN + c);
         const bool relu = (p.relu_mask >> n_tile) & 1u;
@@ -826,7 +849,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -1048,7 +1073,7 @@ template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T,
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st,
                   const CUtensorMap* tah = nullptr) {
   static bool configured = false;
-  constexpr int smem = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR);
+  constexpr int smem = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR, SWAP);
   constexpr bool MC2 = PAIR != 0;
   auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T, VH>;
   const CUtensorMap& th = tah ? *tah : ta;
@@ -1058,7 +1083,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   }
   const int m_tiles = (p.M + MT * BM - 1) / (MT * BM);
   if (MC2) {
-    p.num_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;                 // pair-tiles
+    // pair-tiles: two adjacent row-tiles x one channel tile, or (sibling pair) one row-tile x two output groups
+    p.num_tiles = (SWAP && PAIR == 2) ? m_tiles * p.n_tiles_n : ((m_tiles + 1) / 2) * p.n_tiles_n;
     int grid = 2 * p.num_tiles < (sm_count() & ~1) ? 2 * p.num_tiles : (sm_count() & ~1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -1206,11 +1232,6 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
       BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0) &&
       getenv("BNN_TC_NOSWAP") == nullptr;
-  // ... optionally (BNN_TC_SWAP_MC2=1) as CTA pairs with the 128 x 64 weight tile fetched half by each CTA and multicast
-  // into both (L2 -> SM bytes per k-block 48 -> 40 KB).  Bit-identical, measured neutral to 3 % slower per layer at C2
-  // (the cluster hand-shake costs what the saved bytes buy), so it is off by default.
-  const bool swap_mc2 = swap_ok && mc2_any && gsel == nullptr && getenv("BNN_TC_SWAP_MC2") &&
-                        atoi(getenv("BNN_TC_SWAP_MC2")) == 1;
   const bool cg2_narrow_box = mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
@@ -1228,7 +1249,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     const int K = ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box || swap_mc2) ? BN / 2 : BN)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
   }
 
@@ -1299,7 +1320,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                           !(getenv("BNN_TC_SWAP_EPI") && atoi(getenv("BNN_TC_SWAP_EPI")) == 8);
     // vertical-halo form: 3x3 stride-1 convolutions on 16 x 16 maps (one image per 256-pixel tile) - layer2 of the
     // ResNet, block 1 of the VGG.  BNN_TC_NO_VH=1 keeps the one-box-per-tap kernel (A/B measurements, unit tests).
-    const bool vh = ksize == 3 && stride == 1 && OH == 16 && OW == 16 && groups == 1 && gsel == nullptr && !swap_mc2 &&
+    const bool vh = ksize == 3 && stride == 1 && OH == 16 && OW == 16 && groups == 1 && gsel == nullptr &&
                     !compact_out && getenv("BNN_TC_NO_VH") == nullptr;
     if (vh) {
       p.vh_a = 3;
@@ -1323,11 +1344,15 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
       return dtype == BNN_F16 ? tc::launch<128, 2, true, 0, false, 8, __half, true>(ta, tb, ta2, p, st, &tah)
                               : tc::launch<128, 2, true, 0, false, 8, __nv_bfloat16, true>(ta, tb, ta2, p, st, &tah);
     }
-    if (swap_mc2) {
-      if (wide_epi) {
-        switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 1, false, 16) }
-      }
-      switch (BN) { BNN_TC_DISPATCH(128, 2, true, 1) }
+    // sibling pair: an even number of 128-channel output groups reading the same pixels (the stride-2 siblings behind a
+    // stochastic site) run as CTA pairs with tcgen05.mma.cta_group::2 - one group per CTA, the pixel tile split over the
+    // pair.  Both groups of a pair must agree on the centre-tap flag.  BNN_TC_NO_SCG2=1: one CTA per (tile, group).
+    bool scg2 = groups >= 2 && groups % 2 == 0 && gsel == nullptr && getenv("BNN_TC_NO_SCG2") == nullptr;
+    for (int g = 0; scg2 && g + 1 < groups; g += 2)
+      scg2 = ((p.center_mask >> g) & 1u) == ((p.center_mask >> (g + 1)) & 1u);
+    if (scg2) {
+      p.n_tiles_n = groups / 2;
+      switch (BN) { BNN_TC_DISPATCH(128, 2, true, 2) }
     }
     if (wide_epi) {
       switch (BN) { BNN_TC_DISPATCH_E(128, 2, true, 0, false, 16) }

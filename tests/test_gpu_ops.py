@@ -631,23 +631,47 @@ def test_conv_tc_fused_shortcut(lib, Cin2, C, H, N, pair, drop_kind, monkeypatch
                                       1, 1, ctypes.byref(dd), d_x2.data_ptr(), H, H, Cin2, stream()) == -1
 
 
-@pytest.mark.parametrize("shape", [(4, 16, 16, 128, 128, 3, 1, 1, True, True), (9, 16, 16, 128, 128, 3, 1, 1, True, False),
-                                   (4, 32, 32, 64, 128, 3, 2, 1, True, False)])
-@pytest.mark.parametrize("drop_kind", [0, 1])
-def test_conv_tc_swapped_cta_pair_multicast(lib, shape, drop_kind, monkeypatch):
-    """operand-swapped kernel as CTA pairs (weight halves TMA-multicast into both CTAs), incl. an odd number of
-    row-tiles and the 16-warp dropout epilogue: bit-identical to the single-CTA swapped kernel."""
-    monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
-    monkeypatch.setenv("BNN_TC_SWAP_MC2", "1")
-    monkeypatch.setenv("BNN_TC_NO_VH", "1")        # the vertical-halo form accumulates the taps in another order
-    N = shape[0]
-    dd = drop_desc(drop_kind, 0.5, 0x77, 4, 5, N) if drop_kind else None
-    got, want = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
-    if drop_kind == 0:
-        assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
-    monkeypatch.setenv("BNN_TC_SWAP_MC2", "0")
-    ref, _ = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
-    assert torch.equal(got, ref) and not torch.isnan(got).any()
+@pytest.mark.parametrize("N,Cin,HW,G,center", [(5, 64, 32, 2, 0), (171, 64, 32, 2, 0), (7, 128, 16, 4, 0b1100), (3, 64, 16, 2, 0b10)])
+def test_conv_tc_sibling_pair_cta_group2(lib, N, Cin, HW, G, center, monkeypatch):
+    """Operand-swapped kernel as CTA pairs (tcgen05.mma.cta_group::2): two 128-channel sibling groups that read the same
+    pixels run on one pair - one group per CTA, the 256-pixel tile split over the pair.  vs float64 torch per group,
+    and bit-identical to the one-CTA-per-(tile, group) kernel (same accumulation order); more tiles than SM pairs;
+    a pair of centre-tap (1x1) groups; a pair that DISAGREES on the centre-tap flag falls back to single CTAs."""
+    g = torch.Generator().manual_seed(N * G)
+    x = torch.randn(N, Cin, HW, HW, generator=g).half()
+    ws = []
+    for i in range(G):
+        w = torch.randn(128, Cin, 3, 3, generator=g) / np.sqrt(9 * Cin)
+        if (center >> i) & 1:                                    # a 1x1 kernel held in the centre tap
+            c = w[:, :, 1, 1].clone()
+            w.zero_()
+            w[:, :, 1, 1] = c
+        ws.append(w.half())
+    bias = torch.randn(G * 128, generator=g)
+    relu_mask = 0b0101 & ((1 << G) - 1)
+    d_x = x.permute(0, 2, 3, 1).contiguous().cuda()
+    d_w = torch.cat(ws).permute(0, 2, 3, 1).contiguous().cuda()
+    d_b = bias.cuda()
+
+    def run():
+        outs = [torch.full((N, HW // 2, HW // 2, 128), float("nan"), dtype=torch.float16, device="cuda") for _ in range(G)]
+        ys = (ctypes.c_void_p * G)(*[o.data_ptr() for o in outs])
+        rc = lib.bnn_conv2d_tc_grouped(d_x.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), ys, G, relu_mask, center, 1, N, HW, HW,
+                                       Cin, 128, 3, 2, stream())
+        assert rc == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        return [o.cpu() for o in outs]
+    got = run()
+    monkeypatch.setenv("BNN_TC_NO_SCG2", "1")
+    ref = run()
+    xd = x.double()
+    for i in range(G):
+        want = F.conv2d(xd, ws[i].double(), bias[i * 128:(i + 1) * 128].double(), 2, 1)
+        if (relu_mask >> i) & 1:
+            want = want.relu()
+        err = (got[i].permute(0, 3, 1, 2).double() - want).abs().max().item()
+        assert err <= 1e-3 * max(1.0, want.abs().max().item()), (i, err)
+        assert torch.equal(got[i], ref[i]) and not torch.isnan(got[i]).any()
 
 
 def test_conv_tc_tap_skip_on_1x1_maps_is_bit_exact(lib, monkeypatch):
