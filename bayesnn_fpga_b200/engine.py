@@ -361,6 +361,7 @@ class Engine:
         self.launches = 0
         self._prof = None
         self._graphs = {}
+        self._graph_collectives = os.environ.get("BNN_GRAPH_COLLECTIVES", "1") != "0"
         self._bufs = {}
         self._prepare_weights()
         # Masksembles2D as smaller / re-weighted GEMMs.  0: dense 0/1 multiplies everywhere (the reference's form);
@@ -821,51 +822,89 @@ class Engine:
                 seen.add(id(s.module))
                 s.module.cnt = (int(s.module.cnt) + S) % int(s.module.n)
 
-    def _enqueue_graphed(self, x, S, sample0, seed, want_logits, mask_offset):
-        """CUDA-graph replay of the launch sequence.  Kernel arguments (seed, sample range, Masksembles counters,
-        buffer pointers) are baked into the graph, so graphs are cached per argument tuple: the first call with a
-        tuple runs eagerly, the second captures, later ones replay (a benchmark or a sample-sharded serving loop
-        repeats its tuple; an analysis loop that reseeds every batch simply stays eager)."""
+    def _step(self, x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn):
+        """Everything one batch enqueues on the current stream: the launch sequence, the sample-sharding all-reduce of
+        the sums (if any), the finaliser, the batch-sharding all-gather of the statistics (if any)."""
+        st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
+        if reduce_fn is not None:
+            reduce_fn(st["sums"])
+        views, ent = self.finalize(st, x.shape[0], S_total)
+        if gather_fn is not None:
+            gather_fn(st["out"])
+        return st, views, ent
+
+    def _step_graphed(self, x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn):
+        """CUDA-graph replay of :meth:`_step`.  Kernel arguments (seed, sample range, Masksembles counters, buffer
+        pointers) are baked into the graph, so graphs are cached per argument tuple: the first call with a tuple runs
+        eagerly (this also initialises the NCCL communicator), the second captures, later ones replay (a benchmark or a
+        sample-sharded serving loop repeats its tuple; an analysis loop that reseeds every batch simply stays eager).
+        The NCCL collective is captured INSIDE the graph, right behind the kernels that produce its payload, so a step is
+        one graph launch; if this torch / NCCL build refuses to capture it, the collectives are issued eagerly behind the
+        replayed compute graph instead (decided once per engine)."""
         cnts = tuple(int(s.module.cnt) for s in self.graph.sites if s.kind == "mask")
-        key = (x.shape[0], S, sample0, seed, want_logits, mask_offset, cnts)
+        inside = self._graph_collectives and (reduce_fn is not None or gather_fn is not None)
+        key = (x.shape[0], S, sample0, seed, want_logits, mask_offset, cnts, S_total, reduce_fn is not None,
+               gather_fn is not None, inside)
         st = self._buffers(x.shape[0], S, want_logits)
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs[key] = "seen"
             if len(self._graphs) > 64:
                 self._graphs.pop(next(iter(self._graphs)))
-            return self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
+            return self._step(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn)
         st["x"].copy_(x, non_blocking=True)
+        rf, gf = (reduce_fn, gather_fn) if inside else (None, None)
         if entry == "seen":
             n0 = self.launches
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.enqueue(st["x"], S, sample0, seed, False, want_logits, mask_offset)
-            entry = self._graphs[key] = (g, self.launches - n0)
+            try:
+                with torch.cuda.graph(g):
+                    if rf is None and gf is None and (reduce_fn is not None):
+                        # collectives stay outside: the graph ends in front of the reduction
+                        out = (self.enqueue(st["x"], S, sample0, seed, False, want_logits, mask_offset), None, None)
+                    else:
+                        out = self._step(st["x"], S, sample0, seed, want_logits, mask_offset, S_total, rf, gf)
+            except Exception as e:                      # noqa: BLE001 - capture of the NCCL call refused
+                if not inside:
+                    raise
+                import warnings
+                warnings.warn("CUDA-graph capture of the NCCL collective failed (%s): collectives run eagerly" % (e,))
+                torch.cuda.synchronize(self.device)
+                self._graph_collectives = False
+                self._graphs.pop(key, None)
+                self.launches = n0
+                return self._step_graphed(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn)
+            entry = self._graphs[key] = (g, self.launches - n0, out)
             self.launches = n0
-        g, n = entry
+        g, n, out = entry
         g.replay()
         self.launches += n
-        return st
+        st, views, ent = out
+        if not inside:
+            if reduce_fn is not None:                   # graph = launch sequence only; reduce, then finalise eagerly
+                reduce_fn(st["sums"])
+                views, ent = self.finalize(st, x.shape[0], S_total)
+            if gather_fn is not None:
+                gather_fn(st["out"])
+        return st, views, ent
 
     def run(self, x, S, seed=0x5EED, sample0=0, S_total=None, want_logits=False, reduce_fn=None,
-            mask_offset=None, use_graph=None):
+            mask_offset=None, use_graph=None, gather_fn=None):
         """S local samples starting at global sample index `sample0`; `reduce_fn(sums)` (optional)
-        all-reduces the flat sums tensor across ranks before the finaliser.  Masksembles rows are
-        (module.cnt + mask_offset + s) % n with mask_offset defaulting to sample0."""
+        all-reduces the flat sums tensor across ranks before the finaliser, `gather_fn(out)` (optional) gathers the
+        finished statistics (batch sharding).  Masksembles rows are (module.cnt + mask_offset + s) % n with
+        mask_offset defaulting to sample0."""
         x = x.to(self.device, torch.float32)
         B = x.shape[0]
         if use_graph is None:
             use_graph = os.environ.get("BNN_CUDA_GRAPH", "1") != "0"
+        S_total = S if S_total is None else S_total
         with torch.cuda.device(self.device):
             if use_graph and B > 0 and S > 0 and self._prof is None:
-                st = self._enqueue_graphed(x, S, sample0, seed, want_logits, mask_offset)
+                st, views, ent = self._step_graphed(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn,
+                                                    gather_fn)
             else:
-                st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
-            if reduce_fn is not None:
-                reduce_fn(st["sums"])
-            S_total = S if S_total is None else S_total
-            views, ent = self.finalize(st, B, S_total)
+                st, views, ent = self._step(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn)
         self.advance_masksembles(S_total)
         all_logits = None
         if want_logits:

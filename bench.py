@@ -353,6 +353,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     peaks = load_peaks()
@@ -402,14 +403,15 @@ def main():
         gathered = torch.empty(world * n_stats, device=dev) if shard == "batch" else None
         s0, sl = predict.shard_samples(S, world, rank) if shard == "samples" else (0, S)
 
+        def gather(out):
+            dist.all_gather_into_tensor(gathered, out)
+
         def step_device():
             """inputs already resident in HBM"""
             if shard == "samples":
                 return eng.run(x_dev, sl, sample0=s0, S_total=S, reduce_fn=predict.allreduce_sums)
-            r = eng.run(x_dev, S)
-            if shard == "batch":   # ONE NCCL collective on the compute stream right behind the finaliser
-                dist.all_gather_into_tensor(gathered, eng._bufs[(B, S, False)]["out"])
-            return r
+            # batch sharding: ONE NCCL collective right behind the finaliser, captured inside the step's CUDA graph
+            return eng.run(x_dev, S, gather_fn=gather if shard == "batch" else None)
 
         out_host = torch.empty((4, E, B, classes), dtype=torch.float32).pin_memory()
 
@@ -438,7 +440,8 @@ def main():
                "partition": shard or "none", "per_rank_ms_per_step": [v / steps for v in per_rank],
                "e2e": {"value": images * steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / steps,
                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
-               "gpu_launches": launches, "clocks": clocks}
+               "gpu_launches": launches, "clocks": clocks,
+               "collective_in_graph": bool(eng._graph_collectives) if shard else None}
         prof = eng.profile_step(x_dev, sl)
         roof, kernels = summarize_profile(prof, peaks, clocks, ms * 1e-3, with_traffic=(wl_name == "c2"))
         pre_macs, suf_macs = eng.graph.macs()
@@ -517,6 +520,7 @@ def main():
                        "exits": head["exits"], "classes": head["classes"], "partition": head["partition"],
                        "l2": "per-step activation working set (GiB) >> 126 MB L2; no explicit flush",
                        "cuda_graph": os.environ.get("BNN_CUDA_GRAPH", "1") != "0",
+                       "collective_inside_cuda_graph": head.get("collective_in_graph"),
                        "collective": (None if world == 1 else
                                       "all_reduce(sum) of the per-exit sums before the finaliser" if shard_samples else
                                       "all_gather_into_tensor of the finished statistics, on the compute stream"),
