@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(CSRC, "libbnn_b200.so")
 SOURCES = ["kernels_simt.cu", "kernels_head.cu", "kernels_stats.cu", "conv_tc.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "../../include/bnn_b200.h"]
 
-F32, F16, BF16 = 0, 1, 2
+F32, F16, BF16, I8 = 0, 1, 2, 3
 DROP_NONE, DROP_ELEMENT, DROP_CHANNEL, DROP_MASKSEMBLES = 0, 1, 2, 3
 CAL_TOP, CAL_TOP_NORM, CAL_TFP_RESOFTMAX = 0, 1, 2
 
@@ -97,6 +97,8 @@ _SIGS = {
                         [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_conv2d_tc": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
                       [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_conv2d_tc_i8": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 7 + [ctypes.c_float, ctypes.POINTER(DropDesc),
+                                                                       ctypes.c_void_p]),
     "bnn_conv2d_tc_shortcut": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
                                [ctypes.POINTER(DropDesc), ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p]),
@@ -115,6 +117,11 @@ _SIGS = {
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_channel_affine": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]),
+    "bnn_dropout_q8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_exit_head_q8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p,
+                                                                                                 ctypes.POINTER(DropDesc)] +
+                         [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]),
     "bnn_maxpool2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "bnn_exit_head": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p,
                                                                               ctypes.POINTER(DropDesc)] +

@@ -50,8 +50,15 @@ __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+template <>
+__device__ __forceinline__ float to_f32<uint8_t>(uint8_t v) { return (float)v; }   // 8-bit activations: the integer itself
+
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ uint8_t from_f32<uint8_t>(float v) {   // round half to even, saturate to [0, 255]
+  return (uint8_t)min(max(__float2int_rn(v), 0), 255);
+}
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
@@ -79,6 +86,8 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+template <>
+__device__ __forceinline__ uint32_t pack2<int8_t>(float, float) { return 0u; }   // 8-bit kernels never take this path
 template <typename T>
 __device__ __forceinline__ float2 unpack2(uint32_t v);
 template <>
@@ -89,5 +98,7 @@ template <>
 __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
+template <>
+__device__ __forceinline__ float2 unpack2<int8_t>(uint32_t) { return make_float2(0.f, 0.f); }
 
 }  // namespace bnn

@@ -86,6 +86,8 @@ struct Params {
   // pooled row [N][Cout] is written - the exit head's input
   int pool_hw;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
+  float q_mult;    // 8-bit operands: output LSBs per accumulator LSB = w_scale * in_scale / out_scale (a power of two
+                   // for the QKeras fixed-point formats, any float otherwise)
   int vh_a, vh_w;  // vertical-halo form: slots of the haloed-activation ring and of the weight ring
   int exp_flags;   // MEASUREMENT ONLY (BNN_TC_EXP, results are garbage): bit 0 = do not load activation tiles, bit 1 = do
                    // not load weight tiles - isolates what operand delivery costs a launch
@@ -186,17 +188,29 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 / bf16 operands, fp32 accumulate)
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 / bf16 operands, fp32 accumulate) or - I8 - kind::i8
+// (u8 x s8 operands, int32 accumulate)
+template <bool I8 = false>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (I8)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -239,16 +253,27 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
+template <bool I8 = false>
 __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (I8)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -301,11 +326,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor for kind::f16: fp32 accumulator, A/B type, both K-major, M = 128, N = BN
 template <typename T>
 __host__ __device__ constexpr uint32_t make_idesc_m(int m, int bn) {
+  if (sizeof(T) == 1)   // kind::i8: D = S32 (2), A = activations, unsigned 8-bit (0), B = weights, signed 8-bit (1)
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
   const uint32_t ab = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
   return (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 template <typename T>
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  if (sizeof(T) == 1) return make_idesc_m<T>(BM, bn);
   const uint32_t ab = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = f16, 1 = bf16
   return (1u << 4)                 // D format f32
          | (ab << 7) | (ab << 10)  // A, B format
@@ -352,6 +380,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool MC2 = PAIR == 1;
   constexpr bool CG2 = PAIR == 2;
   constexpr bool PAIRED = PAIR != 0;
+  // 8-bit operands (T = int8_t: unsigned 8-bit activations x signed 8-bit weights -> int32 accumulators, kind::i8): a
+  // k-block is still one 128-byte swizzle row per pixel / weight row, i.e. 128 elements, and one MMA still consumes 32
+  // bytes of K (32 elements), so only element COORDINATES, the instruction and the epilogue differ.
+  constexpr bool I8 = sizeof(T) == 1;
+  constexpr int BKE = I8 ? 2 * BK : BK;               // elements per k-block
+  static_assert(!I8 || (!SWAP && !COMPACT && !VH && PAIR != 1), "8-bit operands: plain and cta_group::2 kernels only");
   static_assert(!VH || (SWAP && PAIR == 0 && BN == 128 && MT == 2), "VH is a variant of the operand-swapped kernel");
   static_assert(!(SWAP && PAIR == 1), "the multicast pairing of the operand-swapped kernel was retired");
   // SCG2 (SWAP && CG2, "sibling pair"): the CTA pair works on the SAME 256 output pixels; CTA r owns output group
@@ -427,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               mbar_arrive(&full_bar[as]);                   // measurement mode: activations never fetched
             } else {
               mbar_expect_tx(&full_bar[as], VH_A_BYTES);
-              tma_load_4d(smem_a + as * VH_A_BYTES, &tmap_ah, &full_bar[as], cb * BK, kw - 1, -1, tile);
+              tma_load_4d(smem_a + as * VH_A_BYTES, &tmap_ah, &full_bar[as], cb * BKE, kw - 1, -1, tile);
             }
             if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
           }
@@ -437,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_expect_tx(&full_bar[as], A_STAGE);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            tma_load_5d(smem_a + as * VH_A_BYTES + mt * A_TILE_BYTES, &tmap_a2, &full_bar[as], cb * BK, 0, 0,
+            tma_load_5d(smem_a + as * VH_A_BYTES + mt * A_TILE_BYTES, &tmap_a2, &full_bar[as], cb * BKE, 0, 0,
                         mt * (BM / p.OW), tile);
           if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
         }
@@ -461,8 +495,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         for (int kw = 0; kw < 3; ++kw)
           for (int cb = 0; cb < p.cblocks; ++cb)
-            for (int kh = 0; kh < 3; ++kh) load_w((kh * 3 + kw) * p.Cin + cb * BK);
-        for (int cb = 0; cb < p.cblocks2; ++cb) load_w(p.taps * p.Cin + cb * BK);
+            for (int kh = 0; kh < 3; ++kh) load_w((kh * 3 + kw) * p.Cin + cb * BKE);
+        for (int cb = 0; cb < p.cblocks2; ++cb) load_w(p.taps * p.Cin + cb * BKE);
       }
     }
   } else if (VH && warp == 1) {
@@ -552,12 +586,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < NLOAD; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                 else
-                  tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh,
+                  tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh,
                                   img0[mt]);
               }
-              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK,
+              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE,
                               SCG2 ? wrow : wrow + (int)cta_rank * (BN / 2));
             } else {
               if (p.exp_flags != 0 && !MC2) {
@@ -569,13 +603,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   for (int mt = 0; mt < MT; ++mt) {
                     uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                     if (p.stride == 1)
-                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                     else
-                      tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
+                      tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
                   }
                 }
                 if (!(p.exp_flags & 2))
-                  tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK, wrow);
+                  tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE, wrow);
                 if (++stage == STAGES) {
                   stage = 0;
                   phase ^= 1;
@@ -587,15 +621,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < MT; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BK, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                 else
-                  tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BK, dw, hp, oh0[mt] + dh, img0[mt]);
+                  tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
               }
               if constexpr (MC2)
                 tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
-                               tap * p.Cin + cb * BK, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
+                               tap * p.Cin + cb * BKE, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
               else
-                tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BK, wrow);
+                tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE, wrow);
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -610,21 +644,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-              tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BK, 0, 0,
+              tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0,
                               oh0[mt], img0[mt]);
-            tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BK,
+            tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BKE,
                             wrow + (int)cta_rank * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-              tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BK, 0, 0, oh0[mt],
+              tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0, oh0[mt],
                           img0[mt]);
             if constexpr (MC2)
               tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
-                             p.taps * p.Cin + cb * BK, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
+                             p.taps * p.Cin + cb * BKE, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
             else
-              tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BK, wrow);
+              tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BKE, wrow);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -674,8 +708,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)
                   if (k < ksteps)
-                    umma_f16_2sm(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k),
-                                 idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16_2sm<I8>(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k),
+                                     idesc, (kb | k) != 0 ? 1u : 0u);
               }
             } else if (SWAP) {
               // D^T[128 ch, 256 px] += W[128 ch, 64] * P[256 px, 64]^T : the MT pixel tiles are contiguous in smem
@@ -692,8 +726,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                   // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
                   if (k < ksteps)
-                    umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
+                    umma_f16<I8>(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(2 * k), w_desc + (uint64_t)(2 * k), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
                 }
               }
             }
@@ -916,10 +950,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float f[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              f[4 * j] = __uint_as_float(v[4 * j]) + bia[j].x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+              if constexpr (I8) {
+                // exact int32 accumulator -> float (round to nearest even), x per-layer multiplier, + bias in output
+                // LSBs: two separately rounded operations (no FMA contraction) so that the NumPy restatement
+                // (oracle/q8.py) reproduces every bit
+                f[4 * j] = __fadd_rn(__fmul_rn((float)(int)v[4 * j], p.q_mult), bia[j].x);
+                f[4 * j + 1] = __fadd_rn(__fmul_rn((float)(int)v[4 * j + 1], p.q_mult), bia[j].y);
+                f[4 * j + 2] = __fadd_rn(__fmul_rn((float)(int)v[4 * j + 2], p.q_mult), bia[j].z);
+                f[4 * j + 3] = __fadd_rn(__fmul_rn((float)(int)v[4 * j + 3], p.q_mult), bia[j].w);
+              } else {
+                f[4 * j] = __uint_as_float(v[4 * j]) + bia[j].x;
+                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bia[j].y;
+                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bia[j].z;
+                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bia[j].w;
+              }
             }
             if (res != nullptr) {
 #pragma unroll
@@ -999,14 +1043,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
               continue;
             }
+            if constexpr (I8) {
+              // requantise: round half to even, clip to the unsigned 8-bit grid of quantized_relu; 32 bytes per pixel
+              uint32_t w8[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = pack2<T>(f[j], f[j + 1]);
-              o.y = pack2<T>(f[j + 2], f[j + 3]);
-              o.z = pack2<T>(f[j + 4], f[j + 5]);
-              o.w = pack2<T>(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(y + off + j) = o;
+              for (int j = 0; j < 8; ++j) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  word |= (uint32_t)min(max(__float2int_rn(f[4 * j + t]), 0), 255) << (8 * t);
+                w8[j] = word;
+              }
+              uint8_t* y8 = reinterpret_cast<uint8_t*>(y) + off;
+              *reinterpret_cast<uint4*>(y8) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+              *reinterpret_cast<uint4*>(y8 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack2<T>(f[j], f[j + 1]);
+                o.y = pack2<T>(f[j + 2], f[j + 3]);
+                o.z = pack2<T>(f[j + 4], f[j + 5]);
+                o.w = pack2<T>(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(y + off + j) = o;
+              }
             }
           }
         }
@@ -1058,7 +1118,9 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
     return BNN_E_CUDA;
   }
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  const CUtensorMapDataType dt = dtype == BNN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = dtype == BNN_I8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : dtype == BNN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1129,12 +1191,17 @@ struct Shortcut {
 static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                        int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
-                       const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr, bool pool = false) {
+                       const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr, bool pool = false,
+                       float q_mult = 1.f) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
   for (int g = 0; g < groups; ++g) BNN_REQUIRE(y[g] != nullptr, "%s: null output %d", who, g);
-  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "%s: dtype must be float16 or bfloat16", who);
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16 || dtype == BNN_I8, "%s: dtype must be float16, bfloat16 or int8", who);
+  const bool i8 = dtype == BNN_I8;
+  const int bke = i8 ? 2 * tc::BK : tc::BK;                  // elements of one 128-byte k-block
+  BNN_REQUIRE(!i8 || (groups == 1 && gsel == nullptr && sc == nullptr && !pool && res == nullptr && (relu_mask & 1u)),
+              "%s: the 8-bit kernel takes one dense output with ReLU, no residual / shortcut / pool fusion", who);
   BNN_REQUIRE(N >= 0 && H > 0 && W > 0, "%s: bad geometry", who);
   BNN_REQUIRE(groups == 1 || (res == nullptr && (drop == nullptr || drop->kind == BNN_DROP_NONE)),
               "%s: residual / stochastic epilogues need a single output group", who);
@@ -1142,7 +1209,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const int pad = ksize == 3 ? 1 : 0;
   const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
   const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) &&
-                  (gsel ? (Cin % 16 == 0 && Cin > 0) : Cin % 64 == 0) && cout_g % 64 == 0 &&
+                  (gsel ? (Cin % 16 == 0 && Cin > 0) : Cin % bke == 0) && cout_g % 64 == 0 &&
                   (stride == 1 || (H % 2 == 0 && W % 2 == 0)) && tc::pow2(OW) && tc::pow2(OH) && OW <= 128;
   if (!ok) {
     set_error("%s: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", who, ksize, stride, Cin,
@@ -1189,18 +1256,18 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const int tn = tc::BM / (tw * th);
 
   CUtensorMap ta, tb, ta2;
-  const cuuint64_t eb = 2;
+  const cuuint64_t eb = i8 ? 1 : 2;
   const int N_in = (gsel && !gsel->x_has_samples) ? gsel->batch : N;     // images held by x
   if (stride == 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N_in};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)H * W * Cin * eb};
-    const cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    const cuuint32_t box[4] = {(cuuint32_t)bke, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
     if (int rc = tc::encode_map(&ta, dtype, 4, x, dims, strides, box)) return rc;
   } else {
     const cuuint64_t dims[5] = {(cuuint64_t)2 * Cin, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N_in};
     const cuuint64_t strides[4] = {(cuuint64_t)2 * Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)2 * W * Cin * eb,
                                    (cuuint64_t)H * W * Cin * eb};
-    const cuuint32_t box[5] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
+    const cuuint32_t box[5] = {(cuuint32_t)bke, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
     if (int rc = tc::encode_map(&ta, dtype, 5, x, dims, strides, box)) return rc;
   }
   // a channel tile never straddles two output groups: BN divides cout_g ...
@@ -1229,10 +1296,10 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
-      BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
+      !i8 && BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0) &&
       getenv("BNN_TC_NOSWAP") == nullptr;
-  const bool cg2_narrow_box = mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
+  const bool cg2_narrow_box = !i8 && mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
   if (sc) {
@@ -1249,7 +1316,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     const int K = ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
+    const cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
     if (int rc = tc::encode_map(&tb, dtype, 2, w, dims, strides, box)) return rc;
   }
 
@@ -1259,9 +1326,10 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   p.n_tiles_n = (Cout + BN - 1) / BN;
   p.num_tiles = ((p.M + tc::BM - 1) / tc::BM) * p.n_tiles_n;
   p.taps = ksize * ksize;
-  p.cblocks = (Cin + tc::BK - 1) / tc::BK;
+  p.cblocks = (Cin + bke - 1) / bke;
   p.Cin = Cin;
-  p.last_ksteps = (Cin - (p.cblocks - 1) * tc::BK) / tc::UMMA_K;
+  p.last_ksteps = (Cin - (p.cblocks - 1) * bke) / (i8 ? 2 * tc::UMMA_K : tc::UMMA_K);
+  p.q_mult = q_mult;
   if (gsel) {
     p.wsel_n = gsel->n_masks;
     p.wsel_cnt0 = ((gsel->cnt0 % gsel->n_masks) + gsel->n_masks) % gsel->n_masks;
@@ -1297,6 +1365,15 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                             : tc::launch<BN_, MT_, SWAP_, PAIR_, COMPACT_, EW_, __nv_bfloat16>(ta, tb, ta2, p, st);
 #define BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, COMPACT_) BNN_TC_DISPATCH_E(BN_, MT_, SWAP_, PAIR_, COMPACT_, 8)
 #define BNN_TC_DISPATCH(BN_, MT_, SWAP_, PAIR_) BNN_TC_DISPATCH_C(BN_, MT_, SWAP_, PAIR_, false)
+  if (i8) {
+    // unsigned 8-bit activations x signed 8-bit weights -> int32 (tcgen05.mma kind::i8), requantising epilogue
+    if (cg2 && mc2) return tc::launch<256, 1, false, 2, false, 8, int8_t>(ta, tb, ta2, p, st);
+    switch (BN) {
+      case 256: return tc::launch<256, 1, false, 0, false, 8, int8_t>(ta, tb, ta2, p, st);
+      case 128: return tc::launch<128, 2, false, 0, false, 8, int8_t>(ta, tb, ta2, p, st);
+      default: return tc::launch<64, 2, false, 0, false, 8, int8_t>(ta, tb, ta2, p, st);
+    }
+  }
   const bool cg2_narrow = cg2_narrow_box;   // experiment
   if (compact_out && BN == 256) {
     // compact Masksembles stores: dedicated instantiations so that the other kernels keep their code size
@@ -1416,4 +1493,11 @@ extern "C" int bnn_conv2d_tc_pooled(const void* x, const void* w, const float* b
   void* ys[1] = {y_pooled};
   return conv_tc_run("bnn_conv2d_tc_pooled", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
                      stride, nullptr, stream, nullptr, nullptr, true);
+}
+
+extern "C" int bnn_conv2d_tc_i8(const void* x, const void* w, const float* bias_q, void* y, int N, int H, int W, int Cin,
+                                int Cout, int ksize, int stride, float q_mult, const bnn_drop_desc* drop, void* stream) {
+  void* ys[1] = {y};
+  return conv_tc_run("bnn_conv2d_tc_i8", x, w, bias_q, nullptr, ys, 1, 1u, 0u, BNN_I8, N, H, W, Cin, Cout, ksize, stride, drop,
+                     stream, nullptr, nullptr, false, q_mult);
 }

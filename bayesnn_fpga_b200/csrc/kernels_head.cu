@@ -19,7 +19,7 @@ constexpr int HEAD_WARPS = HEAD_THREADS / 32;
 constexpr int HEAD_SCHUNK = 16;  // samples staged in shared memory at a time
 
 template <typename T>
-struct __align__(16) Vec8h {
+struct __align__(8 * sizeof(T)) Vec8h {
   T v[8];
 };
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
     const float* __restrict__ wt, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
     float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate,
-    const T* __restrict__ w_hi, const T* __restrict__ w_lo) {
+    const T* __restrict__ w_hi, const T* __restrict__ w_lo, float feat_scale) {
   extern __shared__ float sm[];
   float* pooled = sm;
   float* part = pooled + (size_t)SCH * F;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float inv_hw = 1.f / (float)HW;
+  const float inv_hw = feat_scale / (float)HW;      // feat_scale: real value of one LSB of 8-bit features, else 1
 
   for (int c = tid; c < C; c += HEAD_THREADS) {
     acc_p[c] = 0.f;
@@ -455,7 +455,7 @@ int bnn_split16(const float* w, void* hi, void* lo, int64_t n, int dtype, void* 
 static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                          const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                          float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
-                         const void* w_lo);
+                         const void* w_lo, float feat_scale = 1.f);
 
 int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                   const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
@@ -475,10 +475,18 @@ int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, 
                        sum_plogp, logits_out, accumulate, stream, w_hi, w_lo);
 }
 
+int bnn_exit_head_q8(const void* feat_q, float feat_scale, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                     const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                     float* sum_plogp, float* logits_out, int accumulate, void* stream) {
+  BNN_REQUIRE(wt && feat_scale > 0.f, "bnn_exit_head_q8: bad arguments");
+  return exit_head_run(feat_q, BNN_I8, feat_has_samples, B, S_local, HW, F, C, wt, bias, drop, sum_p, sum_logit, sum_plogp,
+                       logits_out, accumulate, stream, nullptr, nullptr, feat_scale);
+}
+
 static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                          const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                          float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
-                         const void* w_lo) {
+                         const void* w_lo, float feat_scale) {
   if (int rc = check_device()) return rc;
   const bool mma = w_hi != nullptr;
   BNN_REQUIRE(feat && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
@@ -519,7 +527,7 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
     exit_head_kernel<T, M, SCH><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, \
                                                                C, wt, bias, dp, sum_p, sum_logit, sum_plogp,        \
                                                                logits_out, accumulate, (const T*)w_hi,              \
-                                                               (const T*)w_lo);                                     \
+                                                               (const T*)w_lo, feat_scale);                         \
   } while (0)
 #define BNN_HEAD_LAUNCH16(T)                                            \
   do {                                                                  \
@@ -532,6 +540,7 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
     case BNN_F32: BNN_HEAD_LAUNCH(float, false, HEAD_SCHUNK); break;
     case BNN_F16: BNN_HEAD_LAUNCH16(__half); break;
     case BNN_BF16: BNN_HEAD_LAUNCH16(__nv_bfloat16); break;
+    case BNN_I8: BNN_HEAD_LAUNCH(uint8_t, false, HEAD_SCHUNK); break;     // 8-bit features, fp32 FFMA classifier
     default: set_error("unknown dtype code %d", dtype); return BNN_E_ARG;
   }
 #undef BNN_HEAD_LAUNCH16

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) conv2d_simt_kernel(const T* __restrict__ 
 // and loops over the samples so the broadcast source is read from HBM once.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-struct __align__(16) Vec8 {
+struct __align__(8 * sizeof(T)) Vec8 {
   T v[8];
 };
 
@@ -402,6 +402,64 @@ static int dispatch_dtype(int dtype, F&& f) {
   }
 }
 
+// same, plus unsigned 8-bit activations (max-pool and the quantising stochastic layer of the 8-bit path)
+template <typename F>
+static int dispatch_dtype_q(int dtype, F&& f) {
+  if (dtype == BNN_I8) return f((uint8_t*)nullptr);
+  return dispatch_dtype(dtype, f);
+}
+
+// Stochastic layer of the 8-bit path: y_q[s][i] = clip(rint(x[i or s][i] * in_to_out * factor_s(i)), 0, 255) with the same
+// masks as dropout_kernel (factor = keep / (1 - p), a Masksembles row, ...).  x: 16-bit floats (the deterministic
+// prefix -> first 8-bit tensor: in_to_out = 1 / step_y) or unsigned 8-bit (in_to_out = step_x / step_y).
+template <typename TI>
+__global__ void __launch_bounds__(256) dropout_q8_kernel(const TI* __restrict__ x, uint8_t* __restrict__ y, int64_t n_per,
+                                                         int64_t per_image, int C, int S_local, int x_has_samples,
+                                                         float in_to_out, DropParams dp) {
+  const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (v0 >= n_per) return;
+  const bool vec = (v0 + 8 <= n_per) && (n_per % 8 == 0) && (dp.kind == BNN_DROP_ELEMENT || C % 8 == 0) && dp.nchw_flat == 0;
+  const int c0 = (int)(v0 % C);
+  const int64_t b0 = v0 / per_image;
+  for (int s = 0; s < S_local; ++s) {
+    const TI* xs = x + (x_has_samples ? (int64_t)s * n_per : 0);
+    uint8_t* ys = y + (int64_t)s * n_per;
+    if (vec) {
+      const Vec8<TI> in = *reinterpret_cast<const Vec8<TI>*>(xs + v0);
+      float f[8];
+      if (dp.kind == BNN_DROP_MASKSEMBLES) {
+        const int row = (int)(((int64_t)dp.cnt0 + dp.sample0 + s) % dp.n_masks);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __ldg(dp.masks + (size_t)row * C + c0 + j);
+      } else {
+        const uint64_t e = dp.kind == BNN_DROP_ELEMENT ? (uint64_t)v0 : (uint64_t)(b0 * C + c0);
+        const uint32_t k8 = dp.kind == BNN_DROP_NONE ? 0xffu : philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, e >> 3, dp.thr);
+        const float sc = dp.kind == BNN_DROP_NONE ? 1.f : dp.scale;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (sc != 0.f && ((k8 >> j) & 1u)) ? sc : 0.f;
+      }
+      Vec8<uint8_t> out;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        out.v[j] = from_f32<uint8_t>(__fmul_rn(__fmul_rn(to_f32<TI>(in.v[j]), in_to_out), f[j]));
+      *reinterpret_cast<Vec8<uint8_t>*>(ys + v0) = out;
+    } else {
+      for (int j = 0; j < 8 && v0 + j < n_per; ++j) {
+        const int64_t i = v0 + j;
+        const int c = (int)(i % C);
+        const int64_t b = i / per_image;
+        uint64_t e = (uint64_t)i;
+        if (dp.nchw_flat) {
+          const int64_t pix = (i - b * per_image) / C;
+          e = (uint64_t)(b * per_image + (int64_t)c * (per_image / C) + pix);
+        }
+        const float f = dp.kind == BNN_DROP_NONE ? 1.f : drop_factor(dp, (uint32_t)s, e, (uint64_t)(b * C + c), c);
+        ys[i] = from_f32<uint8_t>(__fmul_rn(__fmul_rn(to_f32<TI>(xs[i]), in_to_out), f));
+      }
+    }
+  }
+}
+
 }  // namespace bnn
 
 using namespace bnn;
@@ -524,6 +582,33 @@ int bnn_dropout(const void* x, void* y, int dtype, int64_t per_image, int C, int
   });
 }
 
+int bnn_dropout_q8(const void* x, void* y, int in_dtype, int64_t per_image, int C, int S_local, int x_has_samples,
+                   float in_to_out, const bnn_drop_desc* drop, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(x && y && drop && per_image >= 0 && C > 0 && S_local >= 0 && drop->batch >= 0, "bnn_dropout_q8: bad arguments");
+  BNN_REQUIRE(in_dtype == BNN_F16 || in_dtype == BNN_BF16 || in_dtype == BNN_I8, "bnn_dropout_q8: input must be 16-bit or 8-bit");
+  if (drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_dropout_q8: Masksembles site without a mask table");
+  }
+  const int64_t n_per = per_image * drop->batch;
+  if (n_per == 0 || S_local == 0) return BNN_OK;
+  const DropParams dp = make_drop_params(drop, C);
+  const int64_t threads = (n_per + 7) / 8;
+  return dispatch_dtype_q(in_dtype, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    if constexpr (std::is_same<T, float>::value) {
+      return (int)BNN_E_ARG;
+    } else {
+      dropout_q8_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+          (const T*)x, (uint8_t*)y, n_per, per_image, C, S_local, x_has_samples, in_to_out, dp);
+      BNN_LAUNCH_OK();
+      return (int)BNN_OK;
+    }
+  });
+}
+
 int bnn_channel_affine(const void* x, void* y, const float* scale, const float* bias, int dtype, int64_t pixels, int C,
                        int relu, void* stream) {
   if (int rc = check_device()) return rc;
@@ -546,7 +631,7 @@ int bnn_maxpool2d(const void* x, void* y, int dtype, int N, int H, int W, int C,
   const int OH = H / k, OW = W / k;
   const int64_t total = (int64_t)N * OH * OW * C;
   if (total == 0) return BNN_OK;
-  return dispatch_dtype(dtype, [&](auto* tag) {
+  return dispatch_dtype_q(dtype, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
     if (C % 8 == 0) {
       const int64_t tv = total / 8;

@@ -321,7 +321,11 @@ def _ptr(t):
 class Engine:
     """Executes a :class:`Graph` on the current CUDA device through the C ABI."""
 
-    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True, mask_gather=None, sample_chunk=None):
+    def __init__(self, graph, dtype="fp16", device=None, use_tc=True, fuse=True, mask_gather=None, sample_chunk=None,
+                 fuse_graph=True):
+        """fuse: sites into the producing convolution's epilogue; fuse_graph: the cross-op fusions on top of that
+        (projection shortcuts as extra K, head pools, sibling groups) - the 8-bit plan (q8.Q8Plan) keeps one op per
+        layer and switches them off."""
         if dtype not in DTYPES:
             raise ValueError("dtype must be one of %s" % sorted(DTYPES))
         if not torch.cuda.is_available():
@@ -346,16 +350,16 @@ class Engine:
             if not readers or not all(o.kind == "conv" and o.res is None and self._tc_eligible(o) for o in readers):
                 self.in_pad = 0
         self.gather_mode = int(os.environ.get("BNN_MASK_GATHER", "1")) if mask_gather is None else int(mask_gather)
-        if self.use_tc and fuse and os.environ.get("BNN_SHORTCUT_FUSION", "1") != "0":
+        if self.use_tc and fuse and fuse_graph and os.environ.get("BNN_SHORTCUT_FUSION", "1") != "0":
             # a Masksembles-masked block input may feed a fused shortcut only when it is materialised densely: a site
             # fused into its producer's epilogue (not the boundary site, which moves into per-mask weight sets, and not
             # the gathered layout of mode 2)
             graph.fuse_shortcuts(self._tc_eligible,
                                  allow_masked=lambda prod: self.gather_mode == 0 or
                                  (prod.kind == "conv" and self.gather_mode < 2))
-        if self.use_tc and fuse and os.environ.get("BNN_HEAD_POOL_FUSION", "1") != "0":
+        if self.use_tc and fuse and fuse_graph and os.environ.get("BNN_HEAD_POOL_FUSION", "1") != "0":
             graph.fuse_head_pools(self._tc_eligible)
-        if self.use_tc and fuse and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
+        if self.use_tc and fuse and fuse_graph and os.environ.get("BNN_NO_SIBLING_FUSION") != "1":
             graph.fuse_sibling_convs(self._tc_eligible)
         self.sample_chunk = int(os.environ.get("BNN_SAMPLE_CHUNK", "0")) if sample_chunk is None else int(sample_chunk)
         self.launches = 0

@@ -38,6 +38,7 @@ extern "C" {
 #define BNN_F32 0
 #define BNN_F16 1
 #define BNN_BF16 2
+#define BNN_I8 3   /* unsigned 8-bit activations / signed 8-bit weights (bnn_conv2d_tc_i8 only) */
 
 /* stochastic-layer kinds (which reference module a site replaces) */
 #define BNN_DROP_NONE 0
@@ -160,6 +161,33 @@ int bnn_conv2d_tc_gathered(const void* x, const void* w, const float* bias, void
                            uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Kc,
                            int cout_per_group, int ksize, int stride, int n_masks, int cnt0, uint32_t sample0,
                            int batch, int x_has_samples, void* stream);
+
+/* ---- 8-bit fixed-point convolution on the tensor cores (tcgen05.mma kind::i8) ----
+ * The B200 analogue of the reference's 8-bit QKeras layers (bayes_hw/models/t_qmodels_bayes_me.py:49-52, :59-63:
+ * QConv2D with kernel/bias quantizer quantized_bits(tbit = 8, ibit, alpha = 1) followed by QActivation
+ * quantized_relu(8)): activations are UNSIGNED 8-bit integers x_q (real value x_q * s_x), weights SIGNED 8-bit
+ * integers w_q (real w_q * s_w), the accumulation is exact in int32, and the epilogue requantises
+ *     y_q = clip(rint(float(acc) * q_mult + bias_q[c]) [* dropout], 0, 255)        rint = round half to even
+ * with q_mult = s_w * s_x / s_y and bias_q = bias / s_y (both float32; powers of two for QKeras formats).  The ReLU is
+ * the clip at 0.  x: NHWC uint8 [N][H][W][Cin], Cin % 128 == 0; w: int8 [Cout][k][k][Cin]; y: NHWC uint8; Cout % 64 == 0;
+ * k in {1, 3}, stride in {1, 2} (same geometry rules as bnn_conv2d_tc).  `drop` (may be NULL): a stochastic site fused
+ * behind the ReLU, applied in float before the requantisation (Philox element / channel masks, Masksembles rows). */
+int bnn_conv2d_tc_i8(const void* x, const void* w, const float* bias_q, void* y, int N, int H, int W, int Cin, int Cout,
+                     int ksize, int stride, float q_mult, const bnn_drop_desc* drop, void* stream);
+
+/* ---- the rest of the 8-bit path (unsigned 8-bit NHWC activations; real value = q * step) ----
+ * bnn_dropout_q8: the stochastic layer that produces / masks 8-bit tensors:
+ *     y_q[s][i] = clip(rint(x[..][i] * in_to_out * factor_s(i)), 0, 255)
+ *   with the masks of bnn_dropout.  x is the 16-bit deterministic prefix tensor (in_dtype BNN_F16 / BNN_BF16, in_to_out =
+ *   1 / step_y: the prefix is computed once per image and enters the 8-bit suffix here) or an 8-bit tensor (BNN_I8,
+ *   in_to_out = step_x / step_y).
+ * bnn_maxpool2d accepts dtype BNN_I8 (max commutes with the monotone quantiser).
+ * bnn_exit_head_q8: bnn_exit_head on 8-bit features (real value feat_q * feat_scale); the classifier runs in fp32. */
+int bnn_dropout_q8(const void* x, void* y, int in_dtype, int64_t per_image, int C, int S_local, int x_has_samples,
+                   float in_to_out, const bnn_drop_desc* drop, void* stream);
+int bnn_exit_head_q8(const void* feat_q, float feat_scale, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                     const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
+                     float* sum_plogp, float* logits_out, int accumulate, void* stream);
 
 /* ---- stand-alone stochastic layer (prefix -> suffix broadcast) ----
  * y[s][b][...] = drop_s(x[b][...]) for s in [0, S_local) when x_has_samples == 0 (the deterministic

@@ -100,8 +100,8 @@ def ece_width(p, label_index, n_bins=10):
 def ece_tfp_as_called(y_prob, label_index, n_bins=10):
     """What hls4ml_pred.py:90-91,115-116 really evaluates:
     ``tfp.stats.expected_calibration_error(num_bins, logits=y_prob, labels_true, labels_predicted=argmax(y_prob))``
-    with PROBABILITIES passed as `logits`.  tensorflow-probability is not installed (and not pinned by the reference:
-    Hardware_Artifact/requirements.txt lists no tfp version), so this restates the published algorithm of
+    with PROBABILITIES passed as `logits`.  tensorflow-probability (pinned by the reference: tensorflow_probability==0.16.0,
+    Hardware_Artifact/requirements.txt:9) is not installed here, so this restates the published algorithm of
     tensorflow_probability/python/stats/calibration.py (`_compute_calibration_bin_statistics` +
     `expected_calibration_error`), float32 like TF:
         pred   = softmax(logits)                      <- the second soft-max of already-normalised probabilities

@@ -457,3 +457,21 @@ def test_converter_structure_matches_the_reference_converter():
             Dropouts.BayesianDropout(nn.Linear(2, 2), bad)
         assert str(e.value) == str(z["err/%g" % bad][0])
     assert Dropouts.BayesianDropout2D(nn.Conv2d(1, 1, 1), 0.25).extra_repr() == str(z["extra_repr"][0])
+
+
+def test_q8_quantizers_follow_qkeras_definitions():
+    """quantized_bits(8, ibit) / quantized_relu(8, ibit) (qkeras/quantizers.py; used by the reference's 8-bit models,
+    t_qmodels_bayes_me.py:49-52): power-of-two steps, round half to even, saturating ranges - product == oracle."""
+    from bayesnn_fpga_b200 import q8
+    from oracle import q8 as oq8
+    x = torch.tensor([-2.0, -1.0, -0.996, -0.00390625, -0.001953125, 0.0, 0.001953125, 0.005859375, 0.5, 0.99, 1.0, 3.0])
+    q, step = q8.quantized_bits(x, 8, 0)
+    assert step == 2.0 ** -7 and q.tolist() == [-128, -128, -127, 0, 0, 0, 0, 1, 64, 127, 127, 127]
+    qo, so = oq8.quantized_bits_int(x.numpy(), 8, 0)
+    assert so == step and qo.tolist() == q.tolist()
+    q, step = q8.quantized_relu(x, 8, 0)
+    assert step == 2.0 ** -8 and q.tolist() == [0, 0, 0, 0, 0, 0, 0, 2, 128, 253, 255, 255]      # 0.5 LSB -> even
+    qo, so = oq8.quantized_relu_int(x.numpy(), 8, 0)
+    assert so == step and qo.tolist() == q.tolist()
+    q, step = q8.quantized_bits(x, 8, 2)                     # ibit = 2: range [-4, 4), step 2^-5
+    assert step == 2.0 ** -5 and q.tolist()[0] == -64 and q.tolist()[-1] == 96
