@@ -17,6 +17,6 @@ All arithmetic runs in the sm_100a kernels behind include/bnn_b200.h; there is n
 """
 from . import _lib                                   # noqa: F401
 from .engine import Engine, Graph, MCResult          # noqa: F401
-from .predict import mc_predict                      # noqa: F401
+from .predict import masksembles_batched_predict, mc_predict   # noqa: F401
 
-__all__ = ["mc_predict", "Engine", "Graph", "MCResult"]
+__all__ = ["mc_predict", "masksembles_batched_predict", "Engine", "Graph", "MCResult"]

@@ -166,6 +166,15 @@ class Graph:
         self.ops.append(Op("head", src, None, weight=w, bias=b, site=site, exit_index=self.n_exits, name=name))
         self.n_exits += 1
 
+    def mark_input_stochastic(self):
+        """The INPUT already carries the sample / group dimension: x is [G * B', ...] and "sample" g is the g-th
+        contiguous chunk of the batch.  This is the Masksembles training-branch / batched formulation
+        (Software_Artifact/software/utils.py:158-164: batch split into n groups, group g uses mask g): nothing is
+        shared between groups, so every tensor is per-group and every site picks its mask row by group index."""
+        for t in self.tensors:
+            t.stoch = True
+        return self
+
     # ---- analysis used by the planner and by the tests -------------------------------------
     def fuse_sites(self):
         """Fuse a site into the epilogue of the conv that produces its input when that conv already
@@ -523,7 +532,7 @@ class Engine:
                 continue                      # e.g. the un-masked output of a conv with a fused site
             n = (chunk if t.stoch else 1) * B
             if t is g.input and self.in_pad:
-                acts[t.id] = torch.zeros((B, t.H, t.W, self.in_pad), dtype=self.tdtype, device=dev)
+                acts[t.id] = torch.zeros((n, t.H, t.W, self.in_pad), dtype=self.tdtype, device=dev)
                 continue
             if t.id in compact:
                 # gathered layout; zero-filled once: the padding slots [kept, kc) are never written
@@ -532,7 +541,8 @@ class Engine:
             acts[t.id] = torch.empty((n, t.H, t.W, t.C), dtype=self.tdtype, device=dev)
         E, C = g.n_exits, g.n_classes
         st = {
-            "x": torch.empty((B, g.input.C, g.input.H, g.input.W), dtype=torch.float32, device=dev),
+            "x": torch.empty(((chunk if g.input.stoch else 1) * B, g.input.C, g.input.H, g.input.W), dtype=torch.float32,
+                             device=dev),
             "sums": torch.zeros((2 * E * B * C + E * B,), dtype=torch.float32, device=dev),
             "out": torch.empty((4 * E * B * C + 3 * E * B,), dtype=torch.float32, device=dev),
             "logits": (torch.empty((E, S_local, B, C), dtype=torch.float32, device=dev) if want_logits else None),
@@ -601,6 +611,14 @@ class Engine:
             op.src.H, op.src.W, info["kc"], d0.C, ksize, op.stride, info["n"], cnt0, 0, B, has_samples, stream)
         return call, flops, nbytes
 
+    def _batch(self, x, S_local):
+        """Images per sample: the batch itself, or (input with a group dimension) one group of it."""
+        if not self.graph.input.stoch:
+            return x.shape[0]
+        if S_local <= 0 or x.shape[0] % S_local != 0:
+            raise ValueError('Batch size must be divisible by n, got batch {} and n {}'.format(x.shape[0], S_local))
+        return x.shape[0] // S_local
+
     def sums_views(self, st, B):
         E, C = self.graph.n_exits, self.graph.n_classes
         n = E * B * C
@@ -625,7 +643,7 @@ class Engine:
         """Enqueue the whole pass for local samples [sample0, sample0 + S_local) on the current
         stream. Returns the buffer set (sums are in st['sums'])."""
         g, lib = self.graph, self.lib
-        B = x.shape[0]
+        B = self._batch(x, S_local)
         if tuple(x.shape[1:]) != (g.input.C, g.input.H, g.input.W):
             raise ValueError("expected input [B, %d, %d, %d], got %s" % (g.input.C, g.input.H, g.input.W,
                                                                          tuple(x.shape)))
@@ -638,9 +656,10 @@ class Engine:
         if B == 0:
             return st
         es = 4 if self.dtype_name == "fp32" else 2
-        n_in = B * g.input.C * g.input.H * g.input.W
+        n_img_in = x.shape[0]
+        n_in = n_img_in * g.input.C * g.input.H * g.input.W
         self._launch("layout", "nchw_to_nhwc", 0, n_in * (4 + es), lambda: lib.bnn_nchw_to_nhwc_pitch(
-            _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, B, g.input.C, g.input.H, g.input.W,
+            _ptr(st["x"]), _ptr(acts[g.input.id]), self.dcode, n_img_in, g.input.C, g.input.H, g.input.W,
             self.in_pad or g.input.C, stream))
         # deterministic prefix once; everything behind the first stochastic site in chunks of `chunk` samples so that
         # the activations handed from one layer to the next stay L2-resident (126 MB) instead of round-tripping HBM
@@ -793,7 +812,7 @@ class Engine:
             self._prof = []
             try:
                 st = self.enqueue(x, S_local, 0, seed)
-                self.finalize(st, x.shape[0], max(S_local, 1))
+                self.finalize(st, self._batch(x, S_local), max(S_local, 1))
                 torch.cuda.synchronize(self.device)
                 rec = self._prof
             finally:
@@ -832,7 +851,7 @@ class Engine:
         st = self.enqueue(x, S, sample0, seed, False, want_logits, mask_offset)
         if reduce_fn is not None:
             reduce_fn(st["sums"])
-        views, ent = self.finalize(st, x.shape[0], S_total)
+        views, ent = self.finalize(st, self._batch(x, S), S_total)
         if gather_fn is not None:
             gather_fn(st["out"])
         return st, views, ent
@@ -847,9 +866,9 @@ class Engine:
         replayed compute graph instead (decided once per engine)."""
         cnts = tuple(int(s.module.cnt) for s in self.graph.sites if s.kind == "mask")
         inside = self._graph_collectives and (reduce_fn is not None or gather_fn is not None)
-        key = (x.shape[0], S, sample0, seed, want_logits, mask_offset, cnts, S_total, reduce_fn is not None,
+        key = (self._batch(x, S), S, sample0, seed, want_logits, mask_offset, cnts, S_total, reduce_fn is not None,
                gather_fn is not None, inside)
-        st = self._buffers(x.shape[0], S, want_logits)
+        st = self._buffers(self._batch(x, S), S, want_logits)
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs[key] = "seen"
@@ -887,7 +906,7 @@ class Engine:
         if not inside:
             if reduce_fn is not None:                   # graph = launch sequence only; reduce, then finalise eagerly
                 reduce_fn(st["sums"])
-                views, ent = self.finalize(st, x.shape[0], S_total)
+                views, ent = self.finalize(st, self._batch(x, S), S_total)
             if gather_fn is not None:
                 gather_fn(st["out"])
         return st, views, ent
@@ -899,7 +918,7 @@ class Engine:
         finished statistics (batch sharding).  Masksembles rows are (module.cnt + mask_offset + s) % n with
         mask_offset defaulting to sample0."""
         x = x.to(self.device, torch.float32)
-        B = x.shape[0]
+        B = self._batch(x, S) if S > 0 else x.shape[0]
         if use_graph is None:
             use_graph = os.environ.get("BNN_CUDA_GRAPH", "1") != "0"
         S_total = S if S_total is None else S_total

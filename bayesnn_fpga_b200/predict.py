@@ -78,3 +78,33 @@ def mc_predict(model, x, S, seed=0x5EED, dtype=None, want_logits=False, distribu
         reduce_fn = lambda flat: allreduce_sums(flat, group)
     return eng.run(x, s_local, seed=seed, sample0=sample0, S_total=S, want_logits=want_logits,
                    reduce_fn=reduce_fn)
+
+
+def masksembles_batched_predict(model, x, dtype=None):
+    """The Keras converter's Masksembles inference (``MasksemblesModel.call(training=False)``,
+    Hardware_Artifact/converter/keras/Masksembles.py:216-239) for this package's multi-exit models: every input runs
+    through ALL n masks in one call and the n predictions are averaged.  The reference tiles the input n times along the
+    batch and lets every layer split it into n groups (:177-181, :220-223); here that is S = n samples of the fused plan
+    with sample g using mask row g - the layers in front of the first Masksembles layer run ONCE per image instead of n
+    times, nothing else changes.  The modules' eval-mode rotation counters are neither used nor advanced.
+
+    -> dict: ``per_exit`` [E, B, C] = mean over the n masks of each exit's soft-max output (:229-232),
+             ``prediction`` [B, C] = their average across exits (:233, what the reference returns for multi-output models).
+    """
+    from .utils import _MasksemblesBase
+    mods = [m for m in model.modules() if isinstance(m, _MasksemblesBase)]
+    if not mods:
+        raise ValueError("masksembles_batched_predict: the model has no Masksembles layers")
+    n = int(mods[0].n)
+    if any(int(m.n) != n for m in mods):
+        raise ValueError("Masksembles layers with different n in one network")
+    saved = [int(m.cnt) for m in mods]
+    for m in mods:
+        m.cnt = 0
+    try:
+        r = mc_predict(model, x, n, dtype=dtype)
+        per_exit = r.mean_probs.clone()
+    finally:
+        for m, c in zip(mods, saved):
+            m.cnt = c
+    return {"per_exit": per_exit, "prediction": per_exit.mean(0), "n": n}

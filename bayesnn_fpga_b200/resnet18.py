@@ -73,8 +73,53 @@ class _BnnModel(nn.Module):
             cache[key] = _engine.Engine(self._bnn_graph(), dtype=dtype, device=dev, **kw)
         return cache[key]
 
+    def _masksembles_modules(self):
+        from .utils import _MasksemblesBase
+        return [m for m in self.modules() if isinstance(m, _MasksemblesBase)]
+
+    def bnn_group_engine(self, dtype=None):
+        """Plan of the Masksembles BATCHED formulation (training branch of utils.py:158-164, :220-226): the batch is n
+        contiguous groups, group g runs through mask g of every Masksembles layer; nothing is shared between groups."""
+        dtype = dtype or self.bnn_dtype
+        cache = _plans.plans_for(self)
+        key = ("groups", dtype)
+        if key not in cache:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("bayesnn_fpga_b200 models run on a CUDA (sm_100) device only; there is no "
+                                   "CPU fallback - call model.cuda() first")
+            cache[key] = _engine.Engine(self._bnn_graph().mark_input_stochastic(), dtype=dtype, device=dev, mask_gather=0)
+        return cache[key]
+
+    def _forward_groups(self, x, mods):
+        """One forward in which every Masksembles module is in TRAINING mode: image group g uses mask row g
+        (no rotation of `cnt`, no rescale) - the reference modules' `if self.training` branch - through the fused plan."""
+        n = int(mods[0].n)
+        if any(int(m.n) != n for m in mods):
+            raise ValueError("Masksembles layers with different n in one network")
+        batch = x.shape[0]
+        if batch % n != 0:
+            raise ValueError('Batch size must be divisible by n, got batch {} and n {}'.format(batch, n))
+        eng = self.bnn_group_engine()
+        saved = [int(m.cnt) for m in mods]
+        for m in mods:
+            m.cnt = 0                                   # rows 0 .. n-1 in order, whatever the eval-mode counter says
+        try:
+            r = eng.run(x, n, seed=self.bnn_seed, want_logits=True, mask_offset=0)
+            # all_logits [n groups, E, batch / n, C] -> per exit [batch, C] in the original image order
+            outs = [r.all_logits[:, e].reshape(batch, -1).clone() for e in range(r.all_logits.shape[1])]
+        finally:
+            for m, c in zip(mods, saved):
+                m.cnt = c
+        return outs
+
     def forward(self, x):
         """One stochastic forward pass -> list of E logits tensors [B, out_dim]."""
+        mods = self._masksembles_modules()
+        if mods and all(m.training for m in mods):
+            outs = self._forward_groups(x, mods)
+            self.intermediary_output_list = (outs[-1], outs[:-1], None, [])
+            return outs
         eng = self.bnn_engine()
         sample = self.__dict__.get("_bnn_pass", 0)
         self.__dict__["_bnn_pass"] = sample + 1

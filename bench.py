@@ -500,6 +500,28 @@ def main():
         else:
             c5_strong = measure("c5", sub_steps, False, "samples")
 
+    if extras and world == 1 and args.dtype == "fp16":
+        # BASELINE config 4 with its stochastic suffix in 8 bits (q8.Q8Plan: tcgen05 kind::i8)
+        from bayesnn_fpga_b200 import q8
+        desc, kind, B, S, classes = WORKLOADS["c4"]
+        model = build_model(kind, classes).to(dev)
+        xq = torch.randn(B, *input_shape(kind), generator=torch.Generator().manual_seed(100)).to(dev)
+        plan = q8.Q8Plan(model, xq[:64], S_calib=4)
+        for _ in range(W):
+            plan.run(xq, S)
+        k8 = max(5, min(args.steps, 20))
+        ms8, _, win8 = timed(lambda: plan.run(xq, S), k8)
+        pre_macs, suf_macs = plan.eng.graph.macs()
+        extras["c4_int8_suffix"] = {
+            "workload": desc + " - stochastic suffix on unsigned 8-bit activations x signed 8-bit weights (tcgen05 "
+                               "kind::i8, int32 accumulate), prefix and classifiers unchanged",
+            "value": B * k8 / (ms8 * 1e-3), "unit": "images/s", "ms_per_step": ms8 / k8, "steps": k8,
+            "suffix_tera_ops_per_s": 2.0 * B * S * suf_macs / (ms8 / k8 * 1e-3) / 1e12,
+            "speedup_vs_fp16_c4": extras["c4"]["ms_per_step"] / (ms8 / k8), "cuda_graph": False,
+            "clocks": sampler.window(*win8) if rank == 0 else None}
+        del plan, model
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         desc, kind, B, S, classes = WORKLOADS[head_wl]

@@ -56,6 +56,23 @@ class InjectedSites:
         return x * (torch.from_numpy(keep).to(x.dtype) * float(scale))
 
 
+class GroupSites:
+    """Masksembles TRAINING-branch / batched formulation: the batch is split into n contiguous groups and group g is
+    multiplied by mask row g (Software_Artifact/software/utils.py:158-164, :220-226; the Keras layer does the same
+    to an input tiled n times, Hardware_Artifact/converter/keras/Masksembles.py:177-181).  No rotation, no rescale."""
+
+    def __init__(self, spec):
+        self.spec = spec
+
+    def __call__(self, name, x):
+        m = self.spec.masks[name]
+        n, batch = m.shape[0], x.shape[0]
+        if batch % n != 0:
+            raise ValueError('Batch size must be divisible by n, got batch {} and n {}'.format(batch, n))
+        rows = m[torch.arange(batch) // (batch // n)].to(x.dtype)                  # [batch, C]
+        return x * rows.reshape(batch, -1, *([1] * (x.dim() - 2)))
+
+
 class TorchRngSites:
     """site(name, x) exactly as the reference executes it (torch global RNG; stateful
     Masksembles counter).  Used for the CPU baseline timing leg."""

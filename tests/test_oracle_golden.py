@@ -178,3 +178,25 @@ def test_mask_contract_rows_of_a_larger_batch():
         tail = nets.lenet_forward(sd, x[3:], nets.InjectedSites(spec, 9, 1, batch_offset=3))
     for a, b in zip(whole, tail):
         assert torch.allclose(a[3:], b, atol=1e-6)
+
+
+def test_masksembles_batched_formulation_oracle_matches_reference_fixture():
+    """oracle.nets.GroupSites (batch split into n groups, group g x mask g) reproduces the outputs frozen from the
+    reference's own Masksembles training branch inside its ResNet18MCEarlyExit, and the Keras batched inference
+    formulation built on it (tests/golden/make_golden_masksembles_batched.py)."""
+    z = np.load(GOLDEN + "/masksembles_batched.npz")
+    model, sd, gold = build_seeded("resnet18_mask_block")
+    tables = {k[:-len(".masks")]: v for k, v in sd.items() if k.endswith(".masks")}
+    spec = nets.SiteSpec("mask", 0.0, tables)
+    with torch.no_grad():
+        got = nets.resnet18_forward(sd, torch.from_numpy(z["groups_x"]), nets.GroupSites(spec), "block", True)
+        for a, w in zip(got, z["groups_logits"]):
+            assert np.abs(a.numpy() - w).max() < 2e-6
+        with pytest.raises(ValueError) as e:
+            nets.resnet18_forward(sd, torch.from_numpy(z["groups_x"][:6]), nets.GroupSites(spec), "block", True)
+        assert str(e.value) == str(z["groups_error"][0])
+        xb = torch.from_numpy(z["batched_x"])
+        preds = [torch.softmax(o, 1) for o in nets.resnet18_forward(sd, torch.cat([xb] * 4), nets.GroupSites(spec), "block", True)]
+    per_exit = np.stack([p.reshape(4, -1, p.shape[-1]).mean(0).numpy() for p in preds])
+    assert np.abs(per_exit - z["batched_exit_probs"]).max() < 2e-6
+    assert np.abs(per_exit.mean(0) - z["batched_avg"]).max() < 2e-6
