@@ -11,6 +11,9 @@
 namespace bnn {
 
 void set_error(const char* fmt, ...);
+// conv_tc.cu: the exit-head classifier as a tcgen05 GEMM (fp32 logits); used by kernels_head.cu
+int conv_tc_head_gemm(const void* a, const void* w3, const float* bias_pad, float* logits, int dtype, int M, int Fa, int Cpad,
+                      int kblocks, int head_c, void* stream);
 int check_device();  // BNN_OK iff current device is sm_100
 int sm_count();
 

@@ -86,6 +86,11 @@ struct Params {
   // pooled row [N][Cout] is written - the exit head's input
   int pool_hw;
   int a_img_mod;   // > 0: the input has no sample dimension (deterministic prefix): output image n reads input n % a_img_mod
+  // exit-head GEMM (bnn_exit_head_tc): a 1x1 "convolution" over [x_hi | x_lo] with weights [w_hi | w_lo | w_hi] - k-block
+  // kb of the weights multiplies A block (kb < head_c ? kb : kb - head_c), so x_hi is used twice without being stored
+  // twice; the epilogue writes fp32 logits
+  int head_c;      // > 0: channel blocks of x_hi
+  int out_f32;     // epilogue stores float32 (non-swapped kernels only)
   float q_mult;    // 8-bit operands: output LSBs per accumulator LSB = w_scale * in_scale / out_scale (a power of two
                    // for the QKeras fixed-point formats, any float otherwise)
   int vh_a, vh_w;  // vertical-halo form: slots of the haloed-activation ring and of the weight ring
@@ -578,6 +583,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int hp = rh & 1, dh = (rh - hp) >> 1;                 // -1 -> (1, -1); 0 -> (0, 0); 1 -> (1, 0)
           const int wp = rw & 1, dw = (rw - wp) >> 1;
           for (int cb = 0; cb < p.cblocks; ++cb) {
+            const int a_cb = (p.head_c > 0 && cb >= p.head_c) ? cb - p.head_c : cb;     // exit-head GEMM: x_hi twice
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if constexpr (CG2) {
               // both CTAs' loads complete on the leader's barrier: it expects the bytes of the pair
@@ -586,7 +592,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < NLOAD; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                 else
                   tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh,
                                   img0[mt]);
@@ -603,7 +609,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   for (int mt = 0; mt < MT; ++mt) {
                     uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                     if (p.stride == 1)
-                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                     else
                       tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
                   }
@@ -621,7 +627,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < MT; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
                 else
                   tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
               }
@@ -1043,6 +1049,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
               continue;
             }
+            if (p.out_f32) {
+              float* yf = reinterpret_cast<float*>(p.yg[dead ? 0 : grp]) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yf + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              continue;
+            }
             if constexpr (I8) {
               // requantise: round half to even, clip to the unsigned 8-bit grid of quantized_relu; 32 bytes per pixel
               uint32_t w8[8];
@@ -1183,6 +1195,11 @@ struct GatherSel {
   int x_has_samples;          // 0: x holds `batch` images shared by all samples
 };
 
+struct HeadGemm {
+  int kblocks;   // 64-element k-blocks of the weight matrix (2 or 3 times head_c)
+  int head_c;    // k-blocks of x_hi (= F / 64); A block of weight block kb is kb < head_c ? kb : kb - head_c
+};
+
 struct Shortcut {
   const void* x2;   // [N][H2][W2][Cin2]: the input of the residual block, H2 = 2 * OH, W2 = 2 * OW
   int H2, W2, Cin2;
@@ -1192,7 +1209,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                        int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
                        const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr, bool pool = false,
-                       float q_mult = 1.f) {
+                       float q_mult = 1.f, const HeadGemm* hg = nullptr) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
@@ -1296,7 +1313,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // transposed (operand-swapped) kernel: groups of exactly 128 channels; channel-wise dropout is not implemented
   // in its epilogue, and its stochastic epilogue assumes a 32-pixel chunk never straddles two MC samples
   const bool swap_ok =
-      !i8 && BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
+      !i8 && hg == nullptr && BN == 128 && cout_g == 128 && !(drop && drop->kind == BNN_DROP_CHANNEL) &&
       !(drop && drop->kind != BNN_DROP_NONE && ((int64_t)drop->batch * OH * OW) % 32 != 0) &&
       getenv("BNN_TC_NOSWAP") == nullptr;
   const bool cg2_narrow_box = !i8 && mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
@@ -1313,7 +1330,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     ta2 = ta;
   }
   {
-    const int K = ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
+    const int K = hg ? hg->kblocks * tc::BK : ksize * ksize * Cin + (sc ? sc->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout * (cuuint64_t)(gsel ? gsel->n_masks : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)K * eb};
     const cuuint32_t box[2] = {(cuuint32_t)bke, (cuuint32_t)((mc2 || cg2_narrow_box) ? BN / 2 : BN)};
@@ -1330,6 +1347,12 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   p.Cin = Cin;
   p.last_ksteps = (Cin - (p.cblocks - 1) * bke) / (i8 ? 2 * tc::UMMA_K : tc::UMMA_K);
   p.q_mult = q_mult;
+  if (hg) {                                   // exit-head GEMM: K runs over the weight blocks, A blocks wrap (see Params)
+    p.cblocks = hg->kblocks;
+    p.last_ksteps = tc::BK / tc::UMMA_K;
+    p.head_c = hg->head_c;
+    p.out_f32 = 1;
+  }
   if (gsel) {
     p.wsel_n = gsel->n_masks;
     p.wsel_cnt0 = ((gsel->cnt0 % gsel->n_masks) + gsel->n_masks) % gsel->n_masks;
@@ -1500,4 +1523,14 @@ extern "C" int bnn_conv2d_tc_i8(const void* x, const void* w, const float* bias_
   void* ys[1] = {y};
   return conv_tc_run("bnn_conv2d_tc_i8", x, w, bias_q, nullptr, ys, 1, 1u, 0u, BNN_I8, N, H, W, Cin, Cout, ksize, stride, drop,
                      stream, nullptr, nullptr, false, q_mult);
+}
+
+// logits[M][Cpad] (fp32) = [x_hi | x_lo][M][Fa] * W3[Cpad][kblocks * 64]^T + bias - the classifier of an exit head as a
+// tcgen05 GEMM with hi/lo-split 16-bit operands (see kernels_head.cu: bnn_exit_head_tc)
+int bnn::conv_tc_head_gemm(const void* a, const void* w3, const float* bias_pad, float* logits, int dtype, int M, int Fa,
+                           int Cpad, int kblocks, int head_c, void* stream) {
+  void* ys[1] = {logits};
+  HeadGemm hg{kblocks, head_c};
+  return conv_tc_run("bnn_exit_head_tc", a, w3, bias_pad, nullptr, ys, 1, 0u, 0u, dtype, M, 1, 1, Fa, Cpad, 1, 1, nullptr, stream,
+                     nullptr, nullptr, false, 1.f, &hg);
 }
