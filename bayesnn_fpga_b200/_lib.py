@@ -129,6 +129,9 @@ _SIGS = {
     "bnn_exit_head_mma": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                                                   ctypes.POINTER(DropDesc)] +
                           [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]),
+    "bnn_exit_head_tc": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                                                ctypes.c_int, ctypes.POINTER(DropDesc)] +
+                         [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p]),
     "bnn_split16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_void_p]),
     "bnn_finalize": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 8),

@@ -230,6 +230,120 @@ __global__ void split16_kernel(const float* __restrict__ w, TM* __restrict__ hi,
   lo[i] = to_tm<TM>(v - to_f32<TM>(h));
 }
 
+// Features of the tensor-core exit head: global average pool -> stochastic site -> hi / lo split.  One thread per
+// (row = sample x image, feature octet): x_hi to a[row][f], and (when the features are not exactly representable in 16
+// bits: a pooled mean, or a dropout scale that is not a power of two) the remainder x_lo to a[row][F + f].
+template <typename T>
+__global__ void __launch_bounds__(256) head_prep_kernel(const T* __restrict__ feat, int feat_has_samples, int B, int S_local,
+                                                        int HW, int F, DropParams dp, T* __restrict__ a, int a_pitch,
+                                                        int with_lo) {
+  const int octs = F / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S_local * B * octs) return;
+  const int f0 = (int)(idx % octs) * 8;
+  const int64_t row = idx / octs;                        // s * B + b
+  const int b = (int)(row % B), s = (int)(row / B);
+  const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f0;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < HW; ++p) {
+    const Vec8h<T> v = *reinterpret_cast<const Vec8h<T>*>(src + (size_t)p * F);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += to_f32<T>(v.v[j]);
+  }
+  uint32_t k8 = 0xffu;
+  float fac = 1.f / (float)HW;
+  if (dp.kind == BNN_DROP_ELEMENT || dp.kind == BNN_DROP_CHANNEL) {
+    k8 = dp.scale == 0.f ? 0u : philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, ((uint64_t)b * F + f0) >> 3, dp.thr);
+    fac *= dp.scale;
+  }
+  Vec8h<T> vh, vl;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = ((k8 >> j) & 1u) ? acc[j] * fac : 0.f;
+    if (dp.kind == BNN_DROP_MASKSEMBLES) v *= drop_factor(dp, (uint32_t)s, 0, 0, f0 + j);
+    vh.v[j] = to_tm<T>(v);
+    vl.v[j] = to_tm<T>(v - to_f32<T>(vh.v[j]));
+  }
+  *reinterpret_cast<Vec8h<T>*>(a + (size_t)row * a_pitch + f0) = vh;
+  if (with_lo) *reinterpret_cast<Vec8h<T>*>(a + (size_t)row * a_pitch + F + f0) = vl;
+}
+
+// Soft-max + running sums over the samples for logits that already sit in global memory (the tensor-core head): one
+// CTA of SM_WARPS warps per image, lanes over the classes (NPL per lane); warp w walks samples w, w + SM_WARPS, ... in
+// order and the per-warp partial sums are combined in a fixed order (deterministic).  No barriers inside the sample
+// loop - the block-per-image chunked form of exit_head_kernel spent ~7 us per 16-sample chunk in barriers and dependent
+// loads (83 us per C4 head), a single warp per image 49 us in its own dependent shuffle / expf chain.
+constexpr int SM_WARPS = 8;
+template <int NPL>
+__global__ void __launch_bounds__(SM_WARPS * 32) head_softmax_warp_kernel(
+    const float* __restrict__ logits_in, int pitch, int B, int S_local, int C, float* __restrict__ sum_p,
+    float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate) {
+  __shared__ float part_p[SM_WARPS][NPL * 32], part_l[SM_WARPS][NPL * 32], part_pl[SM_WARPS];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ap[NPL], al[NPL], apl = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) ap[j] = al[j] = 0.f;
+  float v[NPL], nxt[NPL];
+  auto load = [&](int s, float (&dst)[NPL]) {
+    const float* row = logits_in + ((size_t)s * B + b) * pitch;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) dst[j] = (lane + 32 * j < C) ? __ldg(row + lane + 32 * j) : -INFINITY;
+  };
+  if (warp < S_local) load(warp, nxt);
+  for (int s = warp; s < S_local; s += SM_WARPS) {
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) v[j] = nxt[j];
+    if (s + SM_WARPS < S_local) load(s + SM_WARPS, nxt);   // the next row is in flight while this one is reduced
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) mx = fmaxf(mx, v[j]);
+    mx = warp_max(mx);
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j)
+      if (lane + 32 * j < C) den += expf(v[j] - mx);
+    den = warp_sum(den);
+    const float inv = 1.f / den, logden = logf(den);
+    float pl = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) {
+        const float z = v[j] - mx, e = expf(z);
+        pl += e * inv * (z - logden);
+        ap[j] += e * inv;
+        al[j] += v[j];
+        if (logits_out) logits_out[((size_t)s * B + b) * C + c] = v[j];
+      }
+    }
+    apl += warp_sum(pl);
+  }
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    part_p[warp][lane + 32 * j] = ap[j];
+    part_l[warp][lane + 32 * j] = al[j];
+  }
+  if (lane == 0) part_pl[warp] = apl;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += SM_WARPS * 32) {
+    float tp = 0.f, tl = 0.f;
+#pragma unroll
+    for (int w = 0; w < SM_WARPS; ++w) {
+      tp += part_p[w][c];
+      tl += part_l[w][c];
+    }
+    const size_t o = (size_t)b * C + c;
+    sum_p[o] = (accumulate ? sum_p[o] : 0.f) + tp;
+    sum_logit[o] = (accumulate ? sum_logit[o] : 0.f) + tl;
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SM_WARPS; ++w) t += part_pl[w];
+    sum_plogp[b] = (accumulate ? sum_plogp[b] : 0.f) + t;
+  }
+}
+
 // dynamic shared memory layout (floats):
 //   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1)] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
 //   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
@@ -242,7 +356,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
     const T* __restrict__ feat, int feat_has_samples, int B, int S_local, int HW, int F, int C,
     const float* __restrict__ wt, const float* __restrict__ bias, DropParams dp, float* __restrict__ sum_p,
     float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate,
-    const T* __restrict__ w_hi, const T* __restrict__ w_lo, float feat_scale) {
+    const T* __restrict__ w_hi, const T* __restrict__ w_lo, float feat_scale,
+    const float* __restrict__ logits_in = nullptr, int logits_pitch = 0) {
+  // logits_in != nullptr: the classifier already ran as a tensor-core GEMM (bnn_exit_head_tc) and left fp32 logits
+  // [S_local][B][logits_pitch] in global memory - only the soft-max / accumulation phases run here
   extern __shared__ float sm[];
   float* pooled = sm;
   float* part = pooled + (size_t)SCH * F;
@@ -250,6 +367,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   T* a_hi = reinterpret_cast<T*>(sm);
   T* a_lo = a_hi + (size_t)SCH * (F + HEAD_APAD);
   if constexpr (MMA) logits = reinterpret_cast<float*>(a_lo + (size_t)SCH * (F + HEAD_APAD));
+  if (logits_in != nullptr) logits = sm;                // no feature / partial-sum staging in this mode
   float* acc_p = logits + (size_t)SCH * C;
   float* acc_l = acc_p + C;
   float* red = acc_l + C;
@@ -269,6 +387,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
   for (int s0 = 0; s0 < S_local; s0 += SCH) {
     const int ns = min(SCH, S_local - s0);
     __syncthreads();
+    if (logits_in != nullptr) {
+      for (int idx = tid; idx < ns * C; idx += HEAD_THREADS) {
+        const int sl = idx / C, c = idx - sl * C;
+        logits[idx] = __ldg(logits_in + ((size_t)(s0 + sl) * B + b) * logits_pitch + c);
+      }
+      __syncthreads();
+    } else {
     // ---- phase 1: pooled + masked feature vectors for ns samples -----------------------------
     if (F % 8 == 0) {
       // vector path: a thread owns 8 consecutive features (16-byte loads for 16-bit storage, all HW loads of
@@ -342,6 +467,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) exit_head_kernel(
       head_gemm<4>(pooled, part, logits, wt, bias, F, C, ns, tid);
     else
       head_gemm<1>(pooled, part, logits, wt, bias, F, C, ns, tid);
+    }
     // ---- phase 3a: softmax statistics per sample (one warp per sample) -----------------------
     for (int sl = warp; sl < ns; sl += HEAD_WARPS) {
       const float* lg = logits + sl * C;
@@ -455,7 +581,7 @@ int bnn_split16(const float* w, void* hi, void* lo, int64_t n, int dtype, void* 
 static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                          const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                          float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
-                         const void* w_lo, float feat_scale = 1.f);
+                         const void* w_lo, float feat_scale = 1.f, const float* logits_in = nullptr, int logits_pitch = 0);
 
 int bnn_exit_head(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                   const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
@@ -475,6 +601,61 @@ int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, 
                        sum_plogp, logits_out, accumulate, stream, w_hi, w_lo);
 }
 
+int bnn_exit_head_tc(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                     const void* w3, const float* bias_pad, int c_pad, int with_lo, const bnn_drop_desc* drop, void* a_ws,
+                     float* logits_ws, float* sum_p, float* sum_logit, float* sum_plogp, float* logits_out, int accumulate,
+                     void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(feat && w3 && bias_pad && a_ws && logits_ws && sum_p && sum_logit && sum_plogp, "bnn_exit_head_tc: null pointer");
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_exit_head_tc: features must be float16 or bfloat16");
+  BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && F % 64 == 0 && C > 0 && c_pad >= C && c_pad % 64 == 0,
+              "bnn_exit_head_tc: bad geometry (F=%d must be a multiple of 64, c_pad=%d a multiple of 64 >= C=%d)", F, c_pad, C);
+  if (drop && drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_exit_head_tc: Masksembles site without a mask table");
+  }
+  if (B == 0 || S_local == 0) {
+    if (B > 0 && !accumulate) {
+      BNN_CUDA_OK(cudaMemsetAsync(sum_p, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
+      BNN_CUDA_OK(cudaMemsetAsync(sum_logit, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream));
+      BNN_CUDA_OK(cudaMemsetAsync(sum_plogp, 0, sizeof(float) * (size_t)B, (cudaStream_t)stream));
+    }
+    return BNN_OK;
+  }
+  DropParams dp = make_drop_params(drop, F);
+  dp.batch = B;
+  const int a_pitch = with_lo ? 2 * F : F;
+  const int64_t items = (int64_t)S_local * B * (F / 8);
+  const int M = S_local * B;
+  // 1. features: pool -> site -> hi [| lo]     2. logits = [x_hi | x_lo] x [w_hi | w_lo | w_hi]^T on tcgen05 (fp32 out)
+  if (dtype == BNN_F16)
+    head_prep_kernel<__half><<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)feat, feat_has_samples, B, S_local, HW, F, dp, (__half*)a_ws, a_pitch, with_lo);
+  else
+    head_prep_kernel<__nv_bfloat16><<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)feat, feat_has_samples, B, S_local, HW, F, dp, (__nv_bfloat16*)a_ws, a_pitch, with_lo);
+  BNN_LAUNCH_OK();
+  const int head_c = F / 64;
+  if (int rc = conv_tc_head_gemm(a_ws, w3, bias_pad, logits_ws, dtype, M, a_pitch, c_pad, (with_lo ? 3 : 2) * head_c, head_c,
+                                 stream))
+    return rc;
+  // 3. soft-max, running sums over the samples (deterministic order), optional per-sample logits
+  if (C <= 512) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 32)
+      head_softmax_warp_kernel<1><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+    else if (C <= 128)
+      head_softmax_warp_kernel<4><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+    else
+      head_softmax_warp_kernel<16><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+    BNN_LAUNCH_OK();
+    return BNN_OK;
+  }
+  return exit_head_run(nullptr, BNN_F32, 1, B, S_local, 1, F, C, nullptr, bias_pad, nullptr, sum_p, sum_logit, sum_plogp,
+                       logits_out, accumulate, stream, nullptr, nullptr, 1.f, logits_ws, c_pad);
+}
+
 int bnn_exit_head_q8(const void* feat_q, float feat_scale, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                      const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                      float* sum_plogp, float* logits_out, int accumulate, void* stream) {
@@ -486,10 +667,10 @@ int bnn_exit_head_q8(const void* feat_q, float feat_scale, int feat_has_samples,
 static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
                          const float* wt, const float* bias, const bnn_drop_desc* drop, float* sum_p, float* sum_logit,
                          float* sum_plogp, float* logits_out, int accumulate, void* stream, const void* w_hi,
-                         const void* w_lo, float feat_scale) {
+                         const void* w_lo, float feat_scale, const float* logits_in, int logits_pitch) {
   if (int rc = check_device()) return rc;
   const bool mma = w_hi != nullptr;
-  BNN_REQUIRE(feat && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
+  BNN_REQUIRE((feat || logits_in) && bias && sum_p && sum_logit && sum_plogp, "bnn_exit_head: null pointer");
   BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && C > 0, "bnn_exit_head: bad geometry");
   if (drop && drop->kind != BNN_DROP_NONE) {
     BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g",
@@ -500,6 +681,7 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
   if (B == 0) return BNN_OK;
   auto smem_for = [&](int sch) {
     const size_t tail = ((size_t)sch * C + 2 * (size_t)C + HEAD_WARPS + 2 * (size_t)sch) * sizeof(float);
+    if (logits_in != nullptr) return tail;
     return mma ? 2 * (size_t)sch * (F + HEAD_APAD) * 2 + tail
                : ((size_t)sch * F + (size_t)HEAD_THREADS * sch * (C > 32 ? 4 : 1)) * sizeof(float) + tail;
   };
@@ -527,7 +709,7 @@ static int exit_head_run(const void* feat, int dtype, int feat_has_samples, int 
     exit_head_kernel<T, M, SCH><<<B, HEAD_THREADS, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, \
                                                                C, wt, bias, dp, sum_p, sum_logit, sum_plogp,        \
                                                                logits_out, accumulate, (const T*)w_hi,              \
-                                                               (const T*)w_lo, feat_scale);                         \
+                                                               (const T*)w_lo, feat_scale, logits_in, logits_pitch);\
   } while (0)
 #define BNN_HEAD_LAUNCH16(T)                                            \
   do {                                                                  \

@@ -423,7 +423,12 @@ class Engine:
                 C_, F_ = op.weight.shape
                 op.head_mma = (self.dtype_name != "fp32" and C_ > 32 and F_ % 32 == 0 and
                                os.environ.get("BNN_HEAD_MMA", "1") != "0")
-                if op.head_mma:
+                # ... or, on 16-bit features with F % 64 == 0, the whole classifier as ONE tcgen05 GEMM over hi/lo-split
+                # operands (bnn_exit_head_tc): [x_hi | x_lo] x [w_hi | w_lo | w_hi]^T with fp32 logits
+                # (narrow heads, C <= 32, stay on the one-kernel FFMA form: three launches cost more than they save)
+                op.head_tc = (self.dtype_name != "fp32" and self.use_tc and F_ % 64 == 0 and C_ > 32 and
+                              os.environ.get("BNN_HEAD_TC", "1") != "0")
+                if op.head_mma or op.head_tc:
                     w32 = op.weight.contiguous().to(dev, torch.float32)             # [C][F], the nn.Linear layout
                     op.d_w_hi = torch.empty((C_, F_), dtype=self.tdtype, device=dev)
                     op.d_w_lo = torch.empty((C_, F_), dtype=self.tdtype, device=dev)
@@ -431,6 +436,20 @@ class Engine:
                         _lib.check(self.lib.bnn_split16(_ptr(w32), _ptr(op.d_w_hi), _ptr(op.d_w_lo), C_ * F_, self.dcode,
                                                         ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
                         torch.cuda.current_stream(dev).synchronize()
+                if op.head_tc:
+                    # features exactly representable in 16 bits (already-pooled 16-bit rows, mask multipliers that are
+                    # 0/1 or powers of two) need no x_lo block
+                    p_ = op.site.p if op.site is not None and op.site.kind != "mask" else 0.0
+                    keep_scale = 1.0 / (1.0 - p_) if p_ < 1.0 else 0.0
+                    pow2 = keep_scale == 0.0 or abs(np.log2(keep_scale) - round(np.log2(keep_scale))) < 1e-12
+                    op.head_with_lo = int(not (op.src.H * op.src.W == 1 and pow2))
+                    op.c_pad = (C_ + 63) // 64 * 64 if C_ <= 128 else (C_ + 255) // 256 * 256
+                    parts = [op.d_w_hi, op.d_w_lo] + ([op.d_w_hi] if op.head_with_lo else [])
+                    w3 = torch.zeros((op.c_pad, len(parts) * F_), dtype=self.tdtype, device=dev)
+                    w3[:C_] = torch.cat(parts, dim=1)
+                    op.d_w3 = w3.contiguous()
+                    op.d_b_pad = torch.zeros(op.c_pad, dtype=torch.float32, device=dev)
+                    op.d_b_pad[:C_] = op.d_b
             if op.site is not None and op.site.kind == "mask":
                 op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()
 
@@ -540,6 +559,13 @@ class Engine:
                 continue
             acts[t.id] = torch.empty((n, t.H, t.W, t.C), dtype=self.tdtype, device=dev)
         E, C = g.n_exits, g.n_classes
+        head_ws = None
+        tc_heads = [o for o in g.ops if o.kind == "head" and getattr(o, "head_tc", False)]
+        if tc_heads:            # one workspace pair shared by all tensor-core heads (they run back to back on the stream)
+            rows = chunk * B
+            head_ws = (torch.empty(rows * max((2 if o.head_with_lo else 1) * o.src.C for o in tc_heads), dtype=self.tdtype,
+                                   device=dev),
+                       torch.empty(rows * max(o.c_pad for o in tc_heads), dtype=torch.float32, device=dev))
         st = {
             "x": torch.empty(((chunk if g.input.stoch else 1) * B, g.input.C, g.input.H, g.input.W), dtype=torch.float32,
                              device=dev),
@@ -547,6 +573,7 @@ class Engine:
             "out": torch.empty((4 * E * B * C + 3 * E * B,), dtype=torch.float32, device=dev),
             "logits": (torch.empty((E, S_local, B, C), dtype=torch.float32, device=dev) if want_logits else None),
             "acts": acts,
+            "head_ws": head_ws,
             "compact": compact,
             "gmode": gmode,
             "chunk": chunk,
@@ -791,7 +818,13 @@ class Engine:
                 hw = op.src.H * op.src.W
                 nbytes = (S_local if op.src.stoch else 1) * B * hw * op.src.C * es + op.d_w.numel() * 4
                 flops = 2 * S_local * B * op.src.C * g.n_classes
-                if op.head_mma:
+                if getattr(op, "head_tc", False) and S_local > 0:
+                    a_ws, l_ws = st["head_ws"]
+                    call = lambda: lib.bnn_exit_head_tc(
+                        _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
+                        _ptr(op.d_w3), _ptr(op.d_b_pad), op.c_pad, op.head_with_lo, ctypes.byref(dd), _ptr(a_ws), _ptr(l_ws),
+                        _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]), _ptr(lo_e), int(accumulate), stream)
+                elif op.head_mma:
                     call = lambda: lib.bnn_exit_head_mma(
                         _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
                         _ptr(op.d_w_hi), _ptr(op.d_w_lo), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]),
@@ -802,6 +835,8 @@ class Engine:
                         _ptr(op.d_w), _ptr(op.d_b), ctypes.byref(dd), _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]),
                         _ptr(lo_e), int(accumulate), stream)
                 self._launch("exit_head", op.name, flops, nbytes, call)
+                if getattr(op, "head_tc", False) and S_local > 0:
+                    self.launches += 2            # features + tcgen05 GEMM + soft-max / accumulate: three kernels
 
     def profile_step(self, x, S_local, seed=0x5EED):
         """Device time of every launch of one step (CUDA events on the launching stream).

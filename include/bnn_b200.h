@@ -234,6 +234,19 @@ int bnn_exit_head_mma(const void* feat, int dtype, int feat_has_samples, int B, 
 /* hi[i] = round16(w[i]), lo[i] = round16(w[i] - hi[i]) in `dtype` (1 = float16, 2 = bfloat16). */
 int bnn_split16(const float* w, void* hi, void* lo, int64_t n, int dtype, void* stream);
 
+/* bnn_exit_head with the classifier on the 5th-generation tensor cores (wide heads: C = 100 ... 1000):
+ *   1. features: average pool -> stochastic site -> 16-bit high part x_hi [and remainder x_lo when with_lo != 0: pooled
+ *      means, dropout scales that are not powers of two] into a_ws [S_local * B][F or 2F]
+ *   2. logits_ws [S_local * B][c_pad] (fp32) = [x_hi | x_lo] x w3^T + bias_pad as ONE tcgen05 GEMM; w3 is the nn.Linear
+ *      weight split into hi / lo 16-bit parts and laid out [c_pad][w_hi | w_lo (| w_hi)] (F columns each, rows >= C zero):
+ *      x_hi * w_hi + x_hi * w_lo (+ x_lo * w_hi) keeps the logits within ~2^-20 of the fp32 classifier
+ *   3. soft-max, running sums over the samples, per-sample logits - as bnn_exit_head.
+ * a_ws / logits_ws are caller-owned workspaces. */
+int bnn_exit_head_tc(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                     const void* w3, const float* bias_pad, int c_pad, int with_lo, const bnn_drop_desc* drop, void* a_ws,
+                     float* logits_ws, float* sum_p, float* sum_logit, float* sum_plogp, float* logits_out, int accumulate,
+                     void* stream);
+
 /* ---- statistics finaliser ----
  * From the (all-reduced) sums over S_total samples: predictive mean, mean logits, cumulative exit ensembles
  * (results_analyzer.py:247-248, :260-269), entropy of the mean with the reference's 1e-8 epsilon

@@ -590,6 +590,59 @@ def test_exit_head_mma_matches_ffma_head(lib, dt, C, F_, HW, kind, S):
                                  stream()) == -1                     # F % 16 != 0
 
 
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("C,F_,HW,kind,p,S,B", [(100, 512, 4, 1, 0.25, 19, 5), (100, 512, 1, 1, 0.5, 40, 37), (10, 512, 1, 3, 0.0, 4, 9),
+                                              (10, 512, 16, 1, 0.5, 33, 6), (1000, 256, 1, 2, 0.125, 16, 3), (37, 64, 1, 0, 0.0, 3, 70)])
+def test_exit_head_tc_matches_ffma_head(lib, dt, C, F_, HW, kind, p, S, B):
+    """bnn_exit_head_tc - pool -> site -> hi/lo split, the classifier as ONE tcgen05 GEMM over [x_hi | x_lo] x
+    [w_hi | w_lo | w_hi]^T with fp32 logits, soft-max / accumulation - == bnn_exit_head (fp32 FFMA) on the same 16-bit
+    features, with and without the x_lo block (exact features: HW = 1 and a power-of-two keep scale)."""
+    tdt, code = TORCH_DT[dt]
+    s0, seed, sid = 3, 0x99, 2
+    g = torch.Generator().manual_seed(C + S)
+    feat = (torch.randn(S * B, HW, F_, generator=g).abs() * 3).to(tdt).cuda()
+    w = (torch.randn(C, F_, generator=g) / np.sqrt(F_) * 3).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    masks = (torch.rand(4, F_, generator=g) > 0.5).float().cuda()
+    dd = drop_desc(kind, p, seed, sid, s0, B, masks if kind == 3 else None, cnt0=1)
+    w_hi, w_lo = torch.empty(C, F_, dtype=tdt, device="cuda"), torch.empty(C, F_, dtype=tdt, device="cuda")
+    assert lib.bnn_split16(w.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C * F_, code, stream()) == 0
+    scale_keep = 1.0 / (1.0 - p) if kind in (1, 2) else 1.0
+    with_lo = int(not (HW == 1 and abs(np.log2(scale_keep) - round(np.log2(scale_keep))) < 1e-12))
+    c_pad = (C + 63) // 64 * 64 if C <= 128 else (C + 255) // 256 * 256
+    parts = [w_hi, w_lo] + ([w_hi] if with_lo else [])
+    w3 = torch.zeros(c_pad, len(parts) * F_, dtype=tdt, device="cuda")
+    w3[:C] = torch.cat(parts, dim=1)
+    b_pad = torch.zeros(c_pad, device="cuda")
+    b_pad[:C] = bias
+    a_ws = torch.empty(S * B * (2 if with_lo else 1) * F_, dtype=tdt, device="cuda")
+    l_ws = torch.empty(S * B * c_pad, device="cuda")
+    outs = {}
+    for name in ("ffma", "tc"):
+        o = dict(sp=torch.zeros(B, C).cuda(), sl=torch.zeros(B, C).cuda(), spl=torch.zeros(B).cuda(), lo=torch.zeros(S, B, C).cuda())
+        if name == "ffma":
+            wt = w.t().contiguous()
+            rc = lib.bnn_exit_head(feat.data_ptr(), code, 1, B, S, HW, F_, C, wt.data_ptr(), bias.data_ptr(), ctypes.byref(dd),
+                                   o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(), o["lo"].data_ptr(), 0, stream())
+        else:
+            rc = lib.bnn_exit_head_tc(feat.data_ptr(), code, 1, B, S, HW, F_, C, w3.data_ptr(), b_pad.data_ptr(), c_pad, with_lo,
+                                      ctypes.byref(dd), a_ws.data_ptr(), l_ws.data_ptr(), o["sp"].data_ptr(), o["sl"].data_ptr(),
+                                      o["spl"].data_ptr(), o["lo"].data_ptr(), 0, stream())
+        assert rc == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        outs[name] = o
+    scale = max(1.0, outs["ffma"]["lo"].abs().max().item())
+    e_lo = (outs["tc"]["lo"] - outs["ffma"]["lo"]).abs().max().item()
+    e_p = (outs["tc"]["sp"] - outs["ffma"]["sp"]).abs().max().item()
+    e_pl = (outs["tc"]["spl"] - outs["ffma"]["spl"]).abs().max().item()
+    report(test="exit_head_tc", dtype=dt, C=C, F=F_, HW=HW, with_lo=with_lo, err_logits=e_lo, err_sum_p=e_p, scale=scale)
+    tol = 1e-5 if dt == "fp16" else 3e-4          # bf16 hi+lo carries 16 mantissa bits
+    assert e_lo <= tol * scale and e_p <= tol * S and e_pl <= 10 * tol * S
+    assert lib.bnn_exit_head_tc(feat.data_ptr(), code, 1, B, S, HW, 24, C, w3.data_ptr(), b_pad.data_ptr(), c_pad, with_lo,
+                                ctypes.byref(dd), a_ws.data_ptr(), l_ws.data_ptr(), o["sp"].data_ptr(), o["sl"].data_ptr(),
+                                o["spl"].data_ptr(), None, 0, stream()) == -1          # F % 64 != 0
+
+
 @pytest.mark.parametrize("Cin2,C,H,N,pair", [(64, 128, 16, 6, "0"), (128, 256, 8, 20, "0"), (256, 512, 4, 70, "0"),
                                               (128, 256, 8, 20, "cg2"), (128, 256, 8, 21, "mc2")])
 @pytest.mark.parametrize("drop_kind", [0, 1])
