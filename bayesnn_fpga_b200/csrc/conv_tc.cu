@@ -89,6 +89,11 @@ struct Params {
   // exit-head GEMM (bnn_exit_head_tc): a 1x1 "convolution" over [x_hi | x_lo] with weights [w_hi | w_lo | w_hi] - k-block
   // kb of the weights multiplies A block (kb < head_c ? kb : kb - head_c), so x_hi is used twice without being stored
   // twice; the epilogue writes fp32 logits
+  // MASKED (sibling-pair kernel behind an element-wise MC-dropout site at the prefix boundary): x is the ONE scaled
+  // deterministic tensor (a_img_mod images), mask_bits holds one keep bit per element of every sample
+  // ([N][H][W][Cin / 8] bytes, written by bnn_boundary_bits); helper warps AND the bits into the tile in shared memory
+  const uint8_t* mask_bits;
+  int in_h, in_w;  // input map size (mask-bit addressing)
   int head_c;      // > 0: channel blocks of x_hi
   int out_f32;     // epilogue stores float32 (non-swapped kernels only)
   float q_mult;    // 8-bit operands: output LSBs per accumulator LSB = w_scale * in_scale / out_scale (a power of two
@@ -291,6 +296,27 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
 }
 
+// release at cluster scope: the arriving thread's shared-memory writes (of EITHER CTA of the pair) are visible to whoever
+// acquires the leader's barrier at cluster scope
+__device__ __forceinline__ void mbar_arrive_leader_release_cluster(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE_C;\n"
+      "bra.uni WAIT_LOOP_C;\n"
+      "WAIT_DONE_C:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy writes to shared memory (the mask warps' STS) -> visible to the async proxy (tensor-core operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // same, arriving on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -378,8 +404,8 @@ constexpr int VH_RING_BYTES = 220 * 1024;         // both rings together; the sp
 constexpr int VH_MAX_SLOTS = 12;
 __host__ __device__ constexpr int smem_bytes_vh() { return VH_RING_BYTES + 1024 + 256; }
 
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false>
-__global__ void __launch_bounds__(num_threads(EW) + (VH ? 32 : 0), 1)
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false, bool MASKED = false>
+__global__ void __launch_bounds__(num_threads(EW) + (VH ? 32 : 0) + (MASKED ? 128 : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_ah, const Params p) {
   constexpr bool MC2 = PAIR == 1;
@@ -393,6 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   static_assert(!I8 || (!SWAP && !COMPACT && !VH && PAIR != 1), "8-bit operands: plain and cta_group::2 kernels only");
   static_assert(!VH || (SWAP && PAIR == 0 && BN == 128 && MT == 2), "VH is a variant of the operand-swapped kernel");
   static_assert(!(SWAP && PAIR == 1), "the multicast pairing of the operand-swapped kernel was retired");
+  static_assert(!MASKED || (SWAP && PAIR == 2 && !VH), "in-kernel keep-bit masking: sibling-pair kernel only");
   // SCG2 (SWAP && CG2, "sibling pair"): the CTA pair works on the SAME 256 output pixels; CTA r owns output group
   // 2 * pair + r (its 128 weight rows are the pair-MMA's M rows r*128..) and loads only ITS half of the pixel tile (the
   // MMA's N = 256 columns are split over the pair), so a CTA ingests 16 KB of activations per k-block instead of 32 KB
@@ -416,7 +443,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // MASKED: afull = this CTA's pixel tile has landed (local); ready = both CTAs' mask warps are done with the stage (leader)
+  uint64_t* afull_bar = tmem_empty + 2;
+  uint64_t* ready_bar = afull_bar + (MASKED ? STAGES : 0);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + (MASKED ? STAGES : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.cblocks;
@@ -437,6 +467,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], CG2 ? 2 * EW : EW);   // one arrive per epilogue warp (of both CTAs)
     }
+    if constexpr (MASKED)
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&afull_bar[i], 1);
+        mbar_init(&ready_bar[i], 8);                  // four mask warps in each CTA of the pair
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -547,6 +582,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (MASKED && warp >= 2 + EW) {
+    // ===================== mask warps (sibling pair behind the prefix-boundary MC-dropout site) =====================
+    // One thread per pixel row of this CTA's 128-pixel tile: its 64 channels of the current channel block are eight
+    // 16-byte chunks (128-byte swizzle: chunk j of row r sits at ((j ^ (r & 7)) << 4)); the pixel's keep bits for those
+    // 64 channels are ONE 8-byte word of mask_bits.  AND, fence to the async proxy, hand the stage to the MMA issuer.
+    const int r = (int)threadIdx.x - (2 + EW) * 32;       // 0 .. 127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int row_in_tile = r / p.OW, ow = r - row_in_tile * p.OW;
+    const int cbytes = p.Cin >> 3;                          // mask bytes per input pixel
+    for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
+      const int m_unit = tile / p.n_tiles_n;
+      const int m0 = (m_unit * MT + (int)cta_rank) * BM;
+      const bool live = m0 < p.M;
+      const int img = live ? m0 / p.OHW : 0;               // sample x image index (NOT reduced modulo the batch)
+      const int oh = (live ? (m0 - img * p.OHW) / p.OW : 0) + row_in_tile;
+      auto bits_of = [&](int tap, int cb) -> uint64_t {
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const int ih = 2 * oh + kh - 1, iw = 2 * ow + kw - 1;
+        if (!live || ih < 0 || iw < 0 || ih >= p.in_h || iw >= p.in_w) return 0ull;     // zero padding: nothing to keep
+        return __ldg(reinterpret_cast<const unsigned long long*>(
+            p.mask_bits + (((size_t)img * p.in_h + ih) * p.in_w + iw) * cbytes + cb * 8));
+      };
+      uint64_t cur = bits_of(0, 0);
+      for (int tap = 0; tap < p.taps; ++tap)
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          // the next k-block's bits are in flight while this stage is processed
+          const int ncb = cb + 1 == p.cblocks ? 0 : cb + 1, ntap = ncb == 0 ? tap + 1 : tap;
+          const uint64_t nxt = ntap < p.taps ? bits_of(ntap, ncb) : 0ull;
+          mbar_wait(&afull_bar[stage], phase);
+          uint8_t* row = smem_a + stage * A_STAGE + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4* q = reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4));
+            uint4 v = *q;
+            const uint32_t b8 = (uint32_t)(cur >> (8 * j)) & 0xffu;
+            // bit i of b8 keeps 16-bit element i of the chunk
+            v.x &= ((b8 & 1u) ? 0x0000ffffu : 0u) | ((b8 & 2u) ? 0xffff0000u : 0u);
+            v.y &= ((b8 & 4u) ? 0x0000ffffu : 0u) | ((b8 & 8u) ? 0xffff0000u : 0u);
+            v.z &= ((b8 & 16u) ? 0x0000ffffu : 0u) | ((b8 & 32u) ? 0xffff0000u : 0u);
+            v.w &= ((b8 & 64u) ? 0x0000ffffu : 0u) | ((b8 & 128u) ? 0xffff0000u : 0u);
+            *q = v;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader_release_cluster(&ready_bar[stage]);
+          cur = nxt;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+    }
   } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -587,6 +675,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if constexpr (CG2) {
               // both CTAs' loads complete on the leader's barrier: it expects the bytes of the pair
+              if constexpr (MASKED) {
+                // pixels: plain load that completes on THIS CTA's barrier (its mask warps pick the tile up there);
+                // weights of both CTAs: on the leader's full barrier, as before
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * B_TILE);
+                mbar_expect_tx(&afull_bar[stage], A_STAGE);
+                tma_load_5d(smem_a + stage * A_STAGE, &tmap_a, &afull_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[0] + dh,
+                            img0[0]);
+              } else {
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
               for (int mt = 0; mt < NLOAD; ++mt) {
@@ -596,6 +692,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 else
                   tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh,
                                   img0[mt]);
+              }
               }
               tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE,
                               SCG2 ? wrow : wrow + (int)cta_rank * (BN / 2));
@@ -695,6 +792,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int ksteps = (++cb == p.cblocks) ? p.last_ksteps : BK / UMMA_K;
           if (cb == p.cblocks) cb = 0;
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          if constexpr (MASKED) mbar_wait_acquire_cluster(&ready_bar[stage], phase);   // ... and both pixel halves are masked
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
           if (leader) {
@@ -1143,13 +1241,13 @@ static int encode_map(CUtensorMap* out, int dtype, int rank, const void* base, c
   return BNN_OK;
 }
 
-template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false>
+template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false, bool MASKED = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st,
                   const CUtensorMap* tah = nullptr) {
   static bool configured = false;
   constexpr int smem = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR, SWAP);
   constexpr bool MC2 = PAIR != 0;
-  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T, VH>;
+  auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T, VH, MASKED>;
   const CUtensorMap& th = tah ? *tah : ta;
   if (!configured) {
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1162,7 +1260,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     int grid = 2 * p.num_tiles < (sm_count() & ~1) ? 2 * p.num_tiles : (sm_count() & ~1);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(num_threads(EW) + (VH ? 32 : 0));
+    cfg.blockDim = dim3(num_threads(EW) + (VH ? 32 : 0) + (MASKED ? 128 : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
