@@ -117,6 +117,11 @@ _SIGS = {
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_channel_affine": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]),
+    "bnn_boundary_bits": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 6 + [ctypes.POINTER(DropDesc), ctypes.c_void_p]),
+    "bnn_conv2d_tc_grouped_masked": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_uint32] + [ctypes.c_int] * 7 +
+                                     [ctypes.c_void_p]),
+    "bnn_conv2d_tc_shortcut_plane": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int] * 9 +
+                                     [ctypes.POINTER(DropDesc), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "bnn_dropout_q8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_exit_head_q8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p,

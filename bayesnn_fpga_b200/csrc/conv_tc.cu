@@ -81,6 +81,8 @@ struct Params {
   // SECOND tensor (tmap_a2: the block input x, centre tap of its stride-2 parity view) and whose weights are the
   // columns [taps * Cin, taps * Cin + 64 * cblocks2) of the K-concatenated weight matrix
   int cblocks2;
+  int sc_dense;    // the shortcut operand is already the even/even parity plane [N][OH][OW][Cin2] (written by
+                   // bnn_boundary_bits): a dense 4-D box instead of the centre tap of the 5-D parity view
   // fused global average pool (bnn_conv2d_tc_pooled): the output map of one image (pool_hw = OH * OW pixels, a power of
   // two <= 32, so one image = pool_hw adjacent lanes of an epilogue warp) is averaged with warp shuffles and only the
   // pooled row [N][Cout] is written - the exit head's input
@@ -100,7 +102,8 @@ struct Params {
                    // for the QKeras fixed-point formats, any float otherwise)
   int vh_a, vh_w;  // vertical-halo form: slots of the haloed-activation ring and of the weight ring
   int exp_flags;   // MEASUREMENT ONLY (BNN_TC_EXP, results are garbage): bit 0 = do not load activation tiles, bit 1 = do
-                   // not load weight tiles - isolates what operand delivery costs a launch
+                   // not load weight tiles - isolates what operand delivery costs a launch; MASKED kernel: 4 = no
+                   // masking, 8 = no proxy fence, 16 / 32 = CTA-scope instead of cluster-scope wait / arrive
   const float* bias;
   const void* res;
   void* yg[4];
@@ -510,9 +513,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[as], aph ^ 1);
           mbar_expect_tx(&full_bar[as], A_STAGE);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            tma_load_5d(smem_a + as * VH_A_BYTES + mt * A_TILE_BYTES, &tmap_a2, &full_bar[as], cb * BKE, 0, 0,
-                        mt * (BM / p.OW), tile);
+          for (int mt = 0; mt < MT; ++mt) {
+            uint8_t* dst = smem_a + as * VH_A_BYTES + mt * A_TILE_BYTES;
+            if (p.sc_dense)
+              tma_load_4d(dst, &tmap_a2, &full_bar[as], cb * BKE, 0, mt * (BM / p.OW), tile);
+            else
+              tma_load_5d(dst, &tmap_a2, &full_bar[as], cb * BKE, 0, 0, mt * (BM / p.OW), tile);
+          }
           if (++as == VH_A_SLOTS) { as = 0; aph ^= 1; }
         }
       }
@@ -605,35 +612,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         return __ldg(reinterpret_cast<const unsigned long long*>(
             p.mask_bits + (((size_t)img * p.in_h + ih) * p.in_w + iw) * cbytes + cb * 8));
       };
-      uint64_t cur = bits_of(0, 0);
-      for (int tap = 0; tap < p.taps; ++tap)
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          // the next k-block's bits are in flight while this stage is processed
-          const int ncb = cb + 1 == p.cblocks ? 0 : cb + 1, ntap = ncb == 0 ? tap + 1 : tap;
-          const uint64_t nxt = ntap < p.taps ? bits_of(ntap, ncb) : 0ull;
+      // keep bits of the next PF k-blocks are in flight while a stage is processed (one dependent L2 load per stage
+      // with a look-ahead of one paced the whole kernel: 2 600 cycles per k-block)
+      constexpr int PF = 4;
+      const int nkb = p.taps * p.cblocks;
+      uint64_t ring[PF];
+#pragma unroll
+      for (int i = 0; i < PF; ++i) ring[i] = i < nkb ? bits_of(i / p.cblocks, i % p.cblocks) : 0ull;
+      for (int kb = 0; kb < nkb; kb += PF) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          if (kb + i >= nkb) break;
+          const uint64_t cur = ring[i];
+          const int nx = kb + i + PF;
+          ring[i] = nx < nkb ? bits_of(nx / p.cblocks, nx % p.cblocks) : 0ull;
           mbar_wait(&afull_bar[stage], phase);
           uint8_t* row = smem_a + stage * A_STAGE + r * 128;
+          if (!(p.exp_flags & 4))                     // (measurement switch: leave the tile unmasked)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4* q = reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4));
             uint4 v = *q;
             const uint32_t b8 = (uint32_t)(cur >> (8 * j)) & 0xffu;
-            // bit i of b8 keeps 16-bit element i of the chunk
-            v.x &= ((b8 & 1u) ? 0x0000ffffu : 0u) | ((b8 & 2u) ? 0xffff0000u : 0u);
-            v.y &= ((b8 & 4u) ? 0x0000ffffu : 0u) | ((b8 & 8u) ? 0xffff0000u : 0u);
-            v.z &= ((b8 & 16u) ? 0x0000ffffu : 0u) | ((b8 & 32u) ? 0xffff0000u : 0u);
-            v.w &= ((b8 & 64u) ? 0x0000ffffu : 0u) | ((b8 & 128u) ? 0xffff0000u : 0u);
+            // bit i of b8 keeps 16-bit element i of the chunk: spread four bits into four 0x00 / 0xFF bytes with one
+            // multiply, then duplicate each byte into a halfword mask with PRMT
+            const uint32_t lo = (((b8 & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+            const uint32_t hi = (((b8 >> 4) * 0x00204081u) & 0x01010101u) * 0xffu;
+            v.x &= __byte_perm(lo, 0u, 0x1100);
+            v.y &= __byte_perm(lo, 0u, 0x3322);
+            v.z &= __byte_perm(hi, 0u, 0x1100);
+            v.w &= __byte_perm(hi, 0u, 0x3322);
             *q = v;
           }
-          fence_proxy_async_smem();
+          if (!(p.exp_flags & 8)) fence_proxy_async_smem();      // (measurement switch)
           __syncwarp();
-          if (lane == 0) mbar_arrive_leader_release_cluster(&ready_bar[stage]);
-          cur = nxt;
+          if (lane == 0) {
+            if (p.exp_flags & 32) mbar_arrive_leader(&ready_bar[stage]); else mbar_arrive_leader_release_cluster(&ready_bar[stage]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
+      }
     }
   } else if (warp == 0) {
     // ===================== TMA producer =====================
@@ -746,17 +767,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if constexpr (CG2) {
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0,
-                              oh0[mt], img0[mt]);
+            for (int mt = 0; mt < MT; ++mt) {
+              if (p.sc_dense)
+                tma_load_4d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, oh0[mt],
+                                img0[mt]);
+              else
+                tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0,
+                                oh0[mt], img0[mt]);
+            }
             tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BKE,
                             wrow + (int)cta_rank * (BN / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0, oh0[mt],
-                          img0[mt]);
+            for (int mt = 0; mt < MT; ++mt) {
+              if (p.sc_dense)
+                tma_load_4d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, oh0[mt],
+                            img0[mt]);
+              else
+                tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0, oh0[mt],
+                            img0[mt]);
+            }
             if constexpr (MC2)
               tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
                              p.taps * p.Cin + cb * BKE, wrow + (int)cta_rank * (BN / 2), (uint16_t)3);
@@ -792,7 +823,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int ksteps = (++cb == p.cblocks) ? p.last_ksteps : BK / UMMA_K;
           if (cb == p.cblocks) cb = 0;
           mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
-          if constexpr (MASKED) mbar_wait_acquire_cluster(&ready_bar[stage], phase);   // ... and both pixel halves are masked
+          if constexpr (MASKED) {                         // ... and both pixel halves are masked
+            if (p.exp_flags & 16) mbar_wait(&ready_bar[stage], phase); else mbar_wait_acquire_cluster(&ready_bar[stage], phase);
+          }
           tc_fence_after();
           const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
           if (leader) {
@@ -1301,13 +1334,19 @@ struct HeadGemm {
 struct Shortcut {
   const void* x2;   // [N][H2][W2][Cin2]: the input of the residual block, H2 = 2 * OH, W2 = 2 * OW
   int H2, W2, Cin2;
+  int dense;        // x2 is already the even/even parity plane [N][OH][OW][Cin2]
+};
+
+struct MaskSel {
+  const void* bits;   // keep bits of every sample of x ([N][H][W][Cin / 8] bytes, bnn_boundary_bits)
+  int batch;          // x holds `batch` images shared by all samples
 };
 
 static int conv_tc_run(const char* who, const void* x, const void* w, const float* bias, const void* res,
                        void* const* y, int groups, uint32_t relu_mask, uint32_t center_mask, int dtype, int N, int H, int W, int Cin,
                        int cout_g, int ksize, int stride, const bnn_drop_desc* drop, void* stream,
                        const GatherSel* gsel = nullptr, const Shortcut* sc = nullptr, bool pool = false,
-                       float q_mult = 1.f, const HeadGemm* hg = nullptr) {
+                       float q_mult = 1.f, const HeadGemm* hg = nullptr, const MaskSel* msk = nullptr) {
   if (int rc = check_device()) return rc;
   BNN_REQUIRE(x && w && bias && y, "%s: null pointer", who);
   BNN_REQUIRE(groups >= 1 && groups <= 4, "%s: 1..4 output groups supported, got %d", who, groups);
@@ -1372,7 +1411,13 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
 
   CUtensorMap ta, tb, ta2;
   const cuuint64_t eb = i8 ? 1 : 2;
-  const int N_in = (gsel && !gsel->x_has_samples) ? gsel->batch : N;     // images held by x
+  const int N_in = msk ? msk->batch : ((gsel && !gsel->x_has_samples) ? gsel->batch : N);     // images held by x
+  if (msk) {
+    BNN_REQUIRE(msk->bits != nullptr && msk->batch > 0 && N % msk->batch == 0 && gsel == nullptr && sc == nullptr && !pool &&
+                    groups >= 2 && groups % 2 == 0 && cout_g == 128 && ksize == 3 && stride == 2 && center_mask == 0 &&
+                    Cin % 64 == 0 && dtype != BNN_I8 && tc::BM % OW == 0,
+                "%s: in-kernel keep-bit masking needs an even number of 3x3 stride-2 sibling groups of 128 channels", who);
+  }
   if (stride == 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N_in};
     const cuuint64_t strides[3] = {(cuuint64_t)Cin * eb, (cuuint64_t)W * Cin * eb, (cuuint64_t)H * W * Cin * eb};
@@ -1417,7 +1462,13 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const bool cg2_narrow_box = !i8 && mc2_any && BN < 256 && gsel == nullptr && getenv("BNN_TC_CG2_NARROW") &&
                               atoi(getenv("BNN_TC_CG2_NARROW")) == 1 &&
                               !(getenv("BNN_TC_CG2") && atoi(getenv("BNN_TC_CG2")) == 0);
-  if (sc) {
+  if (sc && sc->dense) {
+    const int C2 = sc->Cin2;
+    const cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C2 * eb, (cuuint64_t)OW * C2 * eb, (cuuint64_t)OH * OW * C2 * eb};
+    const cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    if (int rc = tc::encode_map(&ta2, dtype, 4, sc->x2, dims, strides, box)) return rc;
+  } else if (sc) {
     const int C2 = sc->Cin2, H2 = sc->H2, W2 = sc->W2;
     const cuuint64_t dims[5] = {(cuuint64_t)2 * C2, (cuuint64_t)W2 / 2, 2, (cuuint64_t)H2 / 2, (cuuint64_t)N};
     const cuuint64_t strides[4] = {(cuuint64_t)2 * C2 * eb, (cuuint64_t)W2 * C2 * eb, (cuuint64_t)2 * W2 * C2 * eb,
@@ -1459,6 +1510,13 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   }
   p.exp_flags = getenv("BNN_TC_EXP") ? atoi(getenv("BNN_TC_EXP")) : 0;
   p.cblocks2 = sc ? sc->Cin2 / tc::BK : 0;
+  p.sc_dense = sc ? sc->dense : 0;
+  if (msk) {
+    p.mask_bits = reinterpret_cast<const uint8_t*>(msk->bits);
+    p.a_img_mod = msk->batch;
+    p.in_h = H;
+    p.in_w = W;
+  }
   p.pool_hw = pool ? OH * OW : 0;
   p.stride = stride;
   p.pad = pad;
@@ -1548,6 +1606,12 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     bool scg2 = groups >= 2 && groups % 2 == 0 && gsel == nullptr && getenv("BNN_TC_NO_SCG2") == nullptr;
     for (int g = 0; scg2 && g + 1 < groups; g += 2)
       scg2 = ((p.center_mask >> g) & 1u) == ((p.center_mask >> (g + 1)) & 1u);
+    if (msk) {
+      BNN_REQUIRE(scg2, "%s: in-kernel keep-bit masking needs the sibling-pair kernel", who);
+      p.n_tiles_n = groups / 2;
+      return dtype == BNN_F16 ? tc::launch<128, 2, true, 2, false, 8, __half, false, true>(ta, tb, ta2, p, st)
+                              : tc::launch<128, 2, true, 2, false, 8, __nv_bfloat16, false, true>(ta, tb, ta2, p, st);
+    }
     if (scg2) {
       p.n_tiles_n = groups / 2;
       switch (BN) { BNN_TC_DISPATCH(128, 2, true, 2) }
@@ -1603,7 +1667,7 @@ extern "C" int bnn_conv2d_tc_shortcut(const void* x, const void* w, const float*
                                       int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
                                       const bnn_drop_desc* drop, const void* x2, int H2, int W2, int Cin2, void* stream) {
   void* ys[1] = {y};
-  Shortcut sc{x2, H2, W2, Cin2};
+  Shortcut sc{x2, H2, W2, Cin2, 0};
   return conv_tc_run("bnn_conv2d_tc_shortcut", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
                      stride, drop, stream, nullptr, &sc);
 }
@@ -1614,6 +1678,23 @@ extern "C" int bnn_conv2d_tc_pooled(const void* x, const void* w, const float* b
   void* ys[1] = {y_pooled};
   return conv_tc_run("bnn_conv2d_tc_pooled", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
                      stride, nullptr, stream, nullptr, nullptr, true);
+}
+
+extern "C" int bnn_conv2d_tc_grouped_masked(const void* x_scaled, const void* mask_bits, const void* w, const float* bias,
+                                            void* const* y, int n_groups, uint32_t relu_mask, int dtype, int N, int batch, int H,
+                                            int W, int Cin, int cout_per_group, void* stream) {
+  MaskSel msk{mask_bits, batch};
+  return conv_tc_run("bnn_conv2d_tc_grouped_masked", x_scaled, w, bias, nullptr, y, n_groups, relu_mask, 0u, dtype, N, H, W, Cin,
+                     cout_per_group, 3, 2, nullptr, stream, nullptr, nullptr, false, 1.f, nullptr, &msk);
+}
+
+extern "C" int bnn_conv2d_tc_shortcut_plane(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype,
+                                            int N, int H, int W, int Cin, int Cout, int ksize, int stride, int relu,
+                                            const bnn_drop_desc* drop, const void* x2_plane, int Cin2, void* stream) {
+  void* ys[1] = {y};
+  Shortcut sc{x2_plane, 2 * H, 2 * W, Cin2, 1};
+  return conv_tc_run("bnn_conv2d_tc_shortcut_plane", x, w, bias, res, ys, 1, relu ? 1u : 0u, 0u, dtype, N, H, W, Cin, Cout, ksize,
+                     stride, drop, stream, nullptr, &sc);
 }
 
 extern "C" int bnn_conv2d_tc_i8(const void* x, const void* w, const float* bias_q, void* y, int N, int H, int W, int Cin,

@@ -409,42 +409,55 @@ static int dispatch_dtype(int dtype, F&& f) {
 // plane [S][B][H/2][W/2][C].  Same Philox blocks, same rounding as dropout_kernel: consumers reproduce its values bit
 // for bit.  One thread = 8 consecutive channels of one pixel = one Philox block per sample.
 template <typename T>
-__global__ void __launch_bounds__(256) boundary_bits_kernel(const T* __restrict__ x, T* __restrict__ x_scaled,
-                                                            uint8_t* __restrict__ bits, T* __restrict__ plane, int64_t n_per,
+__global__ void __launch_bounds__(128) boundary_bits_kernel(const T* __restrict__ x, T* __restrict__ x_scaled,
+                                                            uint8_t* __restrict__ bits, T* __restrict__ plane, int64_t n_pix,
                                                             int H, int W, int C, int S_local, DropParams dp) {
-  const int64_t v0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (v0 >= n_per) return;
-  const Vec8<T> in = *reinterpret_cast<const Vec8<T>*>(x + v0);
-  uint4 xs;
-  {
+  // one thread = one pixel and 64 of its channels (eight Philox blocks per sample -> ONE 8-byte store of keep bits; a
+  // warp writes 256 contiguous bytes)
+  const int groups = C >> 6;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pix * groups) return;
+  const int64_t pix = t / groups;                   // (b * H + h) * W + w
+  const int c0 = (int)(t - pix * groups) << 6;
+  const int64_t v0 = pix * C + c0;
+  uint4 xs[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const Vec8<T> in = *reinterpret_cast<const Vec8<T>*>(x + v0 + 8 * o);
     Vec8<T> sc;
 #pragma unroll
     for (int j = 0; j < 8; ++j) sc.v[j] = from_f32<T>(to_f32<T>(in.v[j]) * dp.scale);
-    xs = *reinterpret_cast<const uint4*>(&sc);
+    xs[o] = *reinterpret_cast<const uint4*>(&sc);
+    *reinterpret_cast<uint4*>(x_scaled + v0 + 8 * o) = xs[o];
   }
-  *reinterpret_cast<uint4*>(x_scaled + v0) = xs;
-  const int c0 = (int)(v0 % C);
-  const int64_t pix = v0 / C;                       // (b * H + h) * W + w
   const int w = (int)(pix % W), h = (int)((pix / W) % H);
   const int64_t b = pix / ((int64_t)W * H);
   const bool ee = plane != nullptr && ((h | w) & 1) == 0;
   const int64_t plane_off = ((b * (H / 2) + h / 2) * (W / 2) + w / 2) * C + c0;
-  const int64_t plane_per = n_per / 4;
+  const int64_t n_per = n_pix * C, plane_per = n_per / 4;
   const uint32_t thr2 = dp.thr | (dp.thr << 16);
-  const uint64_t blk = (uint64_t)(v0 >> 3);
-#pragma unroll 2
+  const uint64_t blk0 = (uint64_t)(v0 >> 3);
   for (int s = 0; s < S_local; ++s) {
-    const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk);
-    bits[((int64_t)s * n_per + v0) >> 3] = dp.scale == 0.f ? (uint8_t)0 : (uint8_t)keep_bits8(r, dp.thr);
-    if (ee) {
-      uint4 o;
-      o.x = xs.x & __vcmpgeu2(r.x, thr2);
-      o.y = xs.y & __vcmpgeu2(r.y, thr2);
-      o.z = xs.z & __vcmpgeu2(r.z, thr2);
-      o.w = xs.w & __vcmpgeu2(r.w, thr2);
-      if (dp.scale == 0.f) o = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(plane + (int64_t)s * plane_per + plane_off) = o;
+    unsigned long long word = 0ull;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk0 + o);
+      // per-halfword compare masks (0xFFFF / 0) -> eight keep bits: take one bit of every halfword
+      const uint32_t mx = __vcmpgeu2(r.x, thr2), my = __vcmpgeu2(r.y, thr2), mz = __vcmpgeu2(r.z, thr2), mw = __vcmpgeu2(r.w, thr2);
+      const uint32_t k8 = (mx & 1u) | ((mx >> 15) & 2u) | ((my & 1u) << 2) | ((my >> 13) & 8u) | ((mz & 1u) << 4) |
+                          ((mz >> 11) & 32u) | ((mw & 1u) << 6) | ((mw >> 9) & 128u);
+      word |= (unsigned long long)(dp.scale == 0.f ? 0u : k8) << (8 * o);
+      if (ee) {
+        uint4 ov;
+        ov.x = xs[o].x & mx;
+        ov.y = xs[o].y & my;
+        ov.z = xs[o].z & mz;
+        ov.w = xs[o].w & mw;
+        if (dp.scale == 0.f) ov = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(plane + (int64_t)s * plane_per + plane_off + 8 * o) = ov;
+      }
     }
+    *reinterpret_cast<unsigned long long*>(bits + (((int64_t)s * n_per + v0) >> 3)) = word;
   }
 }
 
@@ -635,18 +648,18 @@ int bnn_boundary_bits(const void* x, void* x_scaled, void* bits, void* plane_ee,
   BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16, "bnn_boundary_bits: 16-bit activations only");
   BNN_REQUIRE(drop->kind == BNN_DROP_ELEMENT && drop->p >= 0.f && drop->p <= 1.f,
               "bnn_boundary_bits: element-wise dropout with 0 <= p <= 1 (got kind %d, p %g)", drop->kind, drop->p);
-  BNN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && S_local >= 0 && (plane_ee == nullptr || (H % 2 == 0 && W % 2 == 0)),
-              "bnn_boundary_bits: bad geometry");
-  const int64_t n_per = (int64_t)B * H * W * C;
-  if (n_per == 0) return BNN_OK;
+  BNN_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && C % 64 == 0 && S_local >= 0 && (plane_ee == nullptr || (H % 2 == 0 && W % 2 == 0)),
+              "bnn_boundary_bits: bad geometry (C = %d must be a multiple of 64)", C);
+  const int64_t n_pix = (int64_t)B * H * W;
+  if (n_pix == 0) return BNN_OK;
   const DropParams dp = make_drop_params(drop, C);
-  const int64_t threads = n_per / 8;
+  const int64_t threads = n_pix * (C / 64);
   if (dtype == BNN_F16)
-    boundary_bits_kernel<__half><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, (__half*)x_scaled, (uint8_t*)bits, (__half*)plane_ee, n_per, H, W, C, S_local, dp);
+    boundary_bits_kernel<__half><<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, (__half*)x_scaled, (uint8_t*)bits, (__half*)plane_ee, n_pix, H, W, C, S_local, dp);
   else
-    boundary_bits_kernel<__nv_bfloat16><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)x_scaled, (uint8_t*)bits, (__nv_bfloat16*)plane_ee, n_per, H, W, C, S_local, dp);
+    boundary_bits_kernel<__nv_bfloat16><<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)x_scaled, (uint8_t*)bits, (__nv_bfloat16*)plane_ee, n_pix, H, W, C, S_local, dp);
   BNN_LAUNCH_OK();
   return BNN_OK;
 }

@@ -383,6 +383,12 @@ class Engine:
         self.gather = {}
         if self.use_tc and self.gather_mode > 0:
             self._plan_gather()
+        self.boundary = {}
+        # opt-in (BNN_BOUNDARY_FUSION=1): bit-identical, removes the S masked copies (1.07 GB -> 335 MB at C2) - but
+        # measured SLOWER on B200 (C2 7.73 vs 7.02 ms/step): the in-shared-memory masking hop sits on the sibling launch's
+        # critical path (1.66 vs 0.59 ms), see DESIGN.md
+        if self.use_tc and fuse and fuse_graph and os.environ.get("BNN_BOUNDARY_FUSION", "0") == "1":
+            self._plan_boundary()
 
     # ---- plan-time weight packing -----------------------------------------------------------
     def _tc_eligible(self, op):
@@ -452,6 +458,33 @@ class Engine:
                     op.d_b_pad[:C_] = op.d_b
             if op.site is not None and op.site.kind == "mask":
                 op.d_masks = op.site.module.masks.detach().to(dev, torch.float32).contiguous()
+
+    # ---- prefix boundary without the S masked copies -------------------------------------------
+    def _plan_boundary(self):
+        """An element-wise MC-dropout site on the deterministic prefix whose output is read ONLY by an even number of
+        128-channel stride-2 sibling convolutions (one grouped launch) and by fused 1x1 stride-2 projection shortcuts:
+        the site launch writes keep BITS (+ the even/even plane the shortcuts read) instead of S masked copies, and the
+        sibling launch ANDs the bits into its tiles in shared memory (north star items 1 and 3: the prefix is computed
+        once AND never replicated; bnn_boundary_bits / bnn_conv2d_tc_grouped_masked / bnn_conv2d_tc_shortcut_plane)."""
+        g = self.graph
+        for op in g.ops:
+            if op.kind != "site" or op.site.kind != "mc" or op.src.stoch or op.site.nchw_flat or op.site.p >= 1.0:
+                continue
+            t = op.dst
+            if t.C % 64 != 0 or t.H % 2 or t.W % 2 or 128 % (t.W // 2) != 0:
+                continue
+            groups = [o for o in g.ops if o.kind == "convg" and o.src is t]
+            scs = [o for o in g.ops if o.kind == "conv" and getattr(o, "sc", None) is not None and o.sc["src"] is t]
+            others = [o for o in g.ops if (o.src is t or o.res is t) and o not in groups]
+            if len(groups) != 1 or others or any(not o.use_tc or o.dst.H * 2 != t.H for o in scs):
+                continue
+            cg = groups[0]
+            if len(cg.dsts) % 2 or any(d.C != 128 for d in cg.dsts) or cg.center_mask != 0:
+                continue
+            self.boundary[t.id] = {"site": op, "convg": cg, "shortcuts": scs}
+            cg.boundary = op
+            for o in scs:
+                o.boundary = op
 
     # ---- Masksembles gathered layout ----------------------------------------------------------
     def _plan_gather(self):
@@ -546,8 +579,16 @@ class Engine:
             live.update(t.id for t in (op.src, op.dst, op.res) + tuple(getattr(op, "dsts", ())) if t is not None)
             if getattr(op, "sc", None) is not None:
                 live.add(op.sc["src"].id)
+        bnd = {}
+        for tid, info in self.boundary.items():
+            t = g.tensors[tid]
+            bnd[tid] = {
+                "x_scaled": torch.empty((B, t.H, t.W, t.C), dtype=self.tdtype, device=dev),
+                "bits": torch.empty((chunk * B * t.H * t.W * t.C // 8,), dtype=torch.uint8, device=dev),
+                "plane": (torch.empty((chunk * B, t.H // 2, t.W // 2, t.C), dtype=self.tdtype, device=dev)
+                          if info["shortcuts"] else None)}
         for t in g.tensors:
-            if t.id not in live or gmode.get(t.id) == "weights":
+            if t.id not in live or gmode.get(t.id) == "weights" or t.id in self.boundary:
                 continue                      # e.g. the un-masked output of a conv with a fused site
             n = (chunk if t.stoch else 1) * B
             if t is g.input and self.in_pad:
@@ -574,6 +615,7 @@ class Engine:
             "logits": (torch.empty((E, S_local, B, C), dtype=torch.float32, device=dev) if want_logits else None),
             "acts": acts,
             "head_ws": head_ws,
+            "boundary": bnd,
             "compact": compact,
             "gmode": gmode,
             "chunk": chunk,
@@ -726,6 +768,15 @@ class Engine:
                 ys = (ctypes.c_void_p * len(op.dsts))(*[acts[d.id].data_ptr() for d in op.dsts])
                 out_px = n_img * d0.H * d0.W
                 flops = sum(2 * out_px * m.dst.C * m.src.C * m.ksize[0] * m.ksize[1] for m in op.members)
+                if getattr(op, "boundary", None) is not None:
+                    bb = st["boundary"][op.src.id]
+                    nbytes = (B * op.src.H * op.src.W * op.src.C + out_px * d0.C * len(op.dsts)) * es + bb["bits"].numel() \
+                        + op.d_w.numel() * op.d_w.element_size()
+                    self._launch("conv_tc", op.name + " [keep bits applied in shared memory]", flops, nbytes,
+                                 lambda: lib.bnn_conv2d_tc_grouped_masked(
+                                     _ptr(bb["x_scaled"]), _ptr(bb["bits"]), _ptr(op.d_w), _ptr(op.d_b), ys, len(op.dsts),
+                                     op.relu_mask, self.dcode, n_img, B, op.src.H, op.src.W, op.src.C, d0.C, stream))
+                    continue
                 nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * d0.C * len(op.dsts)) * es \
                     + op.d_w.numel() * op.d_w.element_size()
                 self._launch("conv_tc", op.name, flops, nbytes, lambda: lib.bnn_conv2d_tc_grouped(
@@ -754,7 +805,15 @@ class Engine:
                     nbytes = (n_img * op.src.H * op.src.W * op.src.C + n_img * op.dst.C + (out_px * op.dst.C if res is not None else 0)) * es \
                         + op.d_w.numel() * op.d_w.element_size()
                 cin = self.in_pad if (op.src is g.input and self.in_pad and op.use_tc) else op.src.C
-                if sc is not None:
+                if sc is not None and getattr(op, "boundary", None) is not None:
+                    flops += 2 * out_px * op.dst.C * sc["src"].C
+                    nbytes += out_px * sc["src"].C * es
+                    plane = st["boundary"][sc["src"].id]["plane"]
+                    call = lambda: lib.bnn_conv2d_tc_shortcut_plane(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), ctypes.byref(dd),
+                        _ptr(plane), sc["src"].C, stream)
+                elif sc is not None:
                     flops += 2 * out_px * op.dst.C * sc["src"].C
                     nbytes += n_img * sc["src"].H * sc["src"].W * sc["src"].C * es
                     call = lambda: lib.bnn_conv2d_tc_shortcut(
@@ -786,6 +845,14 @@ class Engine:
                 dd = self._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, mask_offset,
                                      self.gather[op.dst.id] if op.dst.id in compact else None)
                 per_image = op.src.H * op.src.W * op.src.C
+                if op.dst.id in self.boundary:
+                    bb = st["boundary"][op.dst.id]
+                    nbytes = 2 * B * per_image * es + S_local * B * per_image // 8 + \
+                        (S_local * B * per_image // 4 * es if bb["plane"] is not None else 0)
+                    self._launch("dropout", op.name + " [keep bits + shortcut plane]", 0, nbytes, lambda: lib.bnn_boundary_bits(
+                        _ptr(acts[op.src.id]), _ptr(bb["x_scaled"]), _ptr(bb["bits"]), _ptr(bb["plane"]), self.dcode, B,
+                        op.src.H, op.src.W, op.src.C, S_local, ctypes.byref(dd), stream))
+                    continue
                 nbytes = B * per_image * es * ((S_local if op.src.stoch else 1) + S_local)
                 if op.dst.id in compact:
                     nbytes = B * per_image * es * (S_local if op.src.stoch else 1) \

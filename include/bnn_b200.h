@@ -175,6 +175,25 @@ int bnn_conv2d_tc_gathered(const void* x, const void* w, const float* bias, void
 int bnn_conv2d_tc_i8(const void* x, const void* w, const float* bias_q, void* y, int N, int H, int W, int Cin, int Cout,
                      int ksize, int stride, float q_mult, const bnn_drop_desc* drop, void* stream);
 
+/* ---- prefix boundary without the S masked copies (element-wise MC dropout in front of tensor-core convolutions) ----
+ * bnn_boundary_bits replaces bnn_dropout at a site whose input is the deterministic prefix (computed once per image):
+ *   x_scaled [B][H][W][C]            = x * 1/(1-p), rounded to the 16-bit storage type (ONE copy)
+ *   bits     [S_local][B][H][W][C/8] = the keep bits of every sample (bit i of byte j <=> channel 8j + i kept)
+ *   plane_ee [S_local][B][H/2][W/2][C] (may be NULL) = the masked even/even pixels, all a fused 1x1 stride-2 projection
+ *                                      shortcut reads (bnn_conv2d_tc_shortcut_plane)
+ * - 67 + 268 MB instead of 1.07 GB at BASELINE config 2.  Same Philox blocks and rounding as bnn_dropout, so
+ * bnn_conv2d_tc_grouped_masked (the stride-2 sibling groups behind the site: x_scaled is read through TMA and the keep
+ * bits are ANDed into the tile in shared memory by helper warps before the MMAs; N = S_local * batch output images) and
+ * bnn_conv2d_tc_shortcut_plane reproduce bnn_conv2d_tc_grouped / bnn_conv2d_tc_shortcut on the masked copies bit for bit. */
+int bnn_boundary_bits(const void* x, void* x_scaled, void* bits, void* plane_ee, int dtype, int B, int H, int W, int C,
+                      int S_local, const bnn_drop_desc* drop, void* stream);
+int bnn_conv2d_tc_grouped_masked(const void* x_scaled, const void* mask_bits, const void* w, const float* bias, void* const* y,
+                                 int n_groups, uint32_t relu_mask, int dtype, int N, int batch, int H, int W, int Cin,
+                                 int cout_per_group, void* stream);
+int bnn_conv2d_tc_shortcut_plane(const void* x, const void* w, const float* bias, const void* res, void* y, int dtype, int N,
+                                 int H, int W, int Cin, int Cout, int ksize, int stride, int relu, const bnn_drop_desc* drop,
+                                 const void* x2_plane, int Cin2, void* stream);
+
 /* ---- the rest of the 8-bit path (unsigned 8-bit NHWC activations; real value = q * step) ----
  * bnn_dropout_q8: the stochastic layer that produces / masks 8-bit tensors:
  *     y_q[s][i] = clip(rint(x[..][i] * in_to_out * factor_s(i)), 0, 255)
