@@ -413,6 +413,25 @@ class Engine:
             elif op.kind == "conv":
                 w = op.weight.permute(0, 2, 3, 1).contiguous()       # [Cout][KH][KW][Cin]
                 op.use_tc = self._tc_eligible(op)
+                # A 3x3 pad-1 convolution on a 2x2 map (the last VGG block at 32x32 inputs) is a DENSE map from the 4
+                # input pixels to the 4 output pixels: every (output p, input q) pair is linked by exactly one tap.  In
+                # NHWC memory the image is one row of 4*Cin values and the output one row of 4*Cout, so the layer runs
+                # as ONE 1x1 GEMM with K = 4*Cin and 4*Cout outputs - 16 Cin x Cout blocks instead of the 36 the nine
+                # taps would issue (20 of them multiplying zero padding): 2.25x fewer MMAs.  Element-wise dropout in the
+                # epilogue sees the same linear element indices; channel-wise sites keep the tap form.
+                op.fc22 = (op.use_tc and op.ksize == (3, 3) and op.pad == 1 and op.stride == 1 and op.src.H == 2 and
+                           op.src.W == 2 and getattr(op, "sc", None) is None and getattr(op, "pool_from", None) is None and
+                           (op.site is None or op.site.kind == "mc") and os.environ.get("BNN_SMALLMAP_FC", "1") != "0")
+                if op.fc22:
+                    co, ci = op.weight.shape[:2]
+                    wf = torch.zeros((4 * co, 4 * ci), dtype=torch.float32)
+                    for p_ in range(4):
+                        for q_ in range(4):
+                            kh_, kw_ = q_ // 2 - p_ // 2 + 1, q_ % 2 - p_ % 2 + 1
+                            wf[p_ * co:(p_ + 1) * co, q_ * ci:(q_ + 1) * ci] = op.weight[:, :, kh_, kw_]
+                    op.d_w = wf.contiguous().to(dev, self.tdtype)
+                    op.d_b = op.bias.repeat(4).to(dev, torch.float32)
+                    continue
                 if op.use_tc and op.src is self.graph.input and self.in_pad:
                     w = torch.nn.functional.pad(w, (0, self.in_pad - w.shape[3]))   # zero weights on the padding channels
                 if getattr(op, "sc", None) is not None:              # K-concatenated: 3x3 weights | shortcut weights
@@ -824,6 +843,10 @@ class Engine:
                     call = lambda: lib.bnn_conv2d_tc_pooled(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
                         op.src.H, op.src.W, op.src.C, op.dst.C, kh, op.stride, int(op.relu), stream)
+                elif getattr(op, "fc22", False):
+                    call = lambda: lib.bnn_conv2d_tc(
+                        _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
+                        1, 1, 4 * op.src.C, 4 * op.dst.C, 1, 1, int(op.relu), ctypes.byref(dd), stream)
                 elif op.use_tc:
                     call = lambda: lib.bnn_conv2d_tc(
                         _ptr(src), _ptr(op.d_w), _ptr(op.d_b), _ptr(res), _ptr(acts[op.dst.id]), self.dcode, n_img,
@@ -837,8 +860,9 @@ class Engine:
                 # eight taps are zero padding and must not count as executed work
                 tap_skip = (op.use_tc and kh == 3 and op.src.H == 1 and op.src.W == 1 and op.stride == 1 and
                             os.environ.get("BNN_TC_NO_TAP_SKIP") is None)
-                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name, flops, nbytes, call,
-                             flops_exec=flops / 9 if tap_skip else None)
+                fexec = flops / 9 if tap_skip else (flops * 16 / 36 if getattr(op, "fc22", False) else None)
+                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name + (" [2x2 map as one GEMM]" if getattr(
+                    op, "fc22", False) else ""), flops, nbytes, call, flops_exec=fexec)
             elif op.kind == "site":
                 if S_local == 0:
                     continue

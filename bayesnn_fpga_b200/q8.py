@@ -148,10 +148,22 @@ class Q8Plan:
                 w_q, w_step = quantized_bits(op.weight, 8, wi)
                 b_q, b_step = quantized_bits(op.bias, 8, bi)
                 out_step = self.step[op.dst.id]
+                bias_q = (b_q.double() * b_step / out_step).float()
+                # 3x3 convolution on a 2x2 map == one dense GEMM over the image's 4*Cin values (see Engine: fc22)
+                fc22 = (kh == 3 and op.stride == 1 and op.src.H == 2 and op.src.W == 2 and
+                        (op.site is None or op.site.kind == "mc") and (4 * op.src.C) % 128 == 0)
+                if fc22:
+                    co, ci = w_q.shape[:2]
+                    wf = torch.zeros((4 * co, 4 * ci), dtype=torch.int8)
+                    for p_ in range(4):
+                        for q_ in range(4):
+                            kh_, kw_ = q_ // 2 - p_ // 2 + 1, q_ % 2 - p_ % 2 + 1
+                            wf[p_ * co:(p_ + 1) * co, q_ * ci:(q_ + 1) * ci] = w_q[:, :, kh_, kw_].to(torch.int8)
+                    d_w, bias_q = wf.contiguous().to(dev), bias_q.repeat(4)
+                else:
+                    d_w = w_q.to(torch.int8).permute(0, 2, 3, 1).contiguous().to(dev)
                 self.layers[i] = dict(
-                    w_q=w_q, w_step=w_step, b_q=b_q, b_step=b_step,
-                    d_w=w_q.to(torch.int8).permute(0, 2, 3, 1).contiguous().to(dev),
-                    d_bias_q=(b_q.double() * b_step / out_step).float().to(dev),
+                    w_q=w_q, w_step=w_step, b_q=b_q, b_step=b_step, fc22=fc22, d_w=d_w, d_bias_q=bias_q.to(dev),
                     q_mult=float(w_step * self.step[op.src.id] / out_step))
             elif op.kind not in ("site", "maxpool"):
                 raise NotImplementedError("8-bit plan: op %s (%s) in the stochastic suffix" % (op.name, op.kind))
@@ -196,9 +208,10 @@ class Q8Plan:
                 elif op.kind == "conv":
                     L = self.layers[i]
                     dd = eng._drop_desc(op.site, getattr(op, "d_masks", None), B, sample0, seed, None)
+                    geo = (1, 1, 4 * op.src.C, 4 * op.dst.C, 1, 1) if L["fc22"] else \
+                        (op.src.H, op.src.W, op.src.C, op.dst.C, op.ksize[0], op.stride)
                     _lib.check(lib.bnn_conv2d_tc_i8(_ptr(q[op.src.id]), _ptr(L["d_w"]), _ptr(L["d_bias_q"]), _ptr(q[op.dst.id]),
-                                                    S * B, op.src.H, op.src.W, op.src.C, op.dst.C, op.ksize[0], op.stride,
-                                                    L["q_mult"], ctypes.byref(dd), stream))
+                                                    S * B, *geo, L["q_mult"], ctypes.byref(dd), stream))
                 elif op.kind == "maxpool":
                     _lib.check(lib.bnn_maxpool2d(_ptr(q[op.src.id]), _ptr(q[op.dst.id]), _lib.I8, S * B, op.src.H, op.src.W,
                                                  op.src.C, op.pool_k, stream))

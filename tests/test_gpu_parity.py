@@ -306,3 +306,30 @@ def test_full_analysis_over_a_loader(tmp_path, monkeypatch):
     with open(tmp_path / "validation_predictions_t.npy", "rb") as f:
         p, ep, lab = np.load(f), np.load(f), np.load(f)
     assert p.shape == (2, N, 10) and np.allclose(ep[1], p.mean(0)) and (lab.argmax(1) == y.numpy()).all()
+
+
+def test_3x3_convolutions_on_2x2_maps_run_as_one_gemm(monkeypatch):
+    """The last VGG block (3x3 pad-1 convolutions on 2x2 maps, fused element dropout included): a dense 4-pixel ->
+    4-pixel map, run as ONE 1x1 GEMM over K = 4*Cin with 4*Cout outputs (16 Cin x Cout blocks instead of the nine taps'
+    36).  Same values as the tap form up to fp32 summation order, same masks, and still inside the fixture tolerance."""
+    tag = "vgg19_mcd_last3"
+    model, sd, gold = build_seeded(tag)
+    model.cuda()
+    x = torch.from_numpy(gold["x"])
+    S, seed = int(gold["S"]), int(gold["seed"])
+    monkeypatch.setenv("BNN_SMALLMAP_FC", "0")
+    e0 = model.bnn_engine("fp16", rebuild=True)
+    assert not any(getattr(o, "fc22", False) for o in e0.graph.ops)
+    ref = e0.run(x, S, seed=seed, want_logits=True, use_graph=False).all_logits.clone()
+    monkeypatch.setenv("BNN_SMALLMAP_FC", "1")
+    e1 = model.bnn_engine("fp16", rebuild=True)
+    assert sum(getattr(o, "fc22", False) for o in e1.graph.ops) == 4          # blocks.4: four convolutions on 2x2 maps
+    r = e1.run(x, S, seed=seed, want_logits=True, use_graph=False)
+    scale = max(1.0, float(ref.abs().max()))
+    d = float((r.all_logits - ref).abs().max())
+    e = _errs(r, gold)
+    prof = e1.profile_step(x.cuda(), S)
+    fc = [o for o in prof if "2x2 map as one GEMM" in o["name"]]
+    report(test="conv_2x2_as_gemm", vs_tap_form=d, scale=scale, **e)
+    assert len(fc) == 4 and all(abs(o["flops_exec"] / o["flops"] - 16 / 36) < 1e-9 for o in fc)
+    assert d <= 1e-3 * scale and e["mean_probs"] <= 1e-3 and e["mean_logits"] <= 1e-3 * scale

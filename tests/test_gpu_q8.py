@@ -165,8 +165,8 @@ def test_q8_suffix_plan_vgg_last3_bit_exact_and_close_to_fp16():
             y = np.clip(np.rint(((xin * scale).astype(np.float32) * keep).astype(np.float32)), 0, 255).astype(np.uint8)
         elif op.kind == "conv":
             L = plan.layers[i]
-            y = oq8.qconv_relu(vals[op.src.id], L["w_q"].numpy(), L["d_bias_q"].cpu().numpy(), np.float32(L["q_mult"]),
-                               op.stride, op.pad, keep_scale=keep)
+            y = oq8.qconv_relu(vals[op.src.id], L["w_q"].numpy(), L["d_bias_q"].cpu().numpy()[:op.dst.C], np.float32(L["q_mult"]),
+                               op.stride, op.pad, keep_scale=keep)      # (integer sums: the 2x2-map GEMM form is bit-identical)
         elif op.kind == "maxpool":
             y = _np_maxpool(vals[op.src.id], op.pool_k)
         elif op.kind == "head":
