@@ -96,6 +96,14 @@ struct Params {
   // ([N][H][W][Cin / 8] bytes, written by bnn_boundary_bits); helper warps AND the bits into the tile in shared memory
   const uint8_t* mask_bits;
   int in_h, in_w;  // input map size (mask-bit addressing)
+  // PM (position-major tiling, small maps): a row-tile is ONE output position (oh, ow) of 128 consecutive images, so a
+  // tap is in bounds for all 128 rows or for none - the taps that would multiply only zero padding are not issued at all
+  // (4x4 maps: 6.25 instead of 9 k-blocks per tile on average, 8x8: 7.6).  Row-tile order (pm_decode): tiles 2q and 2q+1
+  // share a position (a CTA pair runs the same tap set); q walks the OHW positions of one 256-image block before moving
+  // to the next block, so the tiles in flight consume whole images and the input stays in L2 between its 9 uses
+  // (position-outermost order re-read the input from DRAM once per tap row).  pm_nb2 = image blocks rounded up to even.
+  int pm_nb2;      // > 0: position-major tiling
+  int n_img;       // images (M / OHW)
   int head_c;      // > 0: channel blocks of x_hi
   int out_f32;     // epilogue stores float32 (non-swapped kernels only)
   float q_mult;    // 8-bit operands: output LSBs per accumulator LSB = w_scale * in_scale / out_scale (a power of two
@@ -407,6 +415,13 @@ constexpr int VH_RING_BYTES = 220 * 1024;         // both rings together; the sp
 constexpr int VH_MAX_SLOTS = 12;
 __host__ __device__ constexpr int smem_bytes_vh() { return VH_RING_BYTES + 1024 + 256; }
 
+// position-major row-tile -> (output position, first image); see Params::pm_nb2
+__device__ __forceinline__ void pm_decode(int m_tile, int ohw, int& pos, int& img0) {
+  const int q = m_tile >> 1, bp = q / ohw;
+  pos = q - bp * ohw;
+  img0 = (2 * bp + (m_tile & 1)) * BM;
+}
+
 template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T, bool VH = false, bool MASKED = false>
 __global__ void __launch_bounds__(num_threads(EW) + (VH ? 32 : 0) + (MASKED ? 128 : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -666,6 +681,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m_tile = (PAIRED && !SCG2) ? 2 * m_unit + (int)cta_rank : m_unit;
         constexpr int NLOAD = SCG2 ? 1 : MT;          // 128-pixel tiles THIS CTA loads per k-block
         int img0[MT], oh0[MT];
+        int pm_ow = 0;                                // PM: output column of this tile's position (0 otherwise)
 #pragma unroll
         for (int mt = 0; mt < NLOAD; ++mt) {
           int m0 = SCG2 ? (m_unit * MT + (int)cta_rank) * BM : (m_tile * MT + mt) * BM;
@@ -673,6 +689,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           img0[mt] = m0 / p.OHW;
           oh0[mt] = (m0 - img0[mt] * p.OHW) / p.OW;
           if (p.a_img_mod > 0) img0[mt] %= p.a_img_mod;
+        }
+        if (p.pm_nb2 > 0) {                           // (MT == 1) one position, 128 consecutive images
+          int pos;
+          pm_decode(m_tile, p.OHW, pos, img0[0]);     // image blocks past the end: the TMA unit zero-fills
+          oh0[0] = pos / p.OW;
+          pm_ow = pos - oh0[0] * p.OW;
         }
         // SCG2: n_tile counts group PAIRS; this CTA's output group (and weight rows) is 2 * n_tile + rank
         const int grp_w = SCG2 ? 2 * n_tile + (int)cta_rank : n_tile;
@@ -691,6 +713,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int rh = kh - p.pad, rw = kw - p.pad;                 // -1, 0, +1  (0 only for 1x1)
           const int hp = rh & 1, dh = (rh - hp) >> 1;                 // -1 -> (1, -1); 0 -> (0, 0); 1 -> (1, 0)
           const int wp = rw & 1, dw = (rw - wp) >> 1;
+          if (p.pm_nb2 > 0) {                                         // the tap reads zero padding for EVERY row: skip
+            const int ih = p.stride * oh0[0] + rh, iw = p.stride * pm_ow + rw;
+            if (ih < 0 || ih >= p.in_h || iw < 0 || iw >= p.in_w) continue;
+          }
           for (int cb = 0; cb < p.cblocks; ++cb) {
             const int a_cb = (p.head_c > 0 && cb >= p.head_c) ? cb - p.head_c : cb;     // exit-head GEMM: x_hi twice
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -709,9 +735,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < NLOAD; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d_2sm(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw + pm_ow, oh0[mt] + rh, img0[mt]);
                 else
-                  tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh,
+                  tma_load_5d_2sm(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw + pm_ow, hp, oh0[mt] + dh,
                                   img0[mt]);
               }
               }
@@ -727,9 +753,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   for (int mt = 0; mt < MT; ++mt) {
                     uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                     if (p.stride == 1)
-                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                      tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw + pm_ow, oh0[mt] + rh, img0[mt]);
                     else
-                      tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
+                      tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw + pm_ow, hp, oh0[mt] + dh, img0[mt]);
                   }
                 }
                 if (!(p.exp_flags & 2))
@@ -745,9 +771,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int mt = 0; mt < MT; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
                 if (p.stride == 1)
-                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw, oh0[mt] + rh, img0[mt]);
+                  tma_load_4d(a_dst, &tmap_a, &full_bar[stage], a_cb * BKE, rw + pm_ow, oh0[mt] + rh, img0[mt]);
                 else
-                  tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[mt] + dh, img0[mt]);
+                  tma_load_5d(a_dst, &tmap_a, &full_bar[stage], wp * p.Cin + cb * BKE, dw + pm_ow, hp, oh0[mt] + dh, img0[mt]);
               }
               if constexpr (MC2)
                 tma_load_2d_mc(smem_b + stage * B_TILE + cta_rank * (B_TILE / 2), &tmap_b, &full_bar[stage],
@@ -769,10 +795,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               if (p.sc_dense)
-                tma_load_4d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, oh0[mt],
+                tma_load_4d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, pm_ow, oh0[mt],
                                 img0[mt]);
               else
-                tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0,
+                tma_load_5d_2sm(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, pm_ow, 0,
                                 oh0[mt], img0[mt]);
             }
             tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BKE,
@@ -782,10 +808,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               if (p.sc_dense)
-                tma_load_4d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, oh0[mt],
+                tma_load_4d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, pm_ow, oh0[mt],
                             img0[mt]);
               else
-                tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, 0, 0, oh0[mt],
+                tma_load_5d(smem_a + stage * A_STAGE + mt * A_TILE_BYTES, &tmap_a2, &full_bar[stage], cb * BKE, pm_ow, 0, oh0[mt],
                             img0[mt]);
             }
             if constexpr (MC2)
@@ -813,7 +839,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t acc_phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int n_tile_mma = (tile % p.n_tiles_n) * (SCG2 ? 2 : 1);      // SCG2: first group of the pair
-        const int tile_kb = (((p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u) ? p.cblocks : num_kb) + p.cblocks2;
+        const bool center_mma = (p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u;
+        int tile_kb = (center_mma ? p.cblocks : num_kb) + p.cblocks2;
+        if (p.pm_nb2 > 0 && !center_mma && p.taps == 9) {
+          // position-major: only the taps that are in bounds at this tile's position were loaded
+          const int m_tile_mma = PAIRED ? 2 * (tile / p.n_tiles_n) : tile / p.n_tiles_n;
+          int pos, n0_unused;
+          pm_decode(m_tile_mma, p.OHW, pos, n0_unused);
+          const int oh = pos / p.OW, ow = pos - oh * p.OW;
+          int vh = 0, vw = 0;
+          for (int k = 0; k < 3; ++k) {
+            const int ih = p.stride * oh + k - p.pad, iw = p.stride * ow + k - p.pad;
+            vh += (ih >= 0 && ih < p.in_h) ? 1 : 0;
+            vw += (iw >= 0 && iw < p.in_w) ? 1 : 0;
+          }
+          tile_kb = vh * vw * p.cblocks + p.cblocks2;
+        }
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -1043,7 +1084,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (res != nullptr) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+          int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+          if (p.pm_nb2 > 0) {                         // position-major: row r of the tile is image n0 + r at one position
+            int pos, n;
+            pm_decode(m_tile, p.OHW, pos, n);
+            n += q * 32 + lane;
+            m = n < p.n_img ? n * p.OHW + pos : p.M;
+          }
           if (m < p.M) {
             const uint4* src = reinterpret_cast<const uint4*>(res + (size_t)m * p.cout_g + cgrp);
 #pragma unroll
@@ -1058,7 +1105,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+        int m = (m_tile * MT + mt) * BM + q * 32 + lane;
+        if (p.pm_nb2 > 0) {
+          int pos, n;
+          pm_decode(m_tile, p.OHW, pos, n);
+          n += q * 32 + lane;
+          m = n < p.n_img ? n * p.OHW + pos : p.M;
+        }
         const bool valid = m < p.M && !dead;
         // stochastic-site coordinates of this output pixel
         int s_local = 0;
@@ -1286,7 +1339,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int m_tiles = (p.M + MT * BM - 1) / (MT * BM);
+  const int m_tiles = p.pm_nb2 > 0 ? p.OHW * p.pm_nb2 : (p.M + MT * BM - 1) / (MT * BM);
   if (MC2) {
     // pair-tiles: two adjacent row-tiles x one channel tile, or (sibling pair) one row-tile x two output groups
     p.num_tiles = (SWAP && PAIR == 2) ? m_tiles * p.n_tiles_n : ((m_tiles + 1) / 2) * p.n_tiles_n;
@@ -1405,9 +1458,29 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   BNN_REQUIRE((int64_t)N * OH * OW < (int64_t)1 << 31, "%s: M overflows int32", who);
 
   // tile geometry: 128 consecutive output pixels = tn images x th rows x OW columns
-  const int tw = OW;
-  const int th = OH < tc::BM / tw ? OH : tc::BM / tw;
-  const int tn = tc::BM / (tw * th);
+  int tw = OW;
+  int th = OH < tc::BM / tw ? OH : tc::BM / tw;
+  int tn = tc::BM / (tw * th);
+  // ... or, position-major (small maps, 256-channel tiles): ONE output position of 128 consecutive images per row-tile,
+  // so that taps which read only zero padding are skipped for the whole tile (conv_tc_kernel, Params::pm_nb2).
+  // BNN_TC_NO_PM=1 keeps pixel-major tiles; BNN_TC_PM_MIN_IMAGES lowers the batch threshold (unit tests).
+  const int pm_min = getenv("BNN_TC_PM_MIN_IMAGES") ? atoi(getenv("BNN_TC_PM_MIN_IMAGES")) : 1024;
+  int pm_rows = 0, pm_cols = 0;      // in-bounds (position, tap) pairs per axis
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 0; o < OH; ++o) pm_rows += (stride * o + k - 1 >= 0 && stride * o + k - 1 < H) ? 1 : 0;
+    for (int o = 0; o < OW; ++o) pm_cols += (stride * o + k - 1 >= 0 && stride * o + k - 1 < W) ? 1 : 0;
+  }
+  // worth it when at least 10 % of the taps go away (8x8 stride 1: 16 %, 4x4: 31 %; 16x16 -> 8x8 stride 2 saves 8 % of the
+  // MMAs but its 128-image gathers cost more than that: measured 0.515 vs 0.481 ms, profiles/README.md)
+  const bool pm_pays = 10 * pm_rows * pm_cols <= 9 * (9 * OH * OW);
+  const bool pm = ksize == 3 && pm_pays && OH * OW <= 64 && OH * OW >= 4 && cout_g % 256 == 0 && gsel == nullptr && !pool && hg == nullptr &&
+                  msk == nullptr && !(drop && drop->kind == BNN_DROP_MASKSEMBLES && drop->compact_pos != nullptr) &&
+                  !(sc && sc->dense) && N >= pm_min && getenv("BNN_TC_NO_PM") == nullptr;
+  if (pm) {
+    tw = 1;
+    th = 1;
+    tn = tc::BM;
+  }
 
   CUtensorMap ta, tb, ta2;
   const cuuint64_t eb = i8 ? 1 : 2;
@@ -1496,6 +1569,10 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   p.Cin = Cin;
   p.last_ksteps = (Cin - (p.cblocks - 1) * bke) / (i8 ? 2 * tc::UMMA_K : tc::UMMA_K);
   p.q_mult = q_mult;
+  p.in_h = H;
+  p.in_w = W;
+  p.n_img = N;
+  p.pm_nb2 = pm ? (((N + tc::BM - 1) / tc::BM + 1) & ~1) : 0;
   if (hg) {                                   // exit-head GEMM: K runs over the weight blocks, A blocks wrap (see Params)
     p.cblocks = hg->kblocks;
     p.last_ksteps = tc::BK / tc::UMMA_K;

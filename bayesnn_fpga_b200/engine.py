@@ -327,6 +327,20 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def _pm_tap_fraction(n_img, H, W, OH, OW, stride, cout_g, ksize=3):
+    """Executed / algorithmic taps of a 3x3 convolution under position-major tiling (conv_tc.cu, Params::pm_nb2): with one
+    output position per row-tile, taps whose input pixel is zero padding are not issued.  Mirrors the host-side condition
+    in conv_tc_impl; 1.0 when the pixel-major kernel runs."""
+    pm_min = int(os.environ.get("BNN_TC_PM_MIN_IMAGES", "1024"))
+    if not (ksize == 3 and 4 <= OH * OW <= 64 and cout_g % 256 == 0 and n_img >= pm_min and
+            os.environ.get("BNN_TC_NO_PM") is None):
+        return 1.0
+    rows = sum(1 for oh in range(OH) for r in range(3) if 0 <= stride * oh + r - 1 < H)
+    cols = sum(1 for ow in range(OW) for r in range(3) if 0 <= stride * ow + r - 1 < W)
+    frac = rows * cols / (9.0 * OH * OW)
+    return frac if frac <= 0.9 else 1.0        # conv_tc_impl: pm_pays
+
+
 class Engine:
     """Executes a :class:`Graph` on the current CUDA device through the C ABI."""
 
@@ -798,9 +812,11 @@ class Engine:
                     continue
                 nbytes = (n_img * op.src.H * op.src.W * op.src.C + out_px * d0.C * len(op.dsts)) * es \
                     + op.d_w.numel() * op.d_w.element_size()
-                self._launch("conv_tc", op.name, flops, nbytes, lambda: lib.bnn_conv2d_tc_grouped(
+                frac = _pm_tap_fraction(n_img, op.src.H, op.src.W, d0.H, d0.W, 2, d0.C)
+                self._launch("conv_tc", op.name + (" [position-major]" if frac < 1 else ""), flops, nbytes,
+                             lambda: lib.bnn_conv2d_tc_grouped(
                     _ptr(acts[op.src.id]), _ptr(op.d_w), _ptr(op.d_b), ys, len(op.dsts), op.relu_mask, op.center_mask, self.dcode,
-                    n_img, op.src.H, op.src.W, op.src.C, d0.C, 3, 2, stream))
+                    n_img, op.src.H, op.src.W, op.src.C, d0.C, 3, 2, stream), flops_exec=flops * frac)
             elif op.kind == "conv":
                 n_img = (S_local if op.dst.stoch else 1) * B
                 if n_img == 0:
@@ -861,8 +877,14 @@ class Engine:
                 tap_skip = (op.use_tc and kh == 3 and op.src.H == 1 and op.src.W == 1 and op.stride == 1 and
                             os.environ.get("BNN_TC_NO_TAP_SKIP") is None)
                 fexec = flops / 9 if tap_skip else (flops * 16 / 36 if getattr(op, "fc22", False) else None)
-                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name + (" [2x2 map as one GEMM]" if getattr(
-                    op, "fc22", False) else ""), flops, nbytes, call, flops_exec=fexec)
+                tag = " [2x2 map as one GEMM]" if getattr(op, "fc22", False) else ""
+                if (fexec is None and op.use_tc and not pool_from and op.dst.id not in compact and
+                        getattr(op, "boundary", None) is None):
+                    frac = _pm_tap_fraction(n_img, op.src.H, op.src.W, op.dst.H, op.dst.W, op.stride, op.dst.C, kh)
+                    if frac < 1:        # the fused 1x1 shortcut's k-blocks (sc) are all executed
+                        conv_flops = 2 * out_px * op.dst.C * op.src.C * kh * kw
+                        fexec, tag = flops - conv_flops * (1 - frac), " [position-major]"
+                self._launch("conv_tc" if op.use_tc else "conv_simt", op.name + tag, flops, nbytes, call, flops_exec=fexec)
             elif op.kind == "site":
                 if S_local == 0:
                     continue

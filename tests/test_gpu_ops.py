@@ -791,3 +791,62 @@ def test_conv_tc_vertical_halo_form(lib, N, Cin, res, drop_kind, monkeypatch):
     d_old = (got.double() - ref.double()).abs().max().item()
     report(test="conv_tc_vertical_halo", N=N, Cin=Cin, res=res, drop=drop_kind, err=err, vs_per_tap_kernel=d_old, scale=scale)
     assert err <= 1e-3 * scale and d_old <= 2e-3 * scale and not torch.isnan(got).any()
+
+
+@pytest.mark.parametrize("pair", ["single", "cg2"])
+@pytest.mark.parametrize("shape,drop_kind", [((300, 4, 4, 512, 512, 3, 1, 1, True, True), 0), ((260, 8, 8, 256, 256, 3, 1, 1, True, False), 1),
+                                             ((257, 8, 8, 256, 512, 3, 2, 1, True, False), 0), ((130, 2, 2, 512, 512, 3, 1, 1, True, False), 2),
+                                             ((200, 4, 4, 256, 256, 3, 2, 1, False, False), 0)])
+def test_conv_tc_position_major_tiles_skip_padding_taps(lib, shape, drop_kind, pair, monkeypatch):
+    """Position-major tiling (one output position x 128 images per row-tile): taps that read only zero padding are not
+    issued.  Skipped terms are exact zeros, so the result must be BIT-IDENTICAL to the pixel-major kernel - plain and
+    strided convolutions, residual, fused element / channel dropout, ragged image blocks, single CTA and cta_group::2."""
+    monkeypatch.setenv("BNN_TC_PM_MIN_IMAGES", "1")
+    if pair == "cg2":
+        monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    else:
+        monkeypatch.setenv("BNN_TC_NOMC", "1")
+    N = shape[0]
+    B = N // 2 if N % 2 == 0 else N
+    dd = drop_desc(drop_kind, 0.5, 0x31, 4, 1, B) if drop_kind else None
+    got, want = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    monkeypatch.setenv("BNN_TC_NO_PM", "1")
+    ref, _ = _conv_case(lib, "tc", "fp16", *shape, drop=dd)
+    assert torch.equal(got, ref) and not torch.isnan(got).any()
+    if drop_kind == 0:
+        assert (got.double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+def test_conv_tc_position_major_grouped_and_shortcut(lib, monkeypatch):
+    """... and the grouped stride-2 siblings (two 512-channel groups, 8x8 -> 4x4) and the fused projection shortcut."""
+    monkeypatch.setenv("BNN_TC_PM_MIN_IMAGES", "1")
+    monkeypatch.setenv("BNN_TC_MC_MIN_TILES", "1")
+    g = torch.Generator().manual_seed(4)
+    N, Cin, HW, Cg, G = 140, 256, 8, 512, 2
+    x = torch.randn(N, HW, HW, Cin, generator=g).half().cuda()
+    w = (torch.randn(G * Cg, 3, 3, Cin, generator=g) / np.sqrt(9 * Cin)).half().cuda()
+    b = torch.randn(G * Cg, generator=g).cuda()
+
+    def grouped():
+        outs = [torch.full((N, HW // 2, HW // 2, Cg), float("nan"), dtype=torch.half, device="cuda") for _ in range(G)]
+        ys = (ctypes.c_void_p * G)(*[o.data_ptr() for o in outs])
+        assert lib.bnn_conv2d_tc_grouped(x.data_ptr(), w.data_ptr(), b.data_ptr(), ys, G, 1, 0, 1, N, HW, HW, Cin, Cg, 3, 2,
+                                         stream()) == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        return outs
+    h = torch.randn(N, 4, 4, 512, generator=g).half().cuda()
+    wsc = (torch.randn(512, 9 * 512 + Cin, generator=g) / 70).half().cuda()
+    dd = drop_desc(batch=N)
+
+    def shortcut():
+        y = torch.full((N, 4, 4, 512), float("nan"), dtype=torch.half, device="cuda")
+        assert lib.bnn_conv2d_tc_shortcut(h.data_ptr(), wsc.data_ptr(), b.data_ptr(), None, y.data_ptr(), 1, N, 4, 4, 512, 512, 3, 1, 1,
+                                          ctypes.byref(dd), x.data_ptr(), HW, HW, Cin, stream()) == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        return y
+    a, c = grouped(), shortcut()
+    monkeypatch.setenv("BNN_TC_NO_PM", "1")
+    a0, c0 = grouped(), shortcut()
+    for u, v in zip(a, a0):
+        assert torch.equal(u, v) and not torch.isnan(u).any()
+    assert torch.equal(c, c0) and not torch.isnan(c).any()

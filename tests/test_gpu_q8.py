@@ -72,6 +72,19 @@ def test_conv_i8_bit_exact_vs_integer_oracle(lib, shape, pair, monkeypatch):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("pair", ["single", "cg2"])
+@pytest.mark.parametrize("shape", [(300, 4, 512, 512, 3, 1), (140, 8, 256, 256, 3, 1), (150, 8, 256, 512, 3, 2)])
+def test_conv_i8_position_major_tiles_bit_exact(lib, shape, pair, monkeypatch):
+    """position-major tiling (padding-only taps skipped, conv_tc.cu Params::pm_nb2) in the integer kernel: still the
+    oracle's integers, at ragged image counts"""
+    monkeypatch.setenv("BNN_TC_PM_MIN_IMAGES", "1")
+    monkeypatch.setenv("BNN_TC_MC_MIN_TILES" if pair == "cg2" else "BNN_TC_NOMC", "1")
+    N, H, Cin, Cout, k, stride = shape
+    x, w, bias_q, q_mult = _case(*shape, seed=N)
+    got = _run(lib, x, w, bias_q, q_mult, k, stride)
+    assert np.array_equal(got, oq8.qconv_relu(x, w, bias_q, q_mult, stride, 1))
+
+
 @pytest.mark.parametrize("kind", [1, 2])
 def test_conv_i8_fused_dropout_bit_exact(lib, kind):
     """a stochastic site fused behind the ReLU: Philox element / channel masks, applied in float before requantisation"""
