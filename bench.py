@@ -308,8 +308,10 @@ def summarize_profile(prof, peaks, clocks, region_s, with_traffic):
                                    peaks["src"], kind, peaks[kind], region_s, sm, mx, peaks["burst"],
                                    peaks["sustained"]),
                 "flops_counted": "EXECUTED multiply-adds (3x3 windows on 1x1 maps run their centre tap only, on 2x2 maps the "
-                                 "16 of 36 tap blocks that do not multiply zero padding; zero-padded stem channels and "
-                                 "Masksembles-dropped channels are not counted)",
+                                 "16 of 36 tap blocks that do not multiply zero padding, position-major tiles on 4x4 / 8x8 "
+                                 "maps skip the padding-only taps: 25 of 36 / 121 of 144; zero-padded stem channels and "
+                                 "Masksembles-dropped channels are not counted); achieved_algorithmic counts the "
+                                 "reference layer's full multiply-adds over the same time",
                 "achieved_algorithmic": fa / t_tc / 1e12,
                 "launches_per_step": len(tc), "avg_launch_ms": t_tc * 1e3 / len(tc),
                 "flops_per_launch": fx / len(tc), "share_of_step": t_tc * 1e3 / total_ms,
