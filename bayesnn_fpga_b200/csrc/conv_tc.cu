@@ -34,6 +34,7 @@ namespace bnn {
 namespace tc {
 
 constexpr int BM = 128;          // rows (output pixels) per tile
+constexpr int MAX_SMEM_OPTIN = 232448;   // 227 KB of dynamic shared memory per CTA
 constexpr int BK = 64;           // K elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 // EW = epilogue warps.  The operand-swapped kernel's epilogue with a fused element-wise dropout (Philox bits exchanged
@@ -102,6 +103,11 @@ struct Params {
   // share a position (a CTA pair runs the same tap set); q walks the OHW positions of one 256-image block before moving
   // to the next block, so the tiles in flight consume whole images and the input stays in L2 between its 9 uses
   // (position-outermost order re-read the input from DRAM once per tap row).  pm_nb2 = image blocks rounded up to even.
+  // RW (sibling-pair kernel, ONE group pair, K <= 9 k-blocks: ex1conv1 + layer2.0.0.conv1): each CTA's whole weight
+  // matrix (rw_kb x 16 KB) is loaded once and stays in shared memory; only the 16 KB pixel tiles go through the ring
+  // (rw_stages deep).  With the weights re-fetched per k-block a CTA ingests 32 KB per 512-cycle k-block = 64 B/clk, the
+  // L2 -> SM ceiling, and the issuer waited for operands half of the time (profiles/r02_ncu_epilogue_bound.txt).
+  int rw_kb, rw_stages;
   int pm_nb2;      // > 0: position-major tiling
   int n_img;       // images (M / OHW)
   int head_c;      // > 0: channel blocks of x_hi
@@ -109,6 +115,9 @@ struct Params {
   float q_mult;    // 8-bit operands: output LSBs per accumulator LSB = w_scale * in_scale / out_scale (a power of two
                    // for the QKeras fixed-point formats, any float otherwise)
   int vh_a, vh_w;  // vertical-halo form: slots of the haloed-activation ring and of the weight ring
+  // back-off (ns) of the waits with slack: producer <- free ring slot, epilogue <- accumulator full, MMA issuer <-
+  // accumulator drained, MMA issuer <- operands landed (0 = tight loop).  BNN_TC_WAIT_NS="p,e,a,f"
+  uint32_t wait_ns_prod, wait_ns_epi, wait_ns_acc, wait_ns_full;
   int exp_flags;   // MEASUREMENT ONLY (BNN_TC_EXP, results are garbage): bit 0 = do not load activation tiles, bit 1 = do
                    // not load weight tiles - isolates what operand delivery costs a launch; MASKED kernel: 4 = no
                    // masking, 8 = no proxy fence, 16 / 32 = CTA-scope instead of cluster-scope wait / arrive
@@ -144,6 +153,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Wait with nanosleep back-off (experiment, BNN_TC_WAIT_NS): ncu counted 19 % of the issued instructions of the
+// fused-dropout launch in try_wait loops, but backing off changes neither that launch nor the C2 step (try_wait already
+// suspends the warp in hardware; profiles/r02_exp_wait_backoff.txt).  ns == 0 (default): plain try_wait loop.
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try(bar, parity)) return;
+  if (ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  do {
+    __nanosleep(ns);
+  } while (!mbar_try(bar, parity));
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -455,8 +491,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   const int VH_A_SLOTS = p.vh_a, VH_W_SLOTS = p.vh_w;      // ring depths (vertical-halo form only)
-  uint8_t* smem_b = smem + (VH ? VH_A_SLOTS * VH_A_BYTES : STAGES * A_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (VH ? VH_RING_BYTES : STAGES * STAGE_BYTES));
+  const bool RW = SCG2 && !MASKED && p.rw_kb > 0;          // resident weights (Params::rw_kb)
+  const int n_stages = RW ? p.rw_stages : STAGES;          // ring depth in use (<= STAGES barriers)
+  uint8_t* smem_b = smem + (VH ? VH_A_SLOTS * VH_A_BYTES : n_stages * A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      smem + (VH ? VH_RING_BYTES : (RW ? n_stages * A_STAGE + p.rw_kb * B_TILE : STAGES * STAGE_BYTES)));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -465,6 +504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* afull_bar = tmem_empty + 2;
   uint64_t* ready_bar = afull_bar + (MASKED ? STAGES : 0);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ready_bar + (MASKED ? STAGES : 0));
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(tmem_ptr) + 1;      // RW: the resident weights have landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.taps * p.cblocks;
@@ -485,6 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], CG2 ? 2 * EW : EW);   // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(w_bar, 1);
     if constexpr (MASKED)
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&afull_bar[i], 1);
@@ -514,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         for (int kw = 0; kw < 3; ++kw)
           for (int cb = 0; cb < p.cblocks; ++cb) {
-            mbar_wait(&empty_bar[as], aph ^ 1);
+            mbar_wait_ns(&empty_bar[as], aph ^ 1, p.wait_ns_prod);
             if (p.exp_flags & 1) {
               mbar_arrive(&full_bar[as]);                   // measurement mode: activations never fetched
             } else {
@@ -525,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         // fused 1x1 stride-2 shortcut: plain 2 x 128-pixel tiles of the block input's parity view
         for (int cb = 0; cb < p.cblocks2; ++cb) {
-          mbar_wait(&empty_bar[as], aph ^ 1);
+          mbar_wait_ns(&empty_bar[as], aph ^ 1, p.wait_ns_prod);
           mbar_expect_tx(&full_bar[as], A_STAGE);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -545,7 +586,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int ws = 0;
       uint32_t wph = 0;
       auto load_w = [&](int kcol) {
-        mbar_wait(&empty_bar[VH_A_SLOTS + ws], wph ^ 1);
+        mbar_wait_ns(&empty_bar[VH_A_SLOTS + ws], wph ^ 1, p.wait_ns_prod);
         if (p.exp_flags & 2) {
           mbar_arrive(&full_bar[VH_A_SLOTS + ws]);          // measurement mode: weights never fetched
         } else {
@@ -569,17 +610,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int as = 0, ws = 0, acc = 0;
       uint32_t aph = 0, wph = 0, acc_phase = 0;
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_ns(&tmem_empty[acc], acc_phase ^ 1, p.wait_ns_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         uint32_t accum = 0;
         const int groups = 3 * p.cblocks + p.cblocks2;      // (kw, channel block) groups, then the shortcut k-blocks
         for (int g = 0; g < groups; ++g) {
           const int ntap = g < 3 * p.cblocks ? 3 : 1;
-          mbar_wait(&full_bar[as], aph);
+          mbar_wait_ns(&full_bar[as], aph, p.wait_ns_full);
           tc_fence_after();
           for (int kh = 0; kh < ntap; ++kh) {
-            mbar_wait(&full_bar[VH_A_SLOTS + ws], wph);
+            mbar_wait_ns(&full_bar[VH_A_SLOTS + ws], wph, p.wait_ns_full);
             tc_fence_after();
             const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + ws * B_TILE));
             // tap kh reads image rows kh-1 .. kh+14 of the haloed tile: 16 pixels x 128 bytes further per kh
@@ -676,6 +717,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (SCG2 && !MASKED) {
+        if (RW) {
+          // this CTA's group (= its rank: one group pair) x all k-blocks, once; both CTAs' loads complete on the leader's
+          // barrier
+          if (cta_rank == 0) mbar_expect_tx(w_bar, 2 * p.rw_kb * B_TILE);
+          for (int kb = 0; kb < p.rw_kb; ++kb)
+            tma_load_2d_2sm(smem_b + kb * B_TILE, &tmap_b, w_bar, kb * BKE, (int)cta_rank * BN);
+        }
+      }
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
         const int m_tile = (PAIRED && !SCG2) ? 2 * m_unit + (int)cta_rank : m_unit;
@@ -719,7 +769,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           for (int cb = 0; cb < p.cblocks; ++cb) {
             const int a_cb = (p.head_c > 0 && cb >= p.head_c) ? cb - p.head_c : cb;     // exit-head GEMM: x_hi twice
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.wait_ns_prod);
             if constexpr (CG2) {
               // both CTAs' loads complete on the leader's barrier: it expects the bytes of the pair
               if constexpr (MASKED) {
@@ -730,7 +780,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_5d(smem_a + stage * A_STAGE, &tmap_a, &afull_bar[stage], wp * p.Cin + cb * BKE, dw, hp, oh0[0] + dh,
                             img0[0]);
               } else {
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], RW ? 2 * A_STAGE : 2 * STAGE_BYTES);
 #pragma unroll
               for (int mt = 0; mt < NLOAD; ++mt) {
                 uint8_t* a_dst = smem_a + stage * A_STAGE + mt * A_TILE_BYTES;
@@ -741,8 +791,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                   img0[mt]);
               }
               }
-              tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE,
-                              SCG2 ? wrow : wrow + (int)cta_rank * (BN / 2));
+              if (!RW)
+                tma_load_2d_2sm(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE,
+                                SCG2 ? wrow : wrow + (int)cta_rank * (BN / 2));
             } else {
               if (p.exp_flags != 0 && !MC2) {
                 // measurement mode: part of the operands is never fetched
@@ -781,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               else
                 tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], tap * p.Cin + cb * BKE, wrow);
             }
-            if (++stage == STAGES) {
+            if (++stage == n_stages) {
               stage = 0;
               phase ^= 1;
             }
@@ -789,7 +840,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         // fused shortcut: the 1x1 stride-2 convolution of the block input rides in the same accumulator
         for (int cb = 0; cb < p.cblocks2; ++cb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.wait_ns_prod);
           if constexpr (CG2) {
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
 #pragma unroll
@@ -820,7 +871,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             else
               tma_load_2d(smem_b + stage * B_TILE, &tmap_b, &full_bar[stage], p.taps * p.Cin + cb * BKE, wrow);
           }
-          if (++stage == STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -837,6 +888,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (RW) mbar_wait(w_bar, 0);
       for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
         const int n_tile_mma = (tile % p.n_tiles_n) * (SCG2 ? 2 : 1);      // SCG2: first group of the pair
         const bool center_mma = (p.center_mask >> ((n_tile_mma * BN) / p.cout_g)) & 1u;
@@ -855,7 +907,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tile_kb = vh * vw * p.cblocks + p.cblocks2;
         }
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator set
+        mbar_wait_ns(&tmem_empty[acc], acc_phase ^ 1, p.wait_ns_acc);       // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         int cb = 0;
@@ -863,12 +915,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // gathered K: the last channel block of a tap holds fewer than 64 valid channels
           const int ksteps = (++cb == p.cblocks) ? p.last_ksteps : BK / UMMA_K;
           if (cb == p.cblocks) cb = 0;
-          mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          mbar_wait_ns(&full_bar[stage], phase, p.wait_ns_full);   // TMA bytes have landed
           if constexpr (MASKED) {                         // ... and both pixel halves are masked
             if (p.exp_flags & 16) mbar_wait(&ready_bar[stage], phase); else mbar_wait_acquire_cluster(&ready_bar[stage], phase);
           }
           tc_fence_after();
-          const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + stage * B_TILE));
+          const uint64_t w_desc = make_smem_desc(smem_u32(smem_b + (RW ? kb : stage) * B_TILE));
           if (leader) {
             if (SCG2) {
               // D^T[256 ch of the group pair, 256 px] += W[256 ch, 64] * P[256 px, 64]^T over the CTA pair: each CTA holds
@@ -917,7 +969,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
           }
           __syncwarp();
-          if (++stage == STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -972,7 +1024,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(res16 + (size_t)m * BN + q * 32));
           }
         }
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_ns(&tmem_full[acc], acc_phase, p.wait_ns_epi);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + hf * (PX / NHF));
 #pragma unroll 1
@@ -1000,8 +1052,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               bits |= philox_keep8(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, e >> 3, p.dp.thr) << (8 * t);
             }
             if (p.dp.scale == 0.f) bits = 0;
+            // kw[sl] bit 8t = keep bit of this lane's channel at pixel sl + 8t (pre-shifted by the lane's slot in its
+            // octet, so that the per-element test below is an AND with a compile-time mask)
 #pragma unroll
-            for (int sl = 0; sl < 8; ++sl) kw[sl] = __shfl_sync(0xffffffffu, bits, (lane & ~7) | sl);
+            for (int sl = 0; sl < 8; ++sl) kw[sl] = __shfl_sync(0xffffffffu, bits, (lane & ~7) | sl) >> (lane & 7);
             fac = p.dp.scale;
           } else if (p.dp.kind == BNN_DROP_MASKSEMBLES) {
             // host guarantees sample_px % 32 == 0: a 32-pixel chunk never straddles two samples
@@ -1015,8 +1069,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // all 32 residual loads are issued together (each is a 64-byte coalesced warp access), then consumed
           uint32_t rr[32];
           if (has_res) {
+            if (nvalid >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rr[j] = (j < nvalid) ? (uint32_t)__ldg(rp + j * BN) : 0u;
+              for (int j = 0; j < 32; ++j) rr[j] = (uint32_t)__ldg(rp + j * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rr[j] = (j < nvalid) ? (uint32_t)__ldg(rp + j * BN) : 0u;
+            }
           }
           tmem_ld_wait();
           if (p.dp.kind == BNN_DROP_NONE && nvalid >= 32) {
@@ -1043,13 +1102,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float f = __uint_as_float(v[j]) + bias_c;
             if (has_res) f += unpack2<T>(rr[j]).x;
             if (relu) f = fmaxf(f, 0.f);
-            f *= ((kw[j & 7] >> (8 * (j >> 3) + (lane & 7))) & 1u) ? fac : 0.f;
+            f = (kw[j & 7] & (1u << (8 * (j >> 3)))) ? f * fac : 0.f;
             return (uint16_t)(pack2<T>(f, 0.f) & 0xffffu);
           };
-          if (nvalid > 0 && p.dp.compact_pos == nullptr) {
+          if (nvalid >= 32 && p.dp.compact_pos == nullptr) {
+            // full chunk: no per-element predicates (ncu counted 42 issued instructions per element on the fused
+            // element-dropout launch, a fifth of them BSSY / BSYNC / BRA / ISETP around `j < nvalid`)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) yp[j * BN] = value(j);
+            for (int j = 0; j < 32; ++j) yp[j * BN] = value(j);
+          } else if (nvalid > 0 && p.dp.compact_pos == nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint16_t val = value(j);
+              if (j < nvalid) yp[j * BN] = val;
+            }
           } else if (nvalid > 0 && cpos >= 0) {
             // kept channels only, row stride = compact_c: the kept lanes of the warp write one contiguous run
             const int kc = p.dp.compact_c;
@@ -1101,7 +1167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
 
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_ns(&tmem_full[acc], acc_phase, p.wait_ns_epi);
       tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -1331,12 +1397,15 @@ template <int BN, int MT, bool SWAP, int PAIR, bool COMPACT, int EW, typename T,
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, Params p, cudaStream_t st,
                   const CUtensorMap* tah = nullptr) {
   static bool configured = false;
-  constexpr int smem = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR, SWAP);
+  constexpr int smem_static = VH ? smem_bytes_vh() : smem_bytes_pair(BN, MT, PAIR, SWAP);
+  // resident weights: (ring stages + weight k-blocks) x 16 KB
+  const int smem = p.rw_kb > 0 ? (p.rw_stages + p.rw_kb) * A_TILE_BYTES + 1024 + 256 : smem_static;
   constexpr bool MC2 = PAIR != 0;
   auto kern = conv_tc_kernel<BN, MT, SWAP, PAIR, COMPACT, EW, T, VH, MASKED>;
   const CUtensorMap& th = tah ? *tah : ta;
   if (!configured) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (SWAP && PAIR == 2 && !MASKED) ? MAX_SMEM_OPTIN : smem_static));
     configured = true;
   }
   const int m_tiles = p.pm_nb2 > 0 ? p.OHW * p.pm_nb2 : (p.M + MT * BM - 1) / (MT * BM);
@@ -1586,6 +1655,16 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
   }
   p.exp_flags = getenv("BNN_TC_EXP") ? atoi(getenv("BNN_TC_EXP")) : 0;
+  p.wait_ns_prod = p.wait_ns_epi = p.wait_ns_acc = p.wait_ns_full = 0;      // measured neutral (tools/exp_wait.py): off
+  if (const char* e = getenv("BNN_TC_WAIT_NS")) {
+    unsigned a = 0, b = 0, c = 0, d = 0;
+    if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) {
+      p.wait_ns_prod = a;
+      p.wait_ns_epi = b;
+      p.wait_ns_acc = c;
+      p.wait_ns_full = d;
+    }
+  }
   p.cblocks2 = sc ? sc->Cin2 / tc::BK : 0;
   p.sc_dense = sc ? sc->dense : 0;
   if (msk) {
@@ -1691,6 +1770,14 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     }
     if (scg2) {
       p.n_tiles_n = groups / 2;
+      // one group pair whose weights fit beside a >= 4-deep pixel ring: keep them resident (Params::rw_kb)
+      const int kb_all = p.taps * p.cblocks;
+      const int room = (tc::MAX_SMEM_OPTIN - 1024 - 256) / tc::A_TILE_BYTES - kb_all;
+      if (groups == 2 && p.center_mask == 0 && sc == nullptr && BN == 128 && room >= 4 && p.last_ksteps == tc::BK / tc::UMMA_K &&
+          getenv("BNN_TC_NO_RW") == nullptr) {
+        p.rw_kb = kb_all;
+        p.rw_stages = room < 6 ? room : 6;
+      }
       switch (BN) { BNN_TC_DISPATCH(128, 2, true, 2) }
     }
     if (wide_epi) {

@@ -39,6 +39,18 @@ __device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t stream, ui
 
 // 8 keep bits of the elements [8*blk, 8*blk + 7]: bit i <=> element 8*blk + i is kept
 __device__ __forceinline__ uint32_t keep_bits8(const uint4 r, uint32_t thr) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  // VIMNMX.U16x2 compares both halves of a word at once and hands back the two (a >= b) predicates: 20 instead of 28
+  // instructions per block (the fused-dropout epilogues are issue-bound)
+  const uint32_t t2 = thr | (thr << 16);
+  bool h0, l0, h1, l1, h2, l2, h3, l3;
+  __vibmax_u16x2(r.x, t2, &h0, &l0);
+  __vibmax_u16x2(r.y, t2, &h1, &l1);
+  __vibmax_u16x2(r.z, t2, &h2, &l2);
+  __vibmax_u16x2(r.w, t2, &h3, &l3);
+  return (l0 ? 1u : 0u) | (h0 ? 2u : 0u) | (l1 ? 4u : 0u) | (h1 ? 8u : 0u) | (l2 ? 16u : 0u) | (h2 ? 32u : 0u) |
+         (l3 ? 64u : 0u) | (h3 ? 128u : 0u);
+#endif
   return ((r.x & 0xffffu) >= thr ? 1u : 0u) | ((r.x >> 16) >= thr ? 2u : 0u) | ((r.y & 0xffffu) >= thr ? 4u : 0u) |
          ((r.y >> 16) >= thr ? 8u : 0u) | ((r.z & 0xffffu) >= thr ? 16u : 0u) | ((r.z >> 16) >= thr ? 32u : 0u) |
          ((r.w & 0xffffu) >= thr ? 64u : 0u) | ((r.w >> 16) >= thr ? 128u : 0u);

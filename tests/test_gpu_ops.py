@@ -689,7 +689,8 @@ def test_conv_tc_sibling_pair_cta_group2(lib, N, Cin, HW, G, center, monkeypatch
     """Operand-swapped kernel as CTA pairs (tcgen05.mma.cta_group::2): two 128-channel sibling groups that read the same
     pixels run on one pair - one group per CTA, the 256-pixel tile split over the pair.  vs float64 torch per group,
     and bit-identical to the one-CTA-per-(tile, group) kernel (same accumulation order); more tiles than SM pairs;
-    a pair of centre-tap (1x1) groups; a pair that DISAGREES on the centre-tap flag falls back to single CTAs."""
+    a pair of centre-tap (1x1) groups; a pair that DISAGREES on the centre-tap flag falls back to single CTAs.  The two
+    Cin = 64 cases (one group pair, nine k-blocks) run with the weights RESIDENT in shared memory (Params::rw_kb)."""
     g = torch.Generator().manual_seed(N * G)
     x = torch.randn(N, Cin, HW, HW, generator=g).half()
     ws = []
