@@ -1484,8 +1484,12 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   const int Cout = groups * cout_g;
   const int pad = ksize == 3 ? 1 : 0;
   const int OH = (H + 2 * pad - ksize) / stride + 1, OW = (W + 2 * pad - ksize) / stride + 1;
+  // narrow input (the stem: 3 channels stored as 16): ONE k-block per tap of which only Cin / 16 k-steps are issued
+  // (Params::last_ksteps, as for gathered K); the TMA unit zero-fills the box columns past Cin
+  const bool narrow_in = !i8 && gsel == nullptr && Cin > 0 && Cin < 64 && Cin % 16 == 0 && groups == 1 && sc == nullptr &&
+                         !pool && hg == nullptr && msk == nullptr && stride == 1;
   const bool ok = (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) &&
-                  (gsel ? (Cin % 16 == 0 && Cin > 0) : Cin % bke == 0) && cout_g % 64 == 0 &&
+                  (gsel ? (Cin % 16 == 0 && Cin > 0) : (Cin % bke == 0 || narrow_in)) && cout_g % 64 == 0 &&
                   (stride == 1 || (H % 2 == 0 && W % 2 == 0)) && tc::pow2(OW) && tc::pow2(OH) && OW <= 128;
   if (!ok) {
     set_error("%s: unsupported geometry k=%d s=%d Cin=%d Cout=%d %dx%d (use bnn_conv2d_simt)", who, ksize, stride, Cin,
@@ -1542,7 +1546,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
   // worth it when at least 10 % of the taps go away (8x8 stride 1: 16 %, 4x4: 31 %; 16x16 -> 8x8 stride 2 saves 8 % of the
   // MMAs but its 128-image gathers cost more than that: measured 0.515 vs 0.481 ms, profiles/README.md)
   const bool pm_pays = 10 * pm_rows * pm_cols <= 9 * (9 * OH * OW);
-  const bool pm = ksize == 3 && pm_pays && OH * OW <= 64 && OH * OW >= 4 && cout_g % 256 == 0 && gsel == nullptr && !pool && hg == nullptr &&
+  const bool pm = ksize == 3 && pm_pays && !narrow_in && OH * OW <= 64 && OH * OW >= 4 && cout_g % 256 == 0 && gsel == nullptr && !pool && hg == nullptr &&
                   msk == nullptr && !(drop && drop->kind == BNN_DROP_MASKSEMBLES && drop->compact_pos != nullptr) &&
                   !(sc && sc->dense) && N >= pm_min && getenv("BNN_TC_NO_PM") == nullptr;
   if (pm) {
@@ -1732,7 +1736,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
                           !(getenv("BNN_TC_SWAP_EPI") && atoi(getenv("BNN_TC_SWAP_EPI")) == 8);
     // vertical-halo form: 3x3 stride-1 convolutions on 16 x 16 maps (one image per 256-pixel tile) - layer2 of the
     // ResNet, block 1 of the VGG.  BNN_TC_NO_VH=1 keeps the one-box-per-tap kernel (A/B measurements, unit tests).
-    const bool vh = ksize == 3 && stride == 1 && OH == 16 && OW == 16 && groups == 1 && gsel == nullptr &&
+    const bool vh = ksize == 3 && stride == 1 && OH == 16 && OW == 16 && groups == 1 && gsel == nullptr && Cin % 64 == 0 &&
                     !compact_out && getenv("BNN_TC_NO_VH") == nullptr;
     if (vh) {
       p.vh_a = 3;

@@ -369,7 +369,10 @@ class Engine:
         self.in_pad = 0
         if self.use_tc and graph.input.C < 64 and os.environ.get("BNN_STEM_TC", "1") != "0":
             readers = [o for o in graph.ops if o.src is graph.input or o.res is graph.input]
-            self.in_pad = 64
+            # (BNN_STEM_PAD=16: 16 channels, one MMA k-step per tap instead of four - measured SLOWER, 0.098 vs 0.079 ms
+            # for the C2 stem: 32-byte TMA rows and 32-byte pixel stores cost more than the three skipped k-steps save)
+            self.in_pad = 16 if (graph.input.C <= 16 and all(getattr(o, "stride", 1) == 1 for o in readers) and
+                                 os.environ.get("BNN_STEM_PAD") == "16") else 64
             if not readers or not all(o.kind == "conv" and o.res is None and self._tc_eligible(o) for o in readers):
                 self.in_pad = 0
         self.gather_mode = int(os.environ.get("BNN_MASK_GATHER", "1")) if mask_gather is None else int(mask_gather)
@@ -388,6 +391,7 @@ class Engine:
         self.launches = 0
         self._prof = None
         self._graphs = {}
+        self._h2d_done = None
         self._graph_collectives = os.environ.get("BNN_GRAPH_COLLECTIVES", "1") != "0"
         self._bufs = {}
         self._prepare_weights()
@@ -412,7 +416,9 @@ class Engine:
         cin = self.in_pad if (op.src is self.graph.input and self.in_pad) else op.src.C
         oh, ow = getattr(op, "pool_from", None) or (op.dst.H, op.dst.W)
         return (self.use_tc and kh == kw and ((kh == 3 and op.pad == 1) or (kh == 1 and op.pad == 0))
-                and op.stride in (1, 2) and cin % 64 == 0 and op.dst.C % 64 == 0
+                and op.stride in (1, 2) and op.dst.C % 64 == 0
+                and (cin % 64 == 0 or (op.src is self.graph.input and cin == self.in_pad and cin % 16 == 0 and
+                                       op.stride == 1 and getattr(op, "pool_from", None) is None))
                 and (op.stride == 1 or (op.src.H % 2 == 0 and op.src.W % 2 == 0))
                 and pow2(oh) and pow2(ow) and ow <= 128)
 
@@ -465,7 +471,8 @@ class Engine:
                 # ... or, on 16-bit features with F % 64 == 0, the whole classifier as ONE tcgen05 GEMM over hi/lo-split
                 # operands (bnn_exit_head_tc): [x_hi | x_lo] x [w_hi | w_lo | w_hi]^T with fp32 logits
                 # (narrow heads, C <= 32, stay on the one-kernel FFMA form: three launches cost more than they save)
-                op.head_tc = (self.dtype_name != "fp32" and self.use_tc and F_ % 64 == 0 and C_ > 32 and
+                op.head_tc = (self.dtype_name != "fp32" and self.use_tc and F_ % 64 == 0 and
+                              C_ >= int(os.environ.get("BNN_HEAD_TC_MIN_C", "33")) and
                               os.environ.get("BNN_HEAD_TC", "1") != "0")
                 if op.head_mma or op.head_tc:
                     w32 = op.weight.contiguous().to(dev, torch.float32)             # [C][F], the nn.Linear layout
@@ -1022,8 +1029,15 @@ class Engine:
             self._graphs[key] = "seen"
             if len(self._graphs) > 64:
                 self._graphs.pop(next(iter(self._graphs)))
-            return self._step(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn, gather_fn)
+            return self._step(x.to(self.device, non_blocking=True), S, sample0, seed, want_logits, mask_offset, S_total,
+                              reduce_fn, gather_fn)
         st["x"].copy_(x, non_blocking=True)
+        if x.device.type == "cpu" and x.is_pinned():
+            # the caller may reuse its pinned buffer as soon as this call returns: wait for the H2D copy (only)
+            if self._h2d_done is None:
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record()
+            self._h2d_done.synchronize()
         rf, gf = (reduce_fn, gather_fn) if inside else (None, None)
         if entry == "seen":
             n0 = self.launches
@@ -1065,13 +1079,17 @@ class Engine:
         all-reduces the flat sums tensor across ranks before the finaliser, `gather_fn(out)` (optional) gathers the
         finished statistics (batch sharding).  Masksembles rows are (module.cnt + mask_offset + s) % n with
         mask_offset defaulting to sample0."""
-        x = x.to(self.device, torch.float32)
         B = self._batch(x, S) if S > 0 else x.shape[0]
         if use_graph is None:
             use_graph = os.environ.get("BNN_CUDA_GRAPH", "1") != "0"
+        graphed = use_graph and B > 0 and S > 0 and self._prof is None
+        # a float32 HOST batch headed for a graph replay is copied straight into the graph's input buffer (one H2D, async
+        # when the batch is pinned); everything else is moved / converted here
+        if not (graphed and x.device.type == "cpu" and x.dtype == torch.float32 and x.is_contiguous()):
+            x = x.to(self.device, torch.float32)
         S_total = S if S_total is None else S_total
         with torch.cuda.device(self.device):
-            if use_graph and B > 0 and S > 0 and self._prof is None:
+            if graphed:
                 st, views, ent = self._step_graphed(x, S, sample0, seed, want_logits, mask_offset, S_total, reduce_fn,
                                                     gather_fn)
             else:

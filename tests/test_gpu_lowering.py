@@ -206,3 +206,43 @@ def test_converter_matches_the_reference_converter_fixture(tag):
     errs["standalone_passes"] = float(np.abs(passes - want_passes).max())
     assert errs["standalone_passes"] <= 1e-5 * scale
     report(test="converter_vs_reference_fixture", net=tag, scale=scale, **errs)
+
+
+@pytest.mark.parametrize("kind,classes", [("resnet_mcd", 10), ("resnet_mask", 100), ("vgg_last3", 10)])
+def test_unmodified_reference_model_object_is_a_drop_in(kind, classes):
+    """The reference's OWN model object - built by its `models.model_loader.get_network` from the staged tree
+    (oracle/_ref: its ResNet18MCEarlyExit / VGG19MCEarlyExit classes, its MCDropout / Masksembles layers) - handed to
+    `mc_predict` as is: lowering.lower_module traces it to the same plan as this package's class of the same name, so the
+    predictive means are IDENTICAL to the drop-in class holding the same state_dict (whose parity with the oracle the
+    other GPU tests establish).  BASELINE configs 2, 3 and 4."""
+    from oracle import ref_arm
+    if not ref_arm.available():
+        pytest.skip("oracle/_ref is not staged (python oracle/make_ref.py in the build container)")
+    from bayesnn_fpga_b200 import model_loader
+    from bayesnn_fpga_b200.Dropouts import MCDropout as OurMCDropout
+    ref_model = ref_arm.build(kind, classes)
+    assert type(ref_model).__module__.startswith("models.")          # really the reference's class
+    base = dict(load_model=None, out_dim=classes, dropout_exit=True, dropout_p=0.5, mask_type="mc", num_masks=4, mask_scale=4.0)
+    np.random.seed(0)                                                # Masksembles masks: same generator calls as ref_arm.build
+    if kind == "resnet_mcd":
+        ours = model_loader.get_network(dict(base, call="ResNet18", resnet_type="mc_early_exit", dropout="block", n_exits=4))
+    elif kind == "resnet_mask":
+        ours = model_loader.get_network(dict(base, call="ResNet18", resnet_type="mc_early_exit", dropout="block", n_exits=4,
+                                             mask_type="mask", mask_scale=2.0))
+    else:
+        ours = model_loader.get_network(dict(base, call="VGG19", resnet_type="mc_early_exit", dropout=None, n_exits=5,
+                                             image_size=32))
+        for i in (2, 3, 4):
+            ours.blocks[i].append(OurMCDropout(0.5))
+    ours.load_state_dict(ref_model.state_dict())
+    B, S = 24, 4
+    x = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    a = mc_predict(ref_model.cuda().eval(), x.cuda(), S, seed=77, dtype="fp16")
+    a_probs = [p.clone() for p in a.mean_probs]
+    b = mc_predict(ours.cuda().eval(), x.cuda(), S, seed=77, dtype="fp16")
+    assert len(a_probs) == len(b.mean_probs) == (5 if kind == "vgg_last3" else 4)
+    for e, (pa, pb) in enumerate(zip(a_probs, b.mean_probs)):
+        err = (pa - pb).abs().max().item()
+        report(test="reference_object_drop_in", kind=kind, exit=e, err=err)
+        assert torch.isfinite(pa).all() and abs(pa.sum(1) - 1).max().item() < 1e-3
+        assert err == 0.0

@@ -851,3 +851,15 @@ def test_conv_tc_position_major_grouped_and_shortcut(lib, monkeypatch):
     for u, v in zip(a, a0):
         assert torch.equal(u, v) and not torch.isnan(u).any()
     assert torch.equal(c, c0) and not torch.isnan(c).any()
+
+
+@pytest.mark.parametrize("Cin,Cout,HW", [(16, 64, 32), (32, 128, 8), (48, 256, 8), (16, 128, 16)])
+def test_conv_tc_narrow_input_one_kstep_per_tap(lib, Cin, Cout, HW):
+    """Inputs narrower than one 64-channel k-block (the stem: 3 channels stored as 16): one k-block per tap of which only
+    Cin / 16 MMA k-steps are issued; the TMA unit zero-fills the box columns past Cin.  vs float64 torch, all tile shapes
+    (64 / 128-swapped / 256-channel tiles), ragged image count."""
+    shape = (37, HW, HW, Cin, Cout, 3, 1, 1, True, False)
+    got, want = _conv_case(lib, "tc", "fp16", *shape)
+    err = (got.double() - want).abs().max().item()
+    report(test="conv_tc_narrow_input", Cin=Cin, Cout=Cout, err=err)
+    assert err <= 1e-3 * max(1.0, want.abs().max().item())
