@@ -33,6 +33,10 @@
 namespace bnn {
 namespace tc {
 
+#ifndef BNN_PHILOX_UNROLL
+#define BNN_PHILOX_UNROLL 2
+#endif
+constexpr int PHILOX_UNROLL = BNN_PHILOX_UNROLL;   // independent Philox chains per thread in the 256-column epilogue
 constexpr int BM = 128;          // rows (output pixels) per tile
 constexpr int MAX_SMEM_OPTIN = 232448;   // 227 KB of dynamic shared memory per CTA
 constexpr int BK = 64;           // K elements per k-block = one 128-byte swizzle row
@@ -1242,7 +1246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint64_t blk0 = (e_base + (uint64_t)c0) >> 3;      // c0 % 32 == 0 and Cout % 64 == 0
               // rolled loop (keeps the kernel inside the instruction cache): 4 Philox blocks -> 32 keep bits
               uint32_t bits = 0;
-#pragma unroll 1
+#pragma unroll PHILOX_UNROLL
               for (int j = 0; j < 4; ++j)
                 bits |= philox_keep8(p.dp.seed, p.dp.stream_id, p.dp.sample0 + s_local, blk0 + j, p.dp.thr) << (8 * j);
               if (p.dp.scale == 0.f) bits = 0;
