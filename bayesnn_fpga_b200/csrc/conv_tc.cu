@@ -992,7 +992,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // warp w may touch TMEM lanes 32*(w%4)..+31; two warps share a lane group and split the columns.
-    constexpr int NCH = BN / 64;                          // 32-column chunks per warp (non-swapped layout)
+    constexpr int NHFN = EW / 4;                          // warps per TMEM lane group (non-swapped layout): column shares
+    constexpr int NCH = BN / (32 * NHFN);                 // 32-column chunks per warp
+    static_assert(SWAP || (NCH >= 1 && NCH * 32 * NHFN == BN), "epilogue warps must tile the columns in 32-column chunks");
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;                       // which half of the columns
     const T* __restrict__ res = reinterpret_cast<const T*>(p.res);
@@ -1141,7 +1143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = sched_id; tile < p.num_tiles; tile += sched_n) {
       const int m_unit = tile / p.n_tiles_n, n_tile = tile - m_unit * p.n_tiles_n;
       const int m_tile = PAIRED ? 2 * m_unit + (int)cta_rank : m_unit;
-      const int cbase = n_tile * BN + hf * (BN / 2);      // first (concatenated) output channel of this warp
+      const int cbase = n_tile * BN + hf * (BN / NHFN);   // first (concatenated) output channel of this warp
       const int grp = cbase / p.cout_g;                   // output group and channel offset inside it
       const int cgrp = cbase - grp * p.cout_g;
       // 128-channel groups paired into 256-column tiles: an odd group count leaves the last half-tile without output
@@ -1195,7 +1197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               p.dp.kind == BNN_DROP_CHANNEL ? (uint64_t)b * p.Cout : ((uint64_t)b * p.OHW + pix) * (uint64_t)p.Cout;
         }
         const uint32_t t_row =
-            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * BN + hf * (BN / 2));
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * BN + hf * (BN / NHFN));
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           uint32_t v[32];
@@ -1794,6 +1796,8 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     switch (BN) { BNN_TC_DISPATCH(128, 2, true, 0) }
   }
   if (cg2 && mc2) {
+    // (sixteen epilogue warps for the residual + stochastic-site form of this kernel: measured 3 % SLOWER than eight,
+    // tools/exp_epi256.py - the instantiation was dropped again)
     switch (BN) { BNN_TC_DISPATCH(256, 1, false, 2) }
   }
   if (mc2) {

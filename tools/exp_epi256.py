@@ -39,6 +39,8 @@ cases = {"8x8 256ch plain": case(8, 256, False, False), "8x8 256ch +res": case(8
 best = {}
 for rnd in range(6):
     for name, (call, _) in cases.items():
-        best[name] = min(best.get(name, 1e9), timed(call))
+        for epi in ("16", "8"):
+            os.environ["BNN_TC_EPI256"] = epi
+            best[(name, epi)] = min(best.get((name, epi), 1e9), timed(call))
 for name in cases:
-    print("%-28s %.4f ms" % (name, best[name]), flush=True)
+    print("%-28s epilogue warps 16: %.4f ms   8: %.4f ms" % (name, best[(name, "16")], best[(name, "8")]), flush=True)
