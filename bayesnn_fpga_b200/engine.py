@@ -237,6 +237,13 @@ class Graph:
                 continue
             if sum(1 for o in self.ops if o.src is t or o.res is t) != 1:
                 continue
+            if conv.stride == 1 and conv.ksize == (3, 3) and hw <= 16 and os.environ.get("BNN_POOL_UNFUSE_SMALLMAPS") == "1":
+                # experiment: 3x3 stride-1 on a 4x4 / 2x2 map could run with position-major tiles (31 % / 56 % of the taps
+                # skipped, conv_tc.cu Params::pm_nb2) if it did not pool - an image's positions sit in different tiles.
+                # Measured at C2 (layer4.1.conv2): the launch 0.466 -> 0.318 ms, the head 0.052 -> 0.063 ms, the STEP
+                # unchanged (38.3 k img/s both ways): under the power cap the SM clock dropped 1 432 -> 1 387 MHz - the
+                # extra 0.27 GB of HBM traffic costs the energy the skipped zero-MMAs saved.  Off.
+                continue
             if conv.stride == 2 and any(o is not conv and o.kind == "conv" and o.src is conv.src and o.stride == 2
                                         for o in self.ops):
                 continue                      # stays in its sibling group (the shared input is read once)
