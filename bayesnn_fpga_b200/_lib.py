@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libbnn_b200.so")
-SOURCES = ["kernels_simt.cu", "kernels_head.cu", "kernels_stats.cu", "conv_tc.cu"]
+SOURCES = ["kernels_simt.cu", "kernels_head.cu", "kernels_stats.cu", "kernels_comm.cu", "conv_tc.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "../../include/bnn_b200.h"]
 
 F32, F16, BF16, I8 = 0, 1, 2, 3
@@ -113,6 +113,9 @@ _SIGS = {
     "bnn_kde_triweight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "bnn_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "bnn_peer_allreduce_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "bnn_dropout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(DropDesc), ctypes.c_void_p]),
     "bnn_channel_affine": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,

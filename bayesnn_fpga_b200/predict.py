@@ -26,12 +26,100 @@ def shard_batch(B, world_size, rank):
     return shard_samples(B, world_size, rank)
 
 
-def allreduce_sums(flat, group=None):
-    """The single collective of the path: sum the flat statistics buffer over ranks."""
+class PeerReduce:
+    """The path's single collective - the sum of the flat statistics buffer over the ranks - as ONE kernel over NVLink
+    peer memory (csrc/kernels_comm.cu, `bnn_peer_allreduce`): every rank copies its sums into a slot of symmetric memory
+    (torch.distributed._symmetric_memory maps it into all peers), signals the peers, adds the W slots in RANK order - so
+    the totals are bit-identical on every rank - and waits until all peers have read its slot.  Stream-ordered, CUDA-graph
+    capturable, no host synchronisation.  One workspace per payload size; creating it is a collective (first call)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self._ws = {}
+        self.disabled = None                     # a string: why NCCL is used instead
+
+    def _workspace(self, flat):
+        import ctypes
+        import torch.distributed as dist
+        key = (flat.numel(), flat.device.index)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        ok, why = 1, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            n_pad = (flat.numel() + 3) // 4 * 4
+            t = symm.empty(n_pad + 16, dtype=torch.float32, device=flat.device)     # slot | ready[8] | done[8]
+            t.zero_()
+            hdl = symm.rendezvous(t, self.group)
+            bases = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            state = torch.zeros(8, dtype=torch.int32, device=flat.device)
+            ws = (t, hdl, bases, state, n_pad * 4)
+        except Exception as e:                     # noqa: BLE001 - no P2P mapping on this box / torch build
+            ok, why = 0, "%s: %s" % (type(e).__name__, e)
+        # all ranks take the same decision, and nobody signals before every rank's flags are zero
+        flag = torch.tensor([ok], dtype=torch.int32, device=flat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            import warnings
+            self.disabled = why or "a peer could not map the symmetric workspace"
+            warnings.warn("peer-memory all-reduce unavailable (%s): using NCCL" % self.disabled)
+            return None
+        self._ws[key] = ws
+        return ws
+
+    def __call__(self, flat):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        if self.disabled is None and flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous():
+            ws = self._workspace(flat)
+            if ws is not None:
+                _, _, bases, state, flags_off = ws
+                lib = _lib.load()
+                _lib.check(lib.bnn_peer_allreduce(ctypes.c_void_p(flat.data_ptr()), flat.numel(), bases, self.world, self.rank,
+                                                  flags_off, ctypes.c_void_p(state.data_ptr()),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)))
+                return flat
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        return flat
+
+    def check(self):
+        """Raise if a peer ever failed to answer (synchronises the stream)."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        for (_, dev), (_, _, _, state, _) in self._ws.items():
+            _lib.check(lib.bnn_peer_allreduce_status(ctypes.c_void_p(state.data_ptr()),
+                                                     ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
+
+_PEER = {}           # process group -> PeerReduce
+
+
+def allreduce_sums_nccl(flat, group=None):
+    """The same sum through NCCL (`BNN_PEER_REDUCE=0`, CPU / gloo groups, and the baseline bench.py times beside it)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+def allreduce_sums(flat, group=None):
+    """The single collective of the path: sum the flat statistics buffer over ranks (in place, on the current stream)."""
+    import os
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return flat
+    if flat.is_cuda and os.environ.get("BNN_PEER_REDUCE", "1") != "0" and dist.get_world_size(group) <= 8:
+        g = group if group is not None else dist.group.WORLD
+        red = _PEER.get(g)
+        if red is None:
+            red = _PEER[g] = PeerReduce(g)
+        return red(flat)
+    return allreduce_sums_nccl(flat, group)
 
 
 def _generic_engine(model, x, dtype, engine_kwargs):

@@ -476,10 +476,19 @@ def main():
                 predict.allreduce_sums(flat.clone())
             buf = flat.clone()
             ms_c, _, _ = timed(lambda: predict.allreduce_sums(buf), 50)
+            for _ in range(5):
+                predict.allreduce_sums_nccl(buf)
+            ms_nccl, _, _ = timed(lambda: predict.allreduce_sums_nccl(buf), 50)
+            peer = predict._PEER.get(dist.group.WORLD)
+            via = ("bnn_peer_allreduce: one kernel over NVLink peer memory, rank-ordered sums"
+                   if peer is not None and peer.disabled is None else "NCCL")
+            if peer is not None:
+                peer.check()
             t_n1 = ms1 / n1
             extra = {"n1_ms_per_step": t_n1, "speedup_vs_n1": t_n1 / (ms / steps),
                      "efficiency_vs_n1": t_n1 / (ms / steps) / world, "collective_us": ms_c / 50 * 1e3,
-                     "collective": "all_reduce(sum) of %d fp32 statistics" % flat.numel(),
+                     "collective_us_nccl": ms_nccl / 50 * 1e3,
+                     "collective": "all_reduce(sum) of %d fp32 statistics via %s" % (flat.numel(), via),
                      "ideal_efficiency_with_replicated_prefix":
                          (pre_macs + S * suf_macs) / (world * (pre_macs + (S / world) * suf_macs))}
             rec.update(extra)

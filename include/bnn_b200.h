@@ -325,6 +325,20 @@ int bnn_top_label(const double* probs, const int32_t* labels, int N, int C, int 
 int bnn_kde_triweight(const double* data, const int32_t* flags, int n, double bw, double n_points, double x0,
                       double dx, int G, double lo, double hi, double* out, void* stream);
 
+/* ---- the path's one collective as a kernel over NVLink peer memory (sample sharding) ----
+ * The reference is single-device; sharding its S passes over the GPUs of a box leaves one exchange: the sum of the
+ * per-exit statistics sums (what `np.average(all_output_probs, axis=0)` / `all_outputs` run over, results_analyzer.py:
+ * 247-248) before the finaliser.  bnn_peer_allreduce sums `flat` (n float32, device, 16-byte aligned) over `world`
+ * ranks IN PLACE on `stream`: peer_base[r] (HOST array of `world` device pointers) is rank r's workspace as mapped into
+ * THIS process (symmetric memory: same layout everywhere) = a slot of >= n floats followed, at flags_offset_bytes, by
+ * 16 uint32 flags (zeroed once before the first call on any rank); `state` = 32 bytes of local device memory, zeroed
+ * once.  Ranks add the slots in rank order, so every rank gets the same bits.  All ranks must call it the same number
+ * of times.  A peer that does not answer within 2 s sets an error flag instead of hanging the GPU:
+ * bnn_peer_allreduce_status (synchronises `stream`) returns BNN_E_CUDA then. */
+int bnn_peer_allreduce(float* flat, int64_t n, void* const* peer_base, int world, int rank, int64_t flags_offset_bytes,
+                       void* state, void* stream);
+int bnn_peer_allreduce_status(const void* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

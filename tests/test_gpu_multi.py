@@ -29,7 +29,39 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 case = %(case)r
 rep = {"case": case, "world": world, "rank": rank}
-if case == "ragged":
+if case == "peer":
+    # the all-reduce kernel over NVLink peer memory (csrc/kernels_comm.cu) against NCCL on random payloads: several sizes
+    # (one not a multiple of 4, one tiny), several epochs each, eager and replayed from a CUDA graph
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    worst = 0.0
+    for n in (21504, 1031, 7, 262144):
+        for it in range(4):
+            flat = torch.randn(n, device="cuda", generator=g)
+            want = predict.allreduce_sums_nccl(flat.clone())
+            got = predict.allreduce_sums(flat.clone())
+            worst = max(worst, ((got - want).abs().max() / want.abs().max()).item())
+            everyone = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(everyone, got)
+            assert all(torch.equal(everyone[0], t) for t in everyone), "ranks disagree on the bits of the total"
+    red = predict._PEER[dist.group.WORLD]
+    assert red.disabled is None, "peer-memory path not taken: %%s" %% red.disabled
+    buf = torch.zeros(21504, device="cuda")
+    predict.allreduce_sums(buf)                               # workspace exists before the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        predict.allreduce_sums(buf)
+    for it in range(3):
+        src = torch.randn(21504, device="cuda", generator=g)
+        want = predict.allreduce_sums_nccl(src.clone())
+        buf.copy_(src)
+        graph.replay()
+        worst = max(worst, ((buf - want).abs().max() / want.abs().max()).item())
+    red.check()                                               # no peer ever timed out
+    assert worst <= 1e-6, worst
+    rep["peer_allreduce_max_rel_err_vs_nccl"] = worst
+    dtypes = ()
+elif case == "ragged":
     model, sd, gold = build_seeded("resnet18_mcd_block")
     model.cuda()
     x = torch.from_numpy(gold["x"])
@@ -80,6 +112,15 @@ def test_sample_sharding_over_nccl_matches_single_gpu(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run(tmp_path, "ragged", 2, 29533)
+
+
+def test_peer_memory_allreduce_kernel_matches_nccl(tmp_path):
+    """bnn_peer_allreduce (one kernel over NVLink peer loads, rank-ordered sums) == NCCL's all-reduce up to fp32
+    summation order, bit-identical across ranks, eager and inside a CUDA graph, over all visible GPUs."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(tmp_path, "peer", 8 if n >= 8 else (4 if n >= 4 else 2), 29535)
 
 
 def test_c5_s128_sample_sharded_over_all_gpus_is_bit_identical_per_sample(tmp_path):
