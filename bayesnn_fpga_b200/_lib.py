@@ -113,6 +113,8 @@ _SIGS = {
     "bnn_kde_triweight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "bnn_exit_head_rows": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.POINTER(DropDesc)] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p]),
     "bnn_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "bnn_peer_allreduce_status": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -344,6 +344,85 @@ __global__ void __launch_bounds__(SM_WARPS * 32) head_softmax_warp_kernel(
   }
 }
 
+// Narrow heads (C <= 32) with all samples in parallel: one WARP per (sample, image) row.  The block-per-image kernel
+// above walks the samples of an image in chunks with barriers between its phases and takes ~50 us per C2 exit whatever
+// the bandwidth (8 MB of pooled features): a latency chain.  Here 8192 rows are 8192 independent warps: lane l owns the
+// feature octets l, l + 32, ... (one 16-byte load per pixel, one Philox block per octet), multiplies them with the
+// classifier weights held in shared memory ([C][F] fp32, the nn.Linear layout, split into two 4-float planes per octet
+// so that the 16-byte reads of a warp are conflict-free) and the C partial sums are reduced with warp shuffles.  Logits
+// go to a [rows][pitch] fp32 workspace; head_softmax_warp_kernel accumulates them per image in sample order.
+template <typename T, int CMAX>
+__global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ feat, int feat_has_samples, int B, int S_local,
+                                                        int HW, int F, int C, const float* __restrict__ w_cf,
+                                                        const float* __restrict__ bias, DropParams dp,
+                                                        float* __restrict__ logits, int pitch, int rows_per_cta,
+                                                        float feat_scale) {
+  extern __shared__ float w_s[];                       // [C][2][F / 2]: plane h holds features 8 * oct + 4 * h + (0..3)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = F >> 1;
+  for (int i = tid; i < C * F; i += 256) {
+    const int c = i / F, f = i - c * F;
+    w_s[c * F + ((f >> 2) & 1) * half + (f >> 3) * 4 + (f & 3)] = __ldg(w_cf + i);
+  }
+  __syncthreads();
+  const int64_t rows = (int64_t)S_local * B;
+  const int64_t r_end = min(rows, ((int64_t)blockIdx.x + 1) * rows_per_cta);
+  const float inv_hw = feat_scale / (float)HW;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + warp; row < r_end; row += 8) {
+    const int s = (int)(row / B), b = (int)(row - (int64_t)s * B);
+    const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F;
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    for (int f0 = lane * 8; f0 < F; f0 += 256) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < HW; ++p) {
+        const Vec8h<T> v = *reinterpret_cast<const Vec8h<T>*>(src + (size_t)p * F + f0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += to_f32<T>(v.v[j]);
+      }
+      uint32_t k8 = 0xffu;
+      float fac = inv_hw;
+      if (dp.kind == BNN_DROP_ELEMENT || dp.kind == BNN_DROP_CHANNEL) {
+        k8 = dp.scale == 0.f ? 0u
+                             : philox_keep8(dp.seed, dp.stream_id, dp.sample0 + s, ((uint64_t)b * F + f0) >> 3, dp.thr);
+        fac *= dp.scale;
+      }
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j] = ((k8 >> j) & 1u) ? a[j] * fac : 0.f;
+        if (dp.kind == BNN_DROP_MASKSEMBLES) x[j] *= drop_factor(dp, (uint32_t)s, 0, 0, f0 + j);
+      }
+      const float* wp = w_s + (f0 >> 3) * 4;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wp + c * F);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + c * F + half);
+          float t = acc[c];
+          t = fmaf(x[0], w0.x, t);
+          t = fmaf(x[1], w0.y, t);
+          t = fmaf(x[2], w0.z, t);
+          t = fmaf(x[3], w0.w, t);
+          t = fmaf(x[4], w1.x, t);
+          t = fmaf(x[5], w1.y, t);
+          t = fmaf(x[6], w1.z, t);
+          t = fmaf(x[7], w1.w, t);
+          acc[c] = t;
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        const float t = warp_sum(acc[c]);
+        if (lane == c) mine = t;
+      }
+    if (lane < C) logits[(size_t)row * pitch + lane] = mine + __ldg(bias + lane);
+  }
+}
+
 // dynamic shared memory layout (floats):
 //   pooled[F][HEAD_SCHUNK] | part[HEAD_THREADS * HEAD_SCHUNK * (C > 32 ? 4 : 1)] | logits[HEAD_SCHUNK][C] | acc_p[C] | acc_l[C] |
 //   red[HEAD_WARPS] | smax[HEAD_SCHUNK] | sinv[HEAD_SCHUNK]
@@ -654,6 +733,62 @@ int bnn_exit_head_tc(const void* feat, int dtype, int feat_has_samples, int B, i
   }
   return exit_head_run(nullptr, BNN_F32, 1, B, S_local, 1, F, C, nullptr, bias_pad, nullptr, sum_p, sum_logit, sum_plogp,
                        logits_out, accumulate, stream, nullptr, nullptr, 1.f, logits_ws, c_pad);
+}
+
+int bnn_exit_head_rows(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                       const float* w_cf, const float* bias, const bnn_drop_desc* drop, float* logits_ws, float* sum_p,
+                       float* sum_logit, float* sum_plogp, float* logits_out, int accumulate, void* stream) {
+  if (int rc = check_device()) return rc;
+  BNN_REQUIRE(feat && w_cf && bias && logits_ws && sum_p && sum_logit && sum_plogp, "bnn_exit_head_rows: null pointer");
+  BNN_REQUIRE(dtype == BNN_F16 || dtype == BNN_BF16 || dtype == BNN_F32, "bnn_exit_head_rows: float16 / bfloat16 / float32 features");
+  BNN_REQUIRE(B >= 0 && S_local >= 0 && HW > 0 && F > 0 && F % 8 == 0 && C > 0 && C <= 32,
+              "bnn_exit_head_rows: bad geometry (F=%d must be a multiple of 8, C=%d at most 32)", F, C);
+  const size_t smem = (size_t)C * F * sizeof(float);
+  BNN_REQUIRE(smem <= 200 * 1024, "bnn_exit_head_rows: F=%d x C=%d weights do not fit shared memory", F, C);
+  if (drop && drop->kind != BNN_DROP_NONE) {
+    BNN_REQUIRE(drop->p >= 0.f && drop->p <= 1.f, "dropout probability has to be between 0 and 1, but got %g", drop->p);
+    BNN_REQUIRE(drop->kind != BNN_DROP_MASKSEMBLES || (drop->masks && drop->n_masks > 0),
+                "bnn_exit_head_rows: Masksembles site without a mask table");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0 || S_local == 0) {
+    if (B > 0 && !accumulate) {
+      BNN_CUDA_OK(cudaMemsetAsync(sum_p, 0, sizeof(float) * (size_t)B * C, st));
+      BNN_CUDA_OK(cudaMemsetAsync(sum_logit, 0, sizeof(float) * (size_t)B * C, st));
+      BNN_CUDA_OK(cudaMemsetAsync(sum_plogp, 0, sizeof(float) * (size_t)B, st));
+    }
+    return BNN_OK;
+  }
+  DropParams dp = make_drop_params(drop, F);
+  dp.batch = B;
+  const int64_t rows = (int64_t)S_local * B;
+  // two CTAs per SM at most; every CTA fills its copy of the weights once and walks >= 8 rows per warp pass
+  const int64_t max_grid = 2 * (int64_t)sm_count();
+  int64_t grid = (rows + 7) / 8;
+  if (grid > max_grid) grid = max_grid;
+  const int rows_per_cta = (int)(((rows + grid - 1) / grid + 7) / 8 * 8);
+  grid = (rows + rows_per_cta - 1) / rows_per_cta;
+#define BNN_ROWS_LAUNCH(T, CM)                                                                                         \
+  do {                                                                                                                 \
+    BNN_CUDA_OK(cudaFuncSetAttribute(head_rows_kernel<T, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    head_rows_kernel<T, CM><<<(unsigned)grid, 256, smem, st>>>((const T*)feat, feat_has_samples, B, S_local, HW, F, C,  \
+                                                                w_cf, bias, dp, logits_ws, C, rows_per_cta, 1.f);       \
+  } while (0)
+#define BNN_ROWS_LAUNCH_T(T)           \
+  do {                                 \
+    if (C <= 16) BNN_ROWS_LAUNCH(T, 16); \
+    else BNN_ROWS_LAUNCH(T, 32);       \
+  } while (0)
+  if (dtype == BNN_F16) BNN_ROWS_LAUNCH_T(__half);
+  else if (dtype == BNN_BF16) BNN_ROWS_LAUNCH_T(__nv_bfloat16);
+  else BNN_ROWS_LAUNCH_T(float);
+#undef BNN_ROWS_LAUNCH_T
+#undef BNN_ROWS_LAUNCH
+  BNN_LAUNCH_OK();
+  head_softmax_warp_kernel<1><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, C, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out,
+                                                           accumulate);
+  BNN_LAUNCH_OK();
+  return BNN_OK;
 }
 
 int bnn_exit_head_q8(const void* feat_q, float feat_scale, int feat_has_samples, int B, int S_local, int HW, int F, int C,

@@ -481,6 +481,14 @@ class Engine:
                 op.head_tc = (self.dtype_name != "fp32" and self.use_tc and F_ % 64 == 0 and
                               C_ >= int(os.environ.get("BNN_HEAD_TC_MIN_C", "33")) and
                               os.environ.get("BNN_HEAD_TC", "1") != "0")
+                # narrow heads: one warp per (sample, image) row + the sample-ordered soft-max kernel (bnn_exit_head_rows);
+                # the block-per-image kernel is a 50-us latency chain per exit whatever the size
+                # (measured at C2 / C5, ncu: 30 vs 34 us at S = 32, 87 vs 127 us at S = 128 for a pooled 512-feature head; an
+                # un-pooled 4x4 map is SLOWER this way - 0.116 vs 0.063 ms - so those stay on the block-per-image kernel)
+                op.head_rows = (not op.head_tc and C_ <= 32 and F_ % 8 == 0 and C_ * F_ * 4 <= 200 * 1024 and
+                                op.src.H * op.src.W <= 4 and os.environ.get("BNN_HEAD_ROWS", "1") != "0")
+                if op.head_rows:
+                    op.d_w_cf = op.weight.contiguous().to(dev, torch.float32)       # [C][F], the nn.Linear layout
                 if op.head_mma or op.head_tc:
                     w32 = op.weight.contiguous().to(dev, torch.float32)             # [C][F], the nn.Linear layout
                     op.d_w_hi = torch.empty((C_, F_), dtype=self.tdtype, device=dev)
@@ -649,11 +657,13 @@ class Engine:
         E, C = g.n_exits, g.n_classes
         head_ws = None
         tc_heads = [o for o in g.ops if o.kind == "head" and getattr(o, "head_tc", False)]
-        if tc_heads:            # one workspace pair shared by all tensor-core heads (they run back to back on the stream)
+        row_heads = [o for o in g.ops if o.kind == "head" and getattr(o, "head_rows", False)]
+        if tc_heads or row_heads:   # one workspace pair shared by all heads that use it (they run back to back on the stream)
             rows = chunk * B
-            head_ws = (torch.empty(rows * max((2 if o.head_with_lo else 1) * o.src.C for o in tc_heads), dtype=self.tdtype,
-                                   device=dev),
-                       torch.empty(rows * max(o.c_pad for o in tc_heads), dtype=torch.float32, device=dev))
+            a_ws = (torch.empty(rows * max((2 if o.head_with_lo else 1) * o.src.C for o in tc_heads), dtype=self.tdtype,
+                                device=dev) if tc_heads else None)
+            head_ws = (a_ws, torch.empty(rows * max([o.c_pad for o in tc_heads] + [C for _ in row_heads]),
+                                         dtype=torch.float32, device=dev))
         st = {
             "x": torch.empty(((chunk if g.input.stoch else 1) * B, g.input.C, g.input.H, g.input.W), dtype=torch.float32,
                              device=dev),
@@ -951,6 +961,12 @@ class Engine:
                         _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
                         _ptr(op.d_w3), _ptr(op.d_b_pad), op.c_pad, op.head_with_lo, ctypes.byref(dd), _ptr(a_ws), _ptr(l_ws),
                         _ptr(sum_p[e]), _ptr(sum_l[e]), _ptr(sum_pl[e]), _ptr(lo_e), int(accumulate), stream)
+                elif getattr(op, "head_rows", False) and S_local > 0:
+                    l_ws = st["head_ws"][1]
+                    call = lambda: lib.bnn_exit_head_rows(
+                        _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
+                        _ptr(op.d_w_cf), _ptr(op.d_b), ctypes.byref(dd), _ptr(l_ws), _ptr(sum_p[e]), _ptr(sum_l[e]),
+                        _ptr(sum_pl[e]), _ptr(lo_e), int(accumulate), stream)
                 elif op.head_mma:
                     call = lambda: lib.bnn_exit_head_mma(
                         _ptr(acts[op.src.id]), self.dcode, int(op.src.stoch), B, S_local, hw, op.src.C, g.n_classes,
@@ -964,6 +980,8 @@ class Engine:
                 self._launch("exit_head", op.name, flops, nbytes, call)
                 if getattr(op, "head_tc", False) and S_local > 0:
                     self.launches += 2            # features + tcgen05 GEMM + soft-max / accumulate: three kernels
+                elif getattr(op, "head_rows", False) and S_local > 0:
+                    self.launches += 1            # logits rows + soft-max / accumulate: two kernels
 
     def profile_step(self, x, S_local, seed=0x5EED):
         """Device time of every launch of one step (CUDA events on the launching stream).

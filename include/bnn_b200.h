@@ -325,6 +325,14 @@ int bnn_top_label(const double* probs, const int32_t* labels, int N, int C, int 
 int bnn_kde_triweight(const double* data, const int32_t* flags, int n, double bw, double n_points, double x0,
                       double dx, int G, double lo, double hi, double* out, void* stream);
 
+/* Narrow exit heads (C <= 32) with all samples in parallel (same contract as bnn_exit_head; replaces the same reference
+ * code: resnet18.py:309-314 + results_analyzer.py:242-248): one warp per (sample, image) row computes the logits
+ * (pool -> site -> Linear in fp32; w_cf = the nn.Linear weight [C][F] float32) into logits_ws [S_local * B][C] float32,
+ * then one CTA per image runs the soft-max and adds the samples in order (deterministic).  F % 8 == 0. */
+int bnn_exit_head_rows(const void* feat, int dtype, int feat_has_samples, int B, int S_local, int HW, int F, int C,
+                       const float* w_cf, const float* bias, const bnn_drop_desc* drop, float* logits_ws, float* sum_p,
+                       float* sum_logit, float* sum_plogp, float* logits_out, int accumulate, void* stream);
+
 /* ---- the path's one collective as a kernel over NVLink peer memory (sample sharding) ----
  * The reference is single-device; sharding its S passes over the GPUs of a box leaves one exchange: the sum of the
  * per-exit statistics sums (what `np.average(all_output_probs, axis=0)` / `all_outputs` run over, results_analyzer.py:

@@ -863,3 +863,48 @@ def test_conv_tc_narrow_input_one_kstep_per_tap(lib, Cin, Cout, HW):
     err = (got.double() - want).abs().max().item()
     report(test="conv_tc_narrow_input", Cin=Cin, Cout=Cout, err=err)
     assert err <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("dt,C,F_,HW,kind,p,S,B,has_samples", [
+    ("fp16", 10, 512, 1, 1, 0.5, 32, 40, 1), ("fp16", 10, 512, 16, 2, 0.25, 5, 7, 1), ("bf16", 32, 256, 4, 3, 0.0, 6, 9, 1),
+    ("fp32", 17, 264, 1, 1, 0.125, 9, 33, 1), ("fp16", 10, 512, 1, 0, 0.0, 3, 300, 1), ("fp16", 10, 64, 4, 1, 0.5, 4, 6, 0)])
+def test_exit_head_rows_matches_block_per_image_head(lib, dt, C, F_, HW, kind, p, S, B, has_samples):
+    """bnn_exit_head_rows (one warp per (sample, image) row, then the sample-ordered soft-max kernel) == bnn_exit_head on the
+    same features: element / channel dropout, Masksembles rows, no site, pooled and un-pooled maps, features shared by the
+    samples, fp32 / fp16 / bf16 storage, ragged row counts; the sums start from the accumulate flag."""
+    tdt, code = TORCH_DT[dt]
+    s0, seed, sid = 3, 0x99, 2
+    g = torch.Generator().manual_seed(C + S + B)
+    feat = (torch.randn((S if has_samples else 1) * B, HW, F_, generator=g).abs() * 3).to(tdt).cuda()
+    w = (torch.randn(C, F_, generator=g) / np.sqrt(F_) * 3).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    masks = (torch.rand(4, F_, generator=g) > 0.5).float().cuda()
+    dd = drop_desc(kind, p, seed, sid, s0, B, masks if kind == 3 else None, cnt0=1)
+    l_ws = torch.empty(S * B * C, device="cuda")
+    outs = {}
+    for name in ("block", "rows"):
+        o = dict(sp=torch.full((B, C), 0.5).cuda(), sl=torch.full((B, C), -1.0).cuda(), spl=torch.full((B,), 2.0).cuda(),
+                 lo=torch.zeros(S, B, C).cuda())
+        for acc in (0, 1):                          # second call accumulates on top of the first
+            if name == "block":
+                wt = w.t().contiguous()
+                rc = lib.bnn_exit_head(feat.data_ptr(), code, has_samples, B, S, HW, F_, C, wt.data_ptr(), bias.data_ptr(),
+                                       ctypes.byref(dd), o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(),
+                                       o["lo"].data_ptr(), acc, stream())
+            else:
+                rc = lib.bnn_exit_head_rows(feat.data_ptr(), code, has_samples, B, S, HW, F_, C, w.data_ptr(), bias.data_ptr(),
+                                            ctypes.byref(dd), l_ws.data_ptr(), o["sp"].data_ptr(), o["sl"].data_ptr(),
+                                            o["spl"].data_ptr(), o["lo"].data_ptr(), acc, stream())
+            assert rc == 0, lib.bnn_last_error()
+        torch.cuda.synchronize()
+        outs[name] = o
+    scale = max(1.0, outs["block"]["lo"].abs().max().item())
+    e_lo = (outs["rows"]["lo"] - outs["block"]["lo"]).abs().max().item()
+    e_p = (outs["rows"]["sp"] - outs["block"]["sp"]).abs().max().item()
+    e_l = (outs["rows"]["sl"] - outs["block"]["sl"]).abs().max().item()
+    e_pl = (outs["rows"]["spl"] - outs["block"]["spl"]).abs().max().item()
+    report(test="exit_head_rows", dtype=dt, C=C, F=F_, HW=HW, kind=kind, err_logits=e_lo, err_sum_p=e_p, scale=scale)
+    assert e_lo <= 2e-5 * scale and e_p <= 2e-5 * S and e_l <= 4e-5 * S * scale and e_pl <= 2e-4 * S
+    assert lib.bnn_exit_head_rows(feat.data_ptr(), code, has_samples, B, S, HW, F_, 33, w.data_ptr(), bias.data_ptr(),
+                                  ctypes.byref(dd), l_ws.data_ptr(), o["sp"].data_ptr(), o["sl"].data_ptr(), o["spl"].data_ptr(),
+                                  None, 0, stream()) == -1          # wide heads go to bnn_exit_head_tc / bnn_exit_head_mma
