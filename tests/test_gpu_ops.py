@@ -797,7 +797,8 @@ def test_conv_tc_vertical_halo_form(lib, N, Cin, res, drop_kind, monkeypatch):
 @pytest.mark.parametrize("pair", ["single", "cg2"])
 @pytest.mark.parametrize("shape,drop_kind", [((300, 4, 4, 512, 512, 3, 1, 1, True, True), 0), ((260, 8, 8, 256, 256, 3, 1, 1, True, False), 1),
                                              ((257, 8, 8, 256, 512, 3, 2, 1, True, False), 0), ((130, 2, 2, 512, 512, 3, 1, 1, True, False), 2),
-                                             ((200, 4, 4, 256, 256, 3, 2, 1, False, False), 0)])
+                                             ((200, 4, 4, 256, 256, 3, 2, 1, False, False), 0),
+                                             ((150, 2, 8, 256, 256, 3, 1, 1, True, True), 0), ((131, 8, 4, 256, 512, 3, 1, 1, True, False), 1)])
 def test_conv_tc_position_major_tiles_skip_padding_taps(lib, shape, drop_kind, pair, monkeypatch):
     """Position-major tiling (one output position x 128 images per row-tile): taps that read only zero padding are not
     issued.  Skipped terms are exact zeros, so the result must be BIT-IDENTICAL to the pixel-major kernel - plain and
