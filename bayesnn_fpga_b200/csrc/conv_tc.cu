@@ -112,6 +112,7 @@ struct Params {
   // (rw_stages deep).  With the weights re-fetched per k-block a CTA ingests 32 KB per 512-cycle k-block = 64 B/clk, the
   // L2 -> SM ceiling, and the issuer waited for operands half of the time (profiles/r02_ncu_epilogue_bound.txt).
   int rw_kb, rw_stages;
+  int l2pf;        // sibling-pair kernel, stride 2: L2-prefetch the pixel boxes of the tile `l2pf` rounds ahead (0 = off)
   int pm_nb2;      // > 0: position-major tiling
   int n_img;       // images (M / OHW)
   int head_c;      // > 0: channel blocks of x_hi
@@ -303,6 +304,12 @@ __device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* ma
       "%5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+// bring a box into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
@@ -749,6 +756,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           pm_decode(m_tile, p.OHW, pos, img0[0]);     // image blocks past the end: the TMA unit zero-fills
           oh0[0] = pos / p.OW;
           pm_ow = pos - oh0[0] * p.OW;
+        }
+        if constexpr (SCG2 && !MASKED) {
+          if (p.l2pf > 0 && p.stride == 2 && tile + p.l2pf * sched_n < p.num_tiles) {
+            // the DRAM round trip of a later tile's pixels starts now: its TMA loads then hit L2
+            const int t2 = tile + p.l2pf * sched_n, mu2 = t2 / p.n_tiles_n;
+            int m2 = (mu2 * MT + (int)cta_rank) * BM;
+            if (m2 >= p.M) m2 = 0;
+            int i2 = m2 / p.OHW;
+            const int o2 = (m2 - i2 * p.OHW) / p.OW;
+            if (p.a_img_mod > 0) i2 %= p.a_img_mod;
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const int rh = tap / 3 - p.pad, rw = tap - (tap / 3) * 3 - p.pad;
+              const int hp = rh & 1, dh = (rh - hp) >> 1, wp = rw & 1, dw = (rw - wp) >> 1;
+              for (int cb = 0; cb < p.cblocks; ++cb) tma_prefetch_5d(&tmap_a, wp * p.Cin + cb * BKE, dw, hp, o2 + dh, i2);
+            }
+          }
         }
         // SCG2: n_tile counts group PAIRS; this CTA's output group (and weight rows) is 2 * n_tile + rank
         const int grp_w = SCG2 ? 2 * n_tile + (int)cta_rank : n_tile;
@@ -1665,6 +1688,7 @@ static int conv_tc_run(const char* who, const void* x, const void* w, const floa
     p.a_img_mod = gsel->x_has_samples ? 0 : gsel->batch;
   }
   p.exp_flags = getenv("BNN_TC_EXP") ? atoi(getenv("BNN_TC_EXP")) : 0;
+  p.l2pf = getenv("BNN_TC_L2PF") ? atoi(getenv("BNN_TC_L2PF")) : 0;
   p.wait_ns_prod = p.wait_ns_epi = p.wait_ns_acc = p.wait_ns_full = 0;      // measured neutral (tools/exp_wait.py): off
   if (const char* e = getenv("BNN_TC_WAIT_NS")) {
     unsigned a = 0, b = 0, c = 0, d = 0;

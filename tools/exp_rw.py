@@ -26,7 +26,8 @@ def timed(iters=20):
     return e0.elapsed_time(e1) / iters
 
 
-variants = [("resident weights", {}), ("weights per k-block", {"BNN_TC_NO_RW": "1"}), ("one CTA per (tile, group)", {"BNN_TC_NO_SCG2": "1"})]
+variants = [("resident weights", {}), ("resident + L2 prefetch 1 ahead", {"BNN_TC_L2PF": "1"}), ("resident + L2 prefetch 2 ahead", {"BNN_TC_L2PF": "2"}),
+            ("per k-block + L2 prefetch 1 ahead", {"BNN_TC_NO_RW": "1", "BNN_TC_L2PF": "1"}), ("weights per k-block", {"BNN_TC_NO_RW": "1"}), ("one CTA per (tile, group)", {"BNN_TC_NO_SCG2": "1"})]
 best, ref = {}, {}
 for rnd in range(8):
     for name, env in variants:
