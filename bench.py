@@ -179,7 +179,7 @@ def reference_arm(args, wl_name):
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": impl, "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -329,7 +329,29 @@ def summarize_profile(prof, peaks, clocks, region_s, with_traffic):
     return roof, kernels
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 when the
+    box sets NCCL_DEBUG), so the real stdout is kept aside for the result line and fd 1 is pointed at stderr for
+    everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -356,7 +378,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     peaks = load_peaks()
@@ -576,7 +597,7 @@ def main():
             line["configs"] = extras
         if c5_strong is not None:
             line["c5_strong"] = c5_strong
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -475,3 +475,17 @@ def test_q8_quantizers_follow_qkeras_definitions():
     assert so == step and qo.tolist() == q.tolist()
     q, step = q8.quantized_bits(x, 8, 2)                     # ibit = 2: range [-4, 4), step 2^-5
     assert step == 2.0 ** -5 and q.tolist()[0] == -64 and q.tolist()[-1] == 96
+
+
+def test_bench_keeps_stdout_for_the_one_json_line():
+    """bench.py's contract is ONE JSON line on stdout; whatever else writes to fd 1 (NCCL's version banner, stray prints)
+    is sent to stderr once bench.claim_stdout() ran."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import bench, os; bench.claim_stdout(); os.write(1, b'NCCL version 2.x\\n'); print('chatter', flush=True); "
+            "bench.emit({'ok': 1})")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, cwd=root, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout == b'{"ok": 1}\n'
+    assert b"NCCL version" in r.stderr and b"chatter" in r.stderr
