@@ -567,12 +567,15 @@ def main():
             "metric": METRIC, "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if shard_samples else "weak", "vs_baseline": None,
-            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " operands, f32 accumulate",
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype],
             "data": "synthetic",
             "config": {"workload": head["workload"] if not (args.batch or args.samples) else
                        head["workload"] + " [overridden B=%d S=%d]" % (head["batch_per_gpu"], head["S"]),
                        "batch_per_gpu": head["batch_per_gpu"], "global_batch": head["global_batch"], "S": head["S"],
                        "exits": head["exits"], "classes": head["classes"], "partition": head["partition"],
+                       "arithmetic": ("%s operands, f32 accumulate (tcgen05.mma kind::f16), f32 statistics" %
+                                      {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype]
+                                      if args.dtype != "fp32" else "f32 CUDA-core kernels, f32 statistics"),
                        "l2": "per-step activation working set (GiB) >> 126 MB L2; no explicit flush",
                        "cuda_graph": os.environ.get("BNN_CUDA_GRAPH", "1") != "0",
                        "collective_inside_cuda_graph": head.get("collective_in_graph"),
