@@ -10,8 +10,8 @@ mean / entropy statistics.  The HEADLINE (`value`, `e2e`, `roofline`) is BASELIN
 MC dropout after every stage + at every exit, S = 32, B = 256, 3x32x32).  The same JSON line carries, each measured in
 its own short timed region with its own clock sample:
   * N = 1:  `configs` = {c1, c3, c4, c5} (LeNet S=8; Masksembles S=4 C=100; VGG-19 S=64 B=512; ResNet S=128 on one GPU)
-  * N > 1:  the headline is C2 weak-scaled (every rank its own B images; one `all_gather_into_tensor` of the
-            statistics inside the timed region) and `c5_strong` = BASELINE configs[4]: the S = 128 samples of ONE batch
+  * N > 1:  the headline is C2 weak-scaled (every rank its own B images: independent batches, NO data-path collective;
+            BNN_BENCH_WEAK_GATHER=1 adds an `all_gather_into_tensor` of the statistics to every step) and `c5_strong` = BASELINE configs[4]: the S = 128 samples of ONE batch
             sharded over the ranks with a single all-reduce of the per-exit sums (strong scaling), with the unsharded
             single-GPU time measured in the same process for `efficiency_vs_n1`.
 `--workload cX` makes cX the headline instead (debugging / profiling).
@@ -329,6 +329,7 @@ def summarize_profile(prof, peaks, clocks, region_s, with_traffic):
     return roof, kernels
 
 
+WEAK_GATHER = os.environ.get("BNN_BENCH_WEAK_GATHER") == "1"
 _RESULT_OUT = None
 
 
@@ -434,8 +435,9 @@ def main():
             """inputs already resident in HBM"""
             if shard == "samples":
                 return eng.run(x_dev, sl, sample0=s0, S_total=S, reduce_fn=predict.allreduce_sums)
-            # batch sharding: ONE NCCL collective right behind the finaliser, captured inside the step's CUDA graph
-            return eng.run(x_dev, S, gather_fn=gather if shard == "batch" else None)
+            # batch sharding: the ranks' batches are independent - nothing is exchanged (optionally ONE NCCL all-gather
+            # right behind the finaliser, captured inside the step's CUDA graph)
+            return eng.run(x_dev, S, gather_fn=gather if (shard == "batch" and WEAK_GATHER) else None)
 
         out_host = torch.empty((4, E, B, classes), dtype=torch.float32).pin_memory()
 
@@ -465,7 +467,8 @@ def main():
                "e2e": {"value": images * steps / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e / steps,
                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
                "gpu_launches": launches, "clocks": clocks,
-               "collective_in_graph": bool(eng._graph_collectives) if shard else None}
+               "collective_in_graph": (bool(eng._graph_collectives) if (shard == "samples" or (shard and WEAK_GATHER))
+                                       else None)}
         prof = eng.profile_step(x_dev, sl)
         roof, kernels = summarize_profile(prof, peaks, clocks, ms * 1e-3, with_traffic=(wl_name == "c2"))
         pre_macs, suf_macs = eng.graph.macs()
@@ -581,7 +584,8 @@ def main():
                        "collective_inside_cuda_graph": head.get("collective_in_graph"),
                        "collective": (None if world == 1 else
                                       "all_reduce(sum) of the per-exit sums before the finaliser" if shard_samples else
-                                      "all_gather_into_tensor of the finished statistics, on the compute stream"),
+                                      ("all_gather_into_tensor of the finished statistics, on the compute stream"
+                                       if WEAK_GATHER else "none: every rank owns its batch (independent replicas)")),
                        "algorithmic_gflop_per_image": head["algorithmic_gflop_per_image"]},
             "tflops_whole_step": head["tflops_whole_step"],
             "frac_of_tensor_peak_whole_step": head["frac_of_tensor_peak_whole_step"],
