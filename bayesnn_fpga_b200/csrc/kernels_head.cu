@@ -237,12 +237,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) head_prep_kernel(const T* __restrict__ feat, int feat_has_samples, int B, int S_local,
                                                         int HW, int F, DropParams dp, T* __restrict__ a, int a_pitch,
                                                         int with_lo) {
-  const int octs = F / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)S_local * B * octs) return;
-  const int f0 = (int)(idx % octs) * 8;
-  const int64_t row = idx / octs;                        // s * B + b
-  const int b = (int)(row % B), s = (int)(row / B);
+  // 32-bit index arithmetic (the launcher checks S_local * B * F / 8 < 2^31): three 64-bit divisions per thread cost more
+  // than the Philox block of this one-octet-per-thread kernel
+  const uint32_t octs = (uint32_t)F / 8u;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint32_t)S_local * (uint32_t)B * octs) return;
+  const uint32_t row = idx / octs;                       // s * B + b
+  const int f0 = (int)(idx - row * octs) * 8;
+  const int s = (int)(row / (uint32_t)B), b = (int)(row - (uint32_t)s * (uint32_t)B);
   const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F + f0;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int p = 0; p < HW; ++p) {
@@ -273,8 +275,10 @@ __global__ void __launch_bounds__(256) head_prep_kernel(const T* __restrict__ fe
 // order and the per-warp partial sums are combined in a fixed order (deterministic).  No barriers inside the sample
 // loop - the block-per-image chunked form of exit_head_kernel spent ~7 us per 16-sample chunk in barriers and dependent
 // loads (83 us per C4 head), a single warp per image 49 us in its own dependent shuffle / expf chain.
-constexpr int SM_WARPS = 8;
-template <int NPL>
+// warps per image: 16 for up to 128 classes (S = 32 ... 128 samples: two to eight rows per warp), 8 beyond (the per-warp
+// partial sums live in static shared memory)
+constexpr int SMW_NARROW = 16;
+template <int NPL, int SM_WARPS>
 __global__ void __launch_bounds__(SM_WARPS * 32) head_softmax_warp_kernel(
     const float* __restrict__ logits_in, int pitch, int B, int S_local, int C, float* __restrict__ sum_p,
     float* __restrict__ sum_logit, float* __restrict__ sum_plogp, float* __restrict__ logits_out, int accumulate) {
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ fe
   const int64_t r_end = min(rows, ((int64_t)blockIdx.x + 1) * rows_per_cta);
   const float inv_hw = feat_scale / (float)HW;
   for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + warp; row < r_end; row += 8) {
-    const int s = (int)(row / B), b = (int)(row - (int64_t)s * B);
+    const int s = (int)((uint32_t)row / (uint32_t)B), b = (int)((uint32_t)row - (uint32_t)s * (uint32_t)B);   // rows < 2^31 (launcher)
     const T* src = feat + (((size_t)(feat_has_samples ? s : 0) * B + b) * HW) * F;
     float acc[CMAX];
 #pragma unroll
@@ -706,6 +710,7 @@ int bnn_exit_head_tc(const void* feat, int dtype, int feat_has_samples, int B, i
   dp.batch = B;
   const int a_pitch = with_lo ? 2 * F : F;
   const int64_t items = (int64_t)S_local * B * (F / 8);
+  BNN_REQUIRE(items < (int64_t)1 << 31, "bnn_exit_head_tc: S_local * B * F / 8 = %lld exceeds 32-bit indexing", (long long)items);
   const int M = S_local * B;
   // 1. features: pool -> site -> hi [| lo]     2. logits = [x_hi | x_lo] x [w_hi | w_lo | w_hi]^T on tcgen05 (fp32 out)
   if (dtype == BNN_F16)
@@ -723,11 +728,11 @@ int bnn_exit_head_tc(const void* feat, int dtype, int feat_has_samples, int B, i
   if (C <= 512) {
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 32)
-      head_softmax_warp_kernel<1><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+      head_softmax_warp_kernel<1, SMW_NARROW><<<B, SMW_NARROW * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
     else if (C <= 128)
-      head_softmax_warp_kernel<4><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+      head_softmax_warp_kernel<4, SMW_NARROW><<<B, SMW_NARROW * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
     else
-      head_softmax_warp_kernel<16><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
+      head_softmax_warp_kernel<16, 8><<<B, 8 * 32, 0, st>>>(logits_ws, c_pad, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out, accumulate);
     BNN_LAUNCH_OK();
     return BNN_OK;
   }
@@ -762,6 +767,7 @@ int bnn_exit_head_rows(const void* feat, int dtype, int feat_has_samples, int B,
   DropParams dp = make_drop_params(drop, F);
   dp.batch = B;
   const int64_t rows = (int64_t)S_local * B;
+  BNN_REQUIRE(rows < (int64_t)1 << 31, "bnn_exit_head_rows: S_local * B = %lld exceeds 32-bit indexing", (long long)rows);
   // two CTAs per SM at most; every CTA fills its copy of the weights once and walks >= 8 rows per warp pass
   const int64_t max_grid = 2 * (int64_t)sm_count();
   int64_t grid = (rows + 7) / 8;
@@ -785,7 +791,7 @@ int bnn_exit_head_rows(const void* feat, int dtype, int feat_has_samples, int B,
 #undef BNN_ROWS_LAUNCH_T
 #undef BNN_ROWS_LAUNCH
   BNN_LAUNCH_OK();
-  head_softmax_warp_kernel<1><<<B, SM_WARPS * 32, 0, st>>>(logits_ws, C, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out,
+  head_softmax_warp_kernel<1, SMW_NARROW><<<B, SMW_NARROW * 32, 0, st>>>(logits_ws, C, B, S_local, C, sum_p, sum_logit, sum_plogp, logits_out,
                                                            accumulate);
   BNN_LAUNCH_OK();
   return BNN_OK;
