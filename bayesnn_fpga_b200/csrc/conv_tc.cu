@@ -20,6 +20,17 @@
 //             in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2.. : epilogue - tcgen05.ld 32 lanes x 32 columns -> + folded-BN bias -> + residual -> ReLU ->
 //             Philox dropout / Masksembles mask -> 16-bit pack -> 64-byte row stores
+//
+// Variants of the one kernel template (picked per launch from the geometry by conv_tc_run):
+//   PAIR = 2 (CG2)  cta_group::2 - one 256-row MMA over a CTA pair, each CTA holds half of the weight k-block
+//   SWAP            Cout = 128: weights are the MMA's A operand (M = 128 channels), 256 pixels its N; transposed epilogue
+//   VH              SWAP on 16 x 16 maps: one haloed pixel tile serves the three vertical taps (two rings, two producers)
+//   SWAP + PAIR = 2 sibling pair: two 128-channel groups over the same pixels on one CTA pair; Params::rw_kb keeps the
+//                   group's whole weight matrix resident in shared memory (K <= 9 k-blocks)
+//   Params::pm_nb2  position-major row tiles on 2x2 .. 8x8 maps: taps that read only zero padding are not issued
+//   T = int8_t      u8 x s8 -> int32 (kind::i8) with a requantising epilogue
+//   fused shortcut (cblocks2), fused head pool (pool_hw), grouped outputs, Masksembles gathered K / per-mask weights,
+//   head-GEMM mode (head_c), in-kernel keep-bit masking (MASKED, opt-in)
 #include <cuda.h>
 #include <stdlib.h>
 
