@@ -489,3 +489,21 @@ def test_bench_keeps_stdout_for_the_one_json_line():
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     assert r.stdout == b'{"ok": 1}\n'
     assert b"NCCL version" in r.stderr and b"chatter" in r.stderr
+
+
+def test_position_major_tap_fraction_mirrors_the_kernel_rule(monkeypatch):
+    """engine._pm_tap_fraction (EXECUTED / algorithmic multiply-adds under position-major tiling, what bench.py's
+    roofline counts) follows conv_tc.cu's host rule: 3x3 kernels, 2x2 .. 8x8 output maps, 256-channel tiles, >= 1024
+    images, and only where at least a tenth of the taps vanish."""
+    from bayesnn_fpga_b200.engine import _pm_tap_fraction as frac
+    monkeypatch.delenv("BNN_TC_NO_PM", raising=False)
+    monkeypatch.delenv("BNN_TC_PM_MIN_IMAGES", raising=False)
+    assert frac(8192, 4, 4, 4, 4, 1, 512) == pytest.approx(25 / 36)
+    assert frac(8192, 8, 8, 8, 8, 1, 256) == pytest.approx(121 / 144)
+    assert frac(8192, 2, 2, 2, 2, 1, 512) == pytest.approx(16 / 36)
+    assert frac(8192, 8, 8, 4, 4, 2, 512) == pytest.approx(121 / 144)          # stride 2, 8x8 -> 4x4: 11 of 12 per axis
+    assert frac(8192, 16, 16, 8, 8, 2, 256) == 1.0                              # saves 8 % only: pixel-major tiles
+    assert frac(8192, 16, 16, 16, 16, 1, 256) == 1.0 and frac(8192, 4, 4, 4, 4, 1, 128) == 1.0
+    assert frac(512, 4, 4, 4, 4, 1, 512) == 1.0                                 # below the batch threshold
+    monkeypatch.setenv("BNN_TC_NO_PM", "1")
+    assert frac(8192, 4, 4, 4, 4, 1, 512) == 1.0
