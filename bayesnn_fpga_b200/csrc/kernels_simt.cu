@@ -241,6 +241,23 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
       }
       const uint32_t thr2 = dp.thr | (dp.thr << 16);
       const uint64_t blk = (uint64_t)(v0 >> 3);
+      if (dp.thr == 0x8000u && dp.scale != 0.f) {
+        // p = 0.5 (the reference's default): "draw >= 2^15" is the top bit of each 16-bit draw, and PRMT in its
+        // sign-replicating mode (selector 0xbb99: bytes 1, 1, 3, 3 with the byte's msb copied to all eight bits) turns the
+        // two top bits of a word into the two halfword masks in ONE instruction - 8 instead of ~24 integer instructions
+        // per Philox block on the pipe that bounds this kernel.  Same bits as the general compare below.
+#pragma unroll 2
+        for (int s = 0; s < S_local; ++s) {
+          const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk);
+          uint4 m;
+          asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(m.x) : "r"(r.x));
+          asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(m.y) : "r"(r.y));
+          asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(m.z) : "r"(r.z));
+          asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(m.w) : "r"(r.w));
+          *reinterpret_cast<uint4*>(y + (int64_t)s * n_per + v0) = make_uint4(xs.x & m.x, xs.y & m.y, xs.z & m.z, xs.w & m.w);
+        }
+        return;
+      }
 #pragma unroll 2
       for (int s = 0; s < S_local; ++s) {
         const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk);
