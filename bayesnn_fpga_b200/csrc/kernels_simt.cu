@@ -229,6 +229,37 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   if (vec && !x_has_samples) in = *reinterpret_cast<const Vec8<T>*>(x + v0);   // broadcast source: read once
 
   if constexpr (sizeof(T) == 2) {
+    // 16-bit storage, element-wise dropout on a tensor that already has a sample dimension (sites deeper in the suffix,
+    // e.g. behind the max-pools of the VGG): the same mask arithmetic as the broadcast form below, input loaded and
+    // scaled per sample
+    if (vec && x_has_samples && dp.kind == BNN_DROP_ELEMENT && dp.scale != 0.f) {
+      const uint32_t thr2s = dp.thr | (dp.thr << 16);
+      const bool top_bit = dp.thr == 0x8000u;
+      const uint64_t blk = (uint64_t)(v0 >> 3);
+#pragma unroll 2
+      for (int s = 0; s < S_local; ++s) {
+        const Vec8<T> v = *reinterpret_cast<const Vec8<T>*>(x + (int64_t)s * n_per + v0);
+        Vec8<T> sc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sc.v[j] = from_f32<T>(to_f32<T>(v.v[j]) * dp.scale);
+        const uint4 xs = *reinterpret_cast<const uint4*>(&sc);
+        const uint4 r = philox_block(dp.seed, dp.stream_id, dp.sample0 + s, blk);
+        auto mask2 = [&](uint32_t rv) -> uint32_t {
+          uint32_t m;
+          if (top_bit) {
+            asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(m) : "r"(rv));
+          } else {
+            bool hi, lo;
+            __vibmax_u16x2(rv, thr2s, &hi, &lo);
+            m = (hi ? 0xffff0000u : 0u) | (lo ? 0x0000ffffu : 0u);
+          }
+          return m;
+        };
+        *reinterpret_cast<uint4*>(y + (int64_t)s * n_per + v0) =
+            make_uint4(xs.x & mask2(r.x), xs.y & mask2(r.y), xs.z & mask2(r.z), xs.w & mask2(r.w));
+      }
+      return;
+    }
     // 16-bit storage, element-wise dropout, prefix broadcast: scale once, then every sample is one Philox block,
     // four per-halfword compares (the 16-bit draws line up with the 16-bit elements) and four ANDs per 16 bytes
     if (vec && !x_has_samples && dp.kind == BNN_DROP_ELEMENT) {

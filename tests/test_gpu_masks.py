@@ -61,10 +61,13 @@ def test_dropout_p0_p1_and_empty():
 
 @pytest.mark.parametrize("dt", ["fp32", "fp16"])
 @pytest.mark.parametrize("has_samples", [0, 1])
-def test_prefix_broadcast_kernel(lib, dt, has_samples):
-    """bnn_dropout: y[s] = x[(s)] * mask_s, one launch for all local samples, global sample index."""
+@pytest.mark.parametrize("p", [0.5, 0.25])
+def test_prefix_broadcast_kernel(lib, dt, has_samples, p):
+    """bnn_dropout: y[s] = x[(s)] * mask_s, one launch for all local samples, global sample index.  p = 0.5 takes the
+    top-bit (PRMT) mask path of the 16-bit kernels, p = 0.25 the two-halfword compare; both with a broadcast source and with
+    a source that already has a sample dimension."""
     tdt, code = TORCH_DT[dt]
-    B, H, W, C, S, s0, p = 3, 5, 6, 16, 4, 10, 0.5
+    B, H, W, C, S, s0 = 3, 5, 6, 16, 4, 10
     torch.manual_seed(0)
     x = torch.randn((S if has_samples else 1) * B, H, W, C).to(tdt).cuda()
     y = torch.empty(S * B, H, W, C, dtype=tdt, device="cuda")
@@ -74,7 +77,7 @@ def test_prefix_broadcast_kernel(lib, dt, has_samples):
     xs = x.cpu().view(-1, B, H, W, C)
     for s in range(S):
         keep = philox.keep_mask(0xABC, 6, s0 + s, (B, C, H, W), p)            # NCHW view of the NHWC contract
-        want = (xs[s if has_samples else 0].float() * torch.from_numpy(keep).permute(0, 2, 3, 1) * 2.0).to(tdt)
+        want = (xs[s if has_samples else 0].float() * torch.from_numpy(keep).permute(0, 2, 3, 1) * (1.0 / (1.0 - p))).to(tdt)
         assert torch.equal(y[s], want)
 
 
