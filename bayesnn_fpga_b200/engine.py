@@ -328,6 +328,9 @@ class MCResult:
     expected_entropy: torch.Tensor  # [E, B]     mean over samples of per-sample entropy
     all_logits: Optional[torch.Tensor] = None   # [S_local, E, B, C] when requested
     samples: int = 0
+    # every statistic above in ONE contiguous device buffer - [4][E][B][C] (the four [E, B, C] tensors in the order of the
+    # fields) followed by [3][E][B] (the entropies): fetch it with a single device->host copy
+    flat: Optional[torch.Tensor] = None
 
 
 def _ptr(t):
@@ -1124,4 +1127,4 @@ class Engine:
         if want_logits:
             E, C = self.graph.n_exits, self.graph.n_classes
             all_logits = st["logits"].view(E, S, B, C).permute(1, 0, 2, 3)
-        return MCResult(views[0], views[1], views[2], views[3], ent[0], ent[1], ent[2], all_logits, S_total)
+        return MCResult(views[0], views[1], views[2], views[3], ent[0], ent[1], ent[2], all_logits, S_total, st["out"])
