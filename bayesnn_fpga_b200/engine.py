@@ -1060,12 +1060,15 @@ class Engine:
             return self._step(x.to(self.device, non_blocking=True), S, sample0, seed, want_logits, mask_offset, S_total,
                               reduce_fn, gather_fn)
         st["x"].copy_(x, non_blocking=True)
-        if x.device.type == "cpu" and x.is_pinned():
-            # the caller may reuse its pinned buffer as soon as this call returns: wait for the H2D copy (only)
+        pinned_src = x.device.type == "cpu" and x.is_pinned()
+        if pinned_src:
+            # the caller may reuse its pinned buffer as soon as this call returns: the H2D copy (only) is waited for -
+            # AFTER the graph has been launched behind it, so the device never sees the launch latency
             if self._h2d_done is None:
                 self._h2d_done = torch.cuda.Event()
             self._h2d_done.record()
-            self._h2d_done.synchronize()
+            if entry == "seen":
+                self._h2d_done.synchronize()          # the capture below must not start with a copy in flight
         rf, gf = (reduce_fn, gather_fn) if inside else (None, None)
         if entry == "seen":
             n0 = self.launches
@@ -1091,6 +1094,8 @@ class Engine:
             self.launches = n0
         g, n, out = entry
         g.replay()
+        if pinned_src:
+            self._h2d_done.synchronize()
         self.launches += n
         st, views, ent = out
         if not inside:
